@@ -1,0 +1,142 @@
+// capi.cu -- context, memory/stream helpers and element-wise conversion kernels.
+#include "common.cuh"
+
+thread_local std::string g_nsol_create_error;
+
+extern "C" int nsol_version(void) { return NSOL_B200_VERSION; }
+
+extern "C" int nsol_create(int device, nsol_ctx **out) {
+    if (!out) return nsol_fail(nullptr, NSOL_EINVAL, "nsol_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return nsol_fail(nullptr, NSOL_ECUDA,
+                         "nsol_create: no CUDA device (%s); libnsol_b200 has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0) {
+        e = cudaGetDevice(&device);
+        if (e != cudaSuccess) return nsol_fail(nullptr, NSOL_ECUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+    }
+    if (device >= count) return nsol_fail(nullptr, NSOL_EINVAL, "nsol_create: device %d out of range (%d devices)", device, count);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return nsol_fail(nullptr, NSOL_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return nsol_fail(nullptr, NSOL_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10)
+        return nsol_fail(nullptr, NSOL_ECUDA, "nsol_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                         device, prop.major, prop.minor);
+    nsol_ctx *ctx = new nsol_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    *out = ctx;
+    return NSOL_OK;
+}
+
+extern "C" void nsol_destroy(nsol_ctx *ctx) { delete ctx; }
+
+extern "C" const char *nsol_last_error(const nsol_ctx *ctx) {
+    return ctx ? ctx->err.c_str() : g_nsol_create_error.c_str();
+}
+
+extern "C" int nsol_set_tuning(nsol_ctx *ctx, const char *key, int value) {
+    if (!ctx || !key) return NSOL_EINVAL;
+    if (value < 0) value = 0;
+    if (!strcmp(key, "pd_zc")) ctx->pd_zc = value;
+    else if (!strcmp(key, "pd_ty")) ctx->pd_ty = value;
+    else if (!strcmp(key, "pd_variant")) ctx->pd_variant = value;
+    else if (!strcmp(key, "lsmr_blocks")) ctx->lsmr_blocks = value;
+    else return nsol_fail(ctx, NSOL_EINVAL, "nsol_set_tuning: unknown key '%s'", key);
+    return NSOL_OK;
+}
+
+extern "C" int64_t nsol_launch_count(const nsol_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int nsol_device_sm_count(const nsol_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+extern "C" int nsol_device_alloc(nsol_ctx *ctx, size_t bytes, void **dev) {
+    if (!ctx || !dev) return NSOL_EINVAL;
+    NSOL_CHECK(nsol_bind_device(ctx));
+    NSOL_CUDA(ctx, cudaMalloc(dev, bytes ? bytes : 1));
+    return NSOL_OK;
+}
+extern "C" int nsol_device_free(nsol_ctx *ctx, void *dev) {
+    if (!ctx) return NSOL_EINVAL;
+    NSOL_CHECK(nsol_bind_device(ctx));
+    NSOL_CUDA(ctx, cudaFree(dev));
+    return NSOL_OK;
+}
+extern "C" int nsol_host_alloc(nsol_ctx *ctx, size_t bytes, void **host) {
+    if (!ctx || !host) return NSOL_EINVAL;
+    NSOL_CHECK(nsol_bind_device(ctx));
+    NSOL_CUDA(ctx, cudaHostAlloc(host, bytes ? bytes : 1, cudaHostAllocDefault));
+    return NSOL_OK;
+}
+extern "C" int nsol_host_free(nsol_ctx *ctx, void *host) {
+    if (!ctx) return NSOL_EINVAL;
+    NSOL_CUDA(ctx, cudaFreeHost(host));
+    return NSOL_OK;
+}
+extern "C" int nsol_memcpy_h2d(nsol_ctx *ctx, void *dev, const void *host, size_t bytes, nsol_stream s) {
+    if (!ctx) return NSOL_EINVAL;
+    NSOL_CHECK(nsol_bind_device(ctx));
+    NSOL_CUDA(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)s));
+    return NSOL_OK;
+}
+extern "C" int nsol_memcpy_d2h(nsol_ctx *ctx, void *host, const void *dev, size_t bytes, nsol_stream s) {
+    if (!ctx) return NSOL_EINVAL;
+    NSOL_CHECK(nsol_bind_device(ctx));
+    NSOL_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)s));
+    return NSOL_OK;
+}
+extern "C" int nsol_memset_dev(nsol_ctx *ctx, void *dev, int value, size_t bytes, nsol_stream s) {
+    if (!ctx) return NSOL_EINVAL;
+    NSOL_CHECK(nsol_bind_device(ctx));
+    NSOL_CUDA(ctx, cudaMemsetAsync(dev, value, bytes, (cudaStream_t)s));
+    return NSOL_OK;
+}
+extern "C" int nsol_stream_sync(nsol_ctx *ctx, nsol_stream s) {
+    if (!ctx) return NSOL_EINVAL;
+    NSOL_CHECK(nsol_bind_device(ctx));
+    NSOL_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)s));
+    return NSOL_OK;
+}
+
+// out[i] = (TO)(in[i] * f)  or  (TO)(in[i] / f), evaluated in the wider of the two types
+template <typename TI, typename TO, bool DIV>
+__global__ void scale_convert_kernel(long long n, const TI *__restrict__ in, TO *__restrict__ out, double f) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        double v = (double)in[i];
+        v = DIV ? v / f : v * f;
+        out[i] = (TO)v;
+    }
+}
+
+template <typename TI, typename TO>
+static void launch_scale_convert(nsol_ctx *ctx, long long n, const void *in, void *out, double f, int divide, cudaStream_t s) {
+    int threads = 256;
+    long long want = (n + threads - 1) / threads;
+    int blocks = (int)(want < (long long)ctx->sm_count * 16 ? (want > 0 ? want : 1) : (long long)ctx->sm_count * 16);
+    if (divide)
+        scale_convert_kernel<TI, TO, true><<<blocks, threads, 0, s>>>(n, (const TI *)in, (TO *)out, f);
+    else
+        scale_convert_kernel<TI, TO, false><<<blocks, threads, 0, s>>>(n, (const TI *)in, (TO *)out, f);
+}
+
+extern "C" int nsol_scale_convert(nsol_ctx *ctx, int64_t n, int dtype_in, const void *in_dev, int dtype_out,
+                                  void *out_dev, double factor, int divide, nsol_stream s) {
+    if (!ctx) return NSOL_EINVAL;
+    if (n < 0 || !in_dev || !out_dev) return nsol_fail(ctx, NSOL_EINVAL, "nsol_scale_convert: bad arguments");
+    if (n == 0) return NSOL_OK;
+    NSOL_CHECK(nsol_bind_device(ctx));
+    cudaStream_t st = (cudaStream_t)s;
+    if (dtype_in == NSOL_F64 && dtype_out == NSOL_F64) launch_scale_convert<double, double>(ctx, n, in_dev, out_dev, factor, divide, st);
+    else if (dtype_in == NSOL_F64 && dtype_out == NSOL_F32) launch_scale_convert<double, float>(ctx, n, in_dev, out_dev, factor, divide, st);
+    else if (dtype_in == NSOL_F32 && dtype_out == NSOL_F64) launch_scale_convert<float, double>(ctx, n, in_dev, out_dev, factor, divide, st);
+    else if (dtype_in == NSOL_F32 && dtype_out == NSOL_F32) launch_scale_convert<float, float>(ctx, n, in_dev, out_dev, factor, divide, st);
+    else return nsol_fail(ctx, NSOL_EINVAL, "nsol_scale_convert: bad dtype");
+    NSOL_LAUNCH_CHECK(ctx);
+    return NSOL_OK;
+}

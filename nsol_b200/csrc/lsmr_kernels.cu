@@ -1,0 +1,742 @@
+// lsmr_kernels.cu -- LSMR on the stacked system [A; sqrt(alpha) B] x = [b; sqrt(alpha) b_reg]
+// and the ADMM TV-L2 loop on top of it, entirely device-resident.
+//
+// Replaces (reference file:line)
+//   TikhonovLinearSolver._run, lsmr/linear branch   nsol/tikhonov_linear_solver.py:120-158
+//   _get_augmented_linear_system / _A_augmented(_adj) nsol/tikhonov_linear_solver.py:226-274
+//   scipy.sparse.linalg.lsmr (scipy 1.18.1, Fong & Saunders 2011), cold start, atol=btol=0,
+//     conlim=1e8                                      scipy/sparse/linalg/_isolve/lsmr.py:239-479
+//   ADMMLinearSolver._run / _perform_ADMM_iteration / _prox_g  nsol/admm_linear_solver.py:165-253
+//
+// Layout: u has (1 + rows_B) SoA blocks of N (block 0 = data rows, blocks 1.. = rows of B);
+// v, h, hbar, x have N elements.  u and v are stored UN-normalised together with 1/beta and
+// 1/alpha; the scaling is applied by the consumers (no separate scaling pass).  All scalar
+// recurrences (Givens rotations, norm estimates, stopping tests) run in float64 in a
+// one-block kernel between the vector kernels, so an LSMR solve -- and a whole ADMM run --
+// needs no host synchronisation.  Norms: per-block partial sums reduced in a fixed order
+// (deterministic, float64 accumulation).
+#include <vector>
+
+#include "common.cuh"
+
+#define LSMR_THREADS 256
+
+struct LsmrScalars {
+    double alpha, beta, inv_alpha, inv_beta;
+    double zetabar, alphabar, rho, rhobar, cbar, sbar;
+    double betadd, betad, rhodold, tautildeold, thetatilde, zeta, d;
+    double normA2, maxrbar, minrbar, normb, normr, normar, normA, condA, normx;
+    double c_hbar, c_x, c_h;   // coefficients of the vector update
+    double sqrt_alpha;         // weight of the B rows
+    int itn, istop, done, maxiter;
+};
+
+// ---------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double warp_part[LSMR_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();   // protect warp_part against a previous call
+    if (lane == 0) warp_part[wid] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (wid == 0) {
+        r = lane < LSMR_THREADS / 32 ? warp_part[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+    }
+    return r;   // valid in thread 0
+}
+
+// sum of `count` partials, fixed order; result valid in thread 0 (one block)
+__device__ __forceinline__ double reduce_partials(const double *part, int count) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) acc += part[i];
+    return block_sum(acc);
+}
+
+// ---------------------------------------------------------------------------
+// stable Givens rotation (S.-C. Choi's SymOrtho; scipy lsqr.py:62-94)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double sign_d(double a) { return a > 0.0 ? 1.0 : (a < 0.0 ? -1.0 : 0.0); }
+
+__device__ __forceinline__ void sym_ortho(double a, double b, double &c, double &s, double &r) {
+    if (b == 0.0) {
+        c = sign_d(a); s = 0.0; r = fabs(a);
+    } else if (a == 0.0) {
+        c = 0.0; s = sign_d(b); r = fabs(b);
+    } else if (fabs(b) > fabs(a)) {
+        const double tau = a / b;
+        s = sign_d(b) / sqrt(1.0 + tau * tau);
+        c = s * tau;
+        r = b / s;
+    } else {
+        const double tau = b / a;
+        c = sign_d(a) / sqrt(1.0 + tau * tau);
+        s = c * tau;
+        r = a / c;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// scalar kernels (one block)
+// ---------------------------------------------------------------------------
+// after the right-hand side has been written into u: beta = ||b||
+__global__ void lsmr_scalar_init_beta(LsmrScalars *S, const double *part, int count, double sqrt_alpha, int maxiter) {
+    const double ss = reduce_partials(part, count);
+    if (threadIdx.x == 0) {
+        const double beta = sqrt(ss);
+        S->normb = beta;
+        S->beta = beta;
+        S->inv_beta = beta > 0.0 ? 1.0 / beta : 0.0;
+        S->sqrt_alpha = sqrt_alpha;
+        S->maxiter = maxiter;
+        S->itn = 0;
+        S->istop = 0;
+        S->done = 0;
+        S->alpha = 0.0;
+        S->inv_alpha = 0.0;
+    }
+}
+
+// after v = A^T u: alpha = ||v|| and the initial values of lsmr.py:262-313
+__global__ void lsmr_scalar_init_alpha(LsmrScalars *S, const double *part, int count) {
+    const double ss = reduce_partials(part, count);
+    if (threadIdx.x == 0) {
+        const double alpha = S->beta > 0.0 ? sqrt(ss) : 0.0;
+        S->alpha = alpha;
+        S->inv_alpha = alpha > 0.0 ? 1.0 / alpha : 0.0;
+        S->zetabar = alpha * S->beta;
+        S->alphabar = alpha;
+        S->rho = 1.0; S->rhobar = 1.0; S->cbar = 1.0; S->sbar = 0.0;
+        S->betadd = S->beta; S->betad = 0.0; S->rhodold = 1.0; S->tautildeold = 0.0;
+        S->thetatilde = 0.0; S->zeta = 0.0; S->d = 0.0;
+        S->normA2 = alpha * alpha; S->maxrbar = 0.0; S->minrbar = 1e100;
+        S->normA = sqrt(S->normA2); S->condA = 1.0; S->normx = 0.0;
+        S->normr = S->beta;
+        S->normar = alpha * S->beta;
+        // lsmr.py:307-315: nothing to do if A^T b = 0 or b = 0 (x stays 0)
+        if (S->normar == 0.0 || S->normb == 0.0 || S->maxiter <= 0) S->done = 1;
+    }
+}
+
+// beta_{k+1} = ||u||  (lsmr.py:338-340)
+__global__ void lsmr_scalar_beta(LsmrScalars *S, const double *part, int count) {
+    if (S->done) return;
+    const double ss = reduce_partials(part, count);
+    if (threadIdx.x == 0) {
+        const double beta = sqrt(ss);
+        S->beta = beta;
+        S->inv_beta = beta > 0.0 ? 1.0 / beta : 0.0;
+    }
+}
+
+// alpha_{k+1} = ||v|| and the two plane rotations (lsmr.py:344-377, 379-412)
+__global__ void lsmr_scalar_alpha(LsmrScalars *S, const double *part, int count) {
+    if (S->done) return;
+    const double ss = reduce_partials(part, count);
+    if (threadIdx.x != 0) return;
+    double alpha = S->alpha;
+    const double beta = S->beta;
+    if (beta > 0.0) {
+        alpha = sqrt(ss);
+        S->alpha = alpha;
+        S->inv_alpha = alpha > 0.0 ? 1.0 / alpha : S->inv_alpha;
+    }
+    S->itn += 1;
+    const double damp = 0.0;
+    double chat, shat, alphahat;
+    sym_ortho(S->alphabar, damp, chat, shat, alphahat);
+    const double rhoold = S->rho;
+    double c, s, rho;
+    sym_ortho(alphahat, beta, c, s, rho);
+    const double thetanew = s * alpha;
+    S->alphabar = c * alpha;
+    const double rhobarold = S->rhobar;
+    const double zetaold = S->zeta;
+    const double thetabar = S->sbar * rho;
+    const double rhotemp = S->cbar * rho;
+    double cbar, sbar, rhobar;
+    sym_ortho(S->cbar * rho, thetanew, cbar, sbar, rhobar);
+    const double zeta = cbar * S->zetabar;
+    S->zetabar = -sbar * S->zetabar;
+    S->cbar = cbar; S->sbar = sbar; S->rhobar = rhobar; S->rho = rho; S->zeta = zeta;
+    // coefficients of lsmr.py:373-377
+    S->c_hbar = -(thetabar * rho / (rhoold * rhobarold));
+    S->c_x = zeta / (rho * rhobar);
+    S->c_h = -(thetanew / rho);
+    // estimate of ||r|| (lsmr.py:381-404)
+    const double betaacute = chat * S->betadd;
+    const double betacheck = -shat * S->betadd;
+    const double betahat = c * betaacute;
+    S->betadd = -s * betaacute;
+    const double thetatildeold = S->thetatilde;
+    double ctildeold, stildeold, rhotildeold;
+    sym_ortho(S->rhodold, thetabar, ctildeold, stildeold, rhotildeold);
+    S->thetatilde = stildeold * rhobar;
+    S->rhodold = ctildeold * rhobar;
+    S->betad = -stildeold * S->betad + ctildeold * betahat;
+    S->tautildeold = (zetaold - thetatildeold * S->tautildeold) / rhotildeold;
+    const double taud = (zeta - S->thetatilde * S->tautildeold) / S->rhodold;
+    S->d = S->d + betacheck * betacheck;
+    S->normr = sqrt(S->d + (S->betad - taud) * (S->betad - taud) + S->betadd * S->betadd);
+    // estimate of ||A|| and cond(A) (lsmr.py:406-416)
+    S->normA2 = S->normA2 + beta * beta;
+    S->normA = sqrt(S->normA2);
+    S->normA2 = S->normA2 + alpha * alpha;
+    S->maxrbar = fmax(S->maxrbar, rhobarold);
+    if (S->itn > 1) S->minrbar = fmin(S->minrbar, rhobarold);
+    S->condA = fmax(S->maxrbar, rhotemp) / fmin(S->minrbar, rhotemp);
+    S->normar = fabs(S->zetabar);
+}
+
+// ||x|| and the stopping rules with atol = btol = 0, conlim = 1e8 (lsmr.py:418-459)
+__global__ void lsmr_scalar_tests(LsmrScalars *S, const double *part, int count) {
+    if (S->done) return;
+    const double ss = reduce_partials(part, count);
+    if (threadIdx.x != 0) return;
+    S->normx = sqrt(ss);
+    const double normb = S->normb, normA = S->normA, normr = S->normr;
+    const double test1 = normr / normb;
+    const double test2 = (normA * normr) != 0.0 ? S->normar / (normA * normr) : INFINITY;
+    const double test3 = 1.0 / S->condA;
+    const double t1 = test1 / (1.0 + normA * S->normx / normb);
+    const double rtol = 0.0;   // btol + atol * normA * normx / normb
+    const double ctol = 1.0 / 1e8;
+    int istop = 0;
+    if (S->itn >= S->maxiter) istop = 7;
+    if (1.0 + test3 <= 1.0) istop = 6;
+    if (1.0 + test2 <= 1.0) istop = 5;
+    if (1.0 + t1 <= 1.0) istop = 4;
+    if (test3 <= ctol) istop = 3;
+    if (test2 <= 0.0) istop = 2;
+    if (test1 <= rtol) istop = 1;
+    S->istop = istop;
+    if (istop > 0) S->done = 1;
+}
+
+// ---------------------------------------------------------------------------
+// vector kernels
+// ---------------------------------------------------------------------------
+template <typename T>
+struct LsqGeom {
+    long long n;
+    int nx, ny, nz, dim;
+    long long stride[3];   // element stride of reference component k
+    int extent[3];
+    int axis[3];           // 0 = x, 1 = y, 2 = z (kernel axis of component k)
+    T w[3];
+    int b_op;              // nsol_bop
+};
+
+template <typename T>
+__device__ __forceinline__ void lsq_decode(const LsqGeom<T> &g, long long r, int idx[3]) {
+    idx[0] = (int)(r % g.nx);
+    const long long t = r / g.nx;
+    idx[1] = (int)(t % g.ny);
+    idx[2] = (int)(t / g.ny);
+}
+
+// u = [b; sqrt_alpha * b_reg], partial ||u||^2
+template <typename T>
+__global__ void lsmr_rhs_kernel(LsqGeom<T> g, int rows_b, const T *__restrict__ b, const T *__restrict__ breg, double sqrt_alpha,
+                                T *__restrict__ u, double *__restrict__ part) {
+    const long long total = g.n * (1 + rows_b);
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        T v;
+        if (i < g.n) v = b[i];
+        else v = breg ? (T)sqrt_alpha * breg[i - g.n] : T(0);
+        u[i] = v;
+        acc += (double)v * (double)v;
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+// u <- (u * inv_beta) * (-alpha) + [Av; sqrt_alpha * B v],  v = vhat * inv_alpha   (lsmr.py:336-337)
+// Av_hat holds A(vhat) (un-normalised; A is linear) or equals vhat when A is the identity.
+template <typename T>
+__global__ void lsmr_fwd_kernel(LsqGeom<T> g, const LsmrScalars *__restrict__ S, const T *__restrict__ Av_hat, const T *__restrict__ vhat,
+                                T *__restrict__ u, double *__restrict__ part) {
+    if (S->done) return;
+    const T inv_alpha = (T)S->inv_alpha, inv_beta = (T)S->inv_beta, malpha = (T)(-S->alpha), sa = (T)S->sqrt_alpha;
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += (long long)gridDim.x * blockDim.x) {
+        T un = (u[i] * inv_beta) * malpha + Av_hat[i] * inv_alpha;
+        u[i] = un;
+        acc += (double)un * (double)un;
+        if (g.b_op == NSOL_B_GRAD) {
+            int idx[3];
+            lsq_decode(g, i, idx);
+            const T vc = vhat[i] * inv_alpha;
+            for (int k = 0; k < g.dim; ++k) {
+                const T hi = (idx[g.axis[k]] + 1 < g.extent[k]) ? vhat[i + g.stride[k]] * inv_alpha : T(0);
+                const T dk = g.w[k] * hi + (-g.w[k]) * vc;
+                T *uk = u + (long long)(1 + k) * g.n;
+                un = (uk[i] * inv_beta) * malpha + sa * dk;
+                uk[i] = un;
+                acc += (double)un * (double)un;
+            }
+        } else if (g.b_op == NSOL_B_IDENTITY) {
+            T *uk = u + g.n;
+            un = (uk[i] * inv_beta) * malpha + sa * (vhat[i] * inv_alpha);
+            uk[i] = un;
+            acc += (double)un * (double)un;
+        }
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+// vhat <- (vhat * inv_alpha) * (-beta) + (A^T u0 + sqrt_alpha * B^T u1..),  u = uhat * inv_beta   (lsmr.py:342-343)
+// Atu_hat holds A^T(uhat_0) (un-normalised) or equals uhat_0 when A is the identity.
+// first = 1: cold start v = A^T u (no previous v).
+template <typename T>
+__global__ void lsmr_adj_kernel(LsqGeom<T> g, const LsmrScalars *__restrict__ S, const T *__restrict__ Atu_hat, const T *__restrict__ u,
+                                T *__restrict__ vhat, double *__restrict__ part, int first) {
+    if (S->done) return;
+    const T inv_alpha = (T)S->inv_alpha, inv_beta = (T)S->inv_beta, mbeta = (T)(-S->beta), sa = (T)S->sqrt_alpha;
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += (long long)gridDim.x * blockDim.x) {
+        T r = Atu_hat[i] * inv_beta;
+        if (g.b_op == NSOL_B_GRAD) {
+            int idx[3];
+            lsq_decode(g, i, idx);
+            T div = T(0);
+            for (int k = 0; k < g.dim; ++k) {
+                const T *uk = u + (long long)(1 + k) * g.n;
+                const T lo = (idx[g.axis[k]] > 0) ? uk[i - g.stride[k]] * inv_beta : T(0);
+                const T dk = g.w[k] * lo + (-g.w[k]) * (uk[i] * inv_beta);
+                div = (k == 0) ? dk : div + dk;
+            }
+            r = r + sa * div;
+        } else if (g.b_op == NSOL_B_IDENTITY) {
+            r = r + sa * (u[g.n + i] * inv_beta);
+        }
+        const T vn = first ? r : (vhat[i] * inv_alpha) * mbeta + r;
+        vhat[i] = vn;
+        acc += (double)vn * (double)vn;
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+// h = v, hbar = 0, x = 0   (lsmr.py:277-278, 253)
+template <typename T>
+__global__ void lsmr_init_vectors_kernel(long long n, const LsmrScalars *__restrict__ S, const T *__restrict__ vhat, T *__restrict__ h,
+                                         T *__restrict__ hbar, T *__restrict__ x) {
+    const T inv_alpha = (T)S->inv_alpha;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        h[i] = vhat[i] * inv_alpha;
+        hbar[i] = T(0);
+        x[i] = T(0);
+    }
+}
+
+// hbar = c_hbar*hbar + h;  x += c_x*hbar;  h = c_h*h + v;  partial ||x||^2   (lsmr.py:373-377, 421)
+template <typename T>
+__global__ void lsmr_update_kernel(long long n, const LsmrScalars *__restrict__ S, const T *__restrict__ vhat, T *__restrict__ h,
+                                   T *__restrict__ hbar, T *__restrict__ x, double *__restrict__ part) {
+    if (S->done) return;
+    const T c_hbar = (T)S->c_hbar, c_x = (T)S->c_x, c_h = (T)S->c_h, inv_alpha = (T)S->inv_alpha;
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const T hv = h[i];
+        const T hb = hbar[i] * c_hbar + hv;
+        hbar[i] = hb;
+        const T xv = x[i] + c_x * hb;
+        x[i] = xv;
+        h[i] = hv * c_h + vhat[i] * inv_alpha;
+        acc += (double)xv * (double)xv;
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+template <typename T>
+__global__ void clip_kernel(long long n, const T *__restrict__ in, T *__restrict__ out, double lo, double hi) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double v = (double)in[i];
+        v = v < lo ? lo : (v > hi ? hi : v);     // np.clip
+        out[i] = (T)v;
+    }
+}
+
+// ADMM: t = B x + w_in ; v = shrink_iso(t, ell) ; w = t - v      (admm_linear_solver.py:208-216, 239-253)
+// optionally also breg_out = v - w  (the b_reg of the next Tikhonov solve, :222)
+template <typename T>
+__global__ void admm_shrink_kernel(LsqGeom<T> g, const T *__restrict__ x, const T *__restrict__ w_in, T ell, T *__restrict__ v_out,
+                                   T *__restrict__ w_out, T *__restrict__ breg_out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += (long long)gridDim.x * blockDim.x) {
+        int idx[3];
+        lsq_decode(g, i, idx);
+        const T xc = x[i];
+        T t[3];
+        T ss = T(0);
+        for (int k = 0; k < g.dim; ++k) {
+            const T hi = (idx[g.axis[k]] + 1 < g.extent[k]) ? x[i + g.stride[k]] : T(0);
+            T tk = g.w[k] * hi + (-g.w[k]) * xc;
+            if (w_in) tk = tk + w_in[(long long)k * g.n + i];
+            t[k] = tk;
+            ss = (k == 0) ? tk * tk : ss + tk * tk;
+        }
+        const T nrm = sqrt_t(ss);
+        const bool on = nrm > ell;
+        const T soft = max_t(nrm - ell, T(0));     // |n| = n >= 0, sign(n) = 1 where n > ell
+        for (int k = 0; k < g.dim; ++k) {
+            const T vk = on ? soft * t[k] / nrm : T(0);
+            const T wk = t[k] - vk;
+            v_out[(long long)k * g.n + i] = vk;
+            w_out[(long long)k * g.n + i] = wk;
+            if (breg_out) breg_out[(long long)k * g.n + i] = vk - wk;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------
+struct nsol_lsmr_plan {
+    nsol_ctx *ctx = nullptr;
+    nsol_lsq_desc desc;
+    nsol_grid grid;
+    GridView gv;
+    std::vector<double> taps[3];
+    size_t esz = 8;
+    int rows_b = 0;           // number of N-blocks of B rows
+    int nblocks = 0;          // blocks of the vector kernels = number of partials
+    void *u = nullptr, *v = nullptr, *h = nullptr, *hbar = nullptr, *x = nullptr;
+    void *opbuf = nullptr, *optmp = nullptr;   // A v / A^T u and separable scratch
+    void *breg = nullptr;                      // b_reg staging (rows_b * N)
+    void *admm_v = nullptr, *admm_w = nullptr; // ADMM split variables (dim * N each)
+    void *bbuf = nullptr, *xbuf = nullptr;     // scaled observation / current solution (N)
+    void *stage = nullptr;                     // float64 host-transfer staging
+    size_t stage_bytes = 0;
+    double *part = nullptr;
+    LsmrScalars *S = nullptr;
+    size_t bytes = 0;
+};
+
+extern "C" void nsol_lsmr_plan_destroy(nsol_lsmr_plan *pl) {
+    if (!pl) return;
+    if (pl->ctx) nsol_bind_device(pl->ctx);
+    void *ptrs[] = {pl->u, pl->v, pl->h, pl->hbar, pl->x, pl->opbuf, pl->optmp, pl->breg, pl->admm_v, pl->admm_w,
+                    pl->bbuf, pl->xbuf, pl->stage, pl->part, pl->S};
+    for (void *p : ptrs) cudaFree(p);
+    delete pl;
+}
+
+extern "C" int nsol_lsmr_plan_create(nsol_ctx *ctx, const nsol_lsq_desc *desc, nsol_lsmr_plan **out) {
+    if (!ctx) return NSOL_EINVAL;
+    if (!desc || !out) return nsol_fail(ctx, NSOL_EINVAL, "nsol_lsmr_plan_create: NULL argument");
+    *out = nullptr;
+    NSOL_CHECK(nsol_bind_device(ctx));
+    GridView gv;
+    NSOL_CHECK(nsol_grid_view(ctx, &desc->grid, &gv));
+    if (gv.batch != 1) return nsol_fail(ctx, NSOL_EINVAL, "lsmr: grid.batch must be 1");
+    if (desc->a_op != NSOL_A_BLUR && desc->a_op != NSOL_A_IDENTITY) return nsol_fail(ctx, NSOL_EINVAL, "lsmr: unknown a_op %d", desc->a_op);
+    if (desc->b_op < NSOL_B_GRAD || desc->b_op > NSOL_B_NONE) return nsol_fail(ctx, NSOL_EINVAL, "lsmr: unknown b_op %d", desc->b_op);
+    nsol_lsmr_plan *pl = new nsol_lsmr_plan();
+    pl->ctx = ctx;
+    pl->desc = *desc;
+    pl->grid = desc->grid;
+    pl->gv = gv;
+    pl->esz = nsol_dtype_size(gv.dtype);
+    if (desc->a_op == NSOL_A_BLUR) {
+        for (int a = 0; a < gv.dim; ++a) {
+            if (!desc->taps[a] || desc->radius[a] < 0 || desc->radius[a] > 64) {
+                delete pl;
+                return nsol_fail(ctx, NSOL_EINVAL, "lsmr: blur taps[%d] missing or radius out of range", a);
+            }
+            pl->taps[a].assign(desc->taps[a], desc->taps[a] + 2 * desc->radius[a] + 1);
+        }
+    }
+    for (int a = 0; a < 3; ++a) pl->desc.taps[a] = nullptr;
+    pl->rows_b = desc->b_op == NSOL_B_GRAD ? gv.dim : (desc->b_op == NSOL_B_IDENTITY ? 1 : 0);
+    long long want = (gv.n + LSMR_THREADS - 1) / LSMR_THREADS;
+    long long cap = ctx->lsmr_blocks > 0 ? ctx->lsmr_blocks : (long long)ctx->sm_count * 8;
+    pl->nblocks = (int)(want < cap ? (want > 0 ? want : 1) : cap);
+    const size_t nb = (size_t)gv.n * pl->esz;
+    auto alloc = [&](void **ptr, size_t bytes) -> bool {
+        cudaError_t e = cudaMalloc(ptr, bytes ? bytes : 8);
+        if (e != cudaSuccess) {
+            nsol_fail(ctx, NSOL_ENOMEM, "lsmr plan: cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e));
+            return false;
+        }
+        pl->bytes += bytes;
+        return true;
+    };
+    bool ok = alloc(&pl->u, nb * (1 + pl->rows_b)) && alloc(&pl->v, nb) && alloc(&pl->h, nb) && alloc(&pl->hbar, nb) && alloc(&pl->x, nb) &&
+              alloc(&pl->opbuf, nb) && alloc(&pl->optmp, nb) && alloc(&pl->breg, nb * (pl->rows_b ? pl->rows_b : 1)) &&
+              alloc(&pl->admm_v, nb * gv.dim) && alloc(&pl->admm_w, nb * gv.dim) && alloc(&pl->bbuf, nb) && alloc(&pl->xbuf, nb) &&
+              alloc((void **)&pl->part, sizeof(double) * (size_t)pl->nblocks * 2) && alloc((void **)&pl->S, sizeof(LsmrScalars));
+    if (!ok) {
+        nsol_lsmr_plan_destroy(pl);
+        return NSOL_ENOMEM;
+    }
+    *out = pl;
+    return NSOL_OK;
+}
+
+extern "C" size_t nsol_lsmr_plan_bytes(const nsol_lsmr_plan *pl) { return pl ? pl->bytes + pl->stage_bytes : 0; }
+
+template <typename T>
+static LsqGeom<T> make_geom(const nsol_lsmr_plan *pl) {
+    const GridView &gv = pl->gv;
+    LsqGeom<T> g;
+    g.n = gv.n;
+    g.nx = gv.nx;
+    g.ny = gv.ny;
+    g.nz = gv.nz;
+    g.dim = gv.dim;
+    g.b_op = pl->desc.b_op;
+    for (int k = 0; k < 3; ++k) {
+        g.stride[k] = 0;
+        g.extent[k] = 1;
+        g.axis[k] = 0;
+        g.w[k] = T(0);
+    }
+    for (int k = 0; k < gv.dim; ++k) {
+        const int ax = (k == 0) ? 0 : ((gv.dim == 3 && k == 1) ? 1 : 2);
+        g.axis[k] = ax;
+        g.stride[k] = ax == 0 ? 1 : (ax == 1 ? gv.nx : (long long)gv.nx * gv.ny);
+        g.extent[k] = ax == 0 ? gv.nx : (ax == 1 ? gv.ny : gv.nz);
+        g.w[k] = (T)gv.w[k];
+    }
+    return g;
+}
+
+// A(in) -> out for the plan's data operator (un-normalised input); returns the array holding the result
+static int lsq_apply_A(nsol_lsmr_plan *pl, const void *in, const void **result, cudaStream_t s) {
+    if (pl->desc.a_op == NSOL_A_IDENTITY) {
+        *result = in;
+        return NSOL_OK;
+    }
+    const double *taps[3] = {pl->taps[0].data(), pl->taps[1].data(), pl->taps[2].data()};
+    NSOL_CHECK(nsol_blur_sep(pl->ctx, &pl->grid, taps, pl->desc.radius, in, pl->opbuf, pl->optmp, s));
+    *result = pl->opbuf;
+    return NSOL_OK;
+}
+
+template <typename T>
+static int lsmr_solve_t(nsol_lsmr_plan *pl, double alpha, const void *b_dev, const void *breg_dev, int maxiter, double lo, double hi,
+                        void *x_out, cudaStream_t s) {
+    nsol_ctx *ctx = pl->ctx;
+    const LsqGeom<T> g = make_geom<T>(pl);
+    const int nb = pl->nblocks, th = LSMR_THREADS;
+    // alpha <= EPS: plain system A x = b (tikhonov_linear_solver.py:241-248)
+    const bool use_b = alpha > 1e-10 && pl->rows_b > 0;
+    LsqGeom<T> ge = g;
+    if (!use_b) ge.b_op = NSOL_B_NONE;
+    const int rows_b = use_b ? pl->rows_b : 0;
+    const double sa = use_b ? sqrt(alpha) : 0.0;
+    T *u = (T *)pl->u, *v = (T *)pl->v, *h = (T *)pl->h, *hbar = (T *)pl->hbar, *x = (T *)pl->x;
+    double *part = pl->part;
+
+    lsmr_rhs_kernel<T><<<nb, th, 0, s>>>(ge, rows_b, (const T *)b_dev, (const T *)breg_dev, sa, u, part);
+    NSOL_LAUNCH_CHECK(ctx);
+    lsmr_scalar_init_beta<<<1, th, 0, s>>>(pl->S, part, nb, sa, maxiter);
+    NSOL_LAUNCH_CHECK(ctx);
+    const void *op = nullptr;
+    NSOL_CHECK(lsq_apply_A(pl, u, &op, s));       // A^T = A (same mask, periodic)
+    lsmr_adj_kernel<T><<<nb, th, 0, s>>>(ge, pl->S, (const T *)op, u, v, part, 1);
+    NSOL_LAUNCH_CHECK(ctx);
+    lsmr_scalar_init_alpha<<<1, th, 0, s>>>(pl->S, part, nb);
+    NSOL_LAUNCH_CHECK(ctx);
+    lsmr_init_vectors_kernel<T><<<nb, th, 0, s>>>(g.n, pl->S, v, h, hbar, x);
+    NSOL_LAUNCH_CHECK(ctx);
+    for (int it = 0; it < maxiter; ++it) {
+        NSOL_CHECK(lsq_apply_A(pl, v, &op, s));
+        lsmr_fwd_kernel<T><<<nb, th, 0, s>>>(ge, pl->S, (const T *)op, v, u, part);
+        NSOL_LAUNCH_CHECK(ctx);
+        lsmr_scalar_beta<<<1, th, 0, s>>>(pl->S, part, nb);
+        NSOL_LAUNCH_CHECK(ctx);
+        NSOL_CHECK(lsq_apply_A(pl, u, &op, s));
+        lsmr_adj_kernel<T><<<nb, th, 0, s>>>(ge, pl->S, (const T *)op, u, v, part, 0);
+        NSOL_LAUNCH_CHECK(ctx);
+        lsmr_scalar_alpha<<<1, th, 0, s>>>(pl->S, part, nb);
+        NSOL_LAUNCH_CHECK(ctx);
+        lsmr_update_kernel<T><<<nb, th, 0, s>>>(g.n, pl->S, v, h, hbar, x, part);
+        NSOL_LAUNCH_CHECK(ctx);
+        lsmr_scalar_tests<<<1, th, 0, s>>>(pl->S, part, nb);
+        NSOL_LAUNCH_CHECK(ctx);
+    }
+    clip_kernel<T><<<nb, th, 0, s>>>(g.n, x, (T *)x_out, lo, hi);
+    NSOL_LAUNCH_CHECK(ctx);
+    return NSOL_OK;
+}
+
+static int lsmr_solve_any(nsol_lsmr_plan *pl, double alpha, const void *b_dev, const void *breg_dev, int maxiter, double lo, double hi,
+                          void *x_out, cudaStream_t s) {
+    if (pl->gv.dtype == NSOL_F32) return lsmr_solve_t<float>(pl, alpha, b_dev, breg_dev, maxiter, lo, hi, x_out, s);
+    return lsmr_solve_t<double>(pl, alpha, b_dev, breg_dev, maxiter, lo, hi, x_out, s);
+}
+
+extern "C" int nsol_lsmr_solve_dev(nsol_lsmr_plan *pl, double alpha, const void *b_dev, const void *b_reg_dev, int maxiter, double lo,
+                                   double hi, void *x_dev, int *itn_out, int *istop_out, nsol_stream s) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    if (!b_dev || !x_dev) return nsol_fail(ctx, NSOL_EINVAL, "lsmr solve: NULL array");
+    if (maxiter < 0) return nsol_fail(ctx, NSOL_EINVAL, "lsmr solve: maxiter must be >= 0");
+    if (!(alpha >= 0.0)) return nsol_fail(ctx, NSOL_EINVAL, "lsmr solve: alpha must be >= 0");
+    NSOL_CHECK(nsol_bind_device(ctx));
+    cudaStream_t st = (cudaStream_t)s;
+    NSOL_CHECK(lsmr_solve_any(pl, alpha, b_dev, b_reg_dev, maxiter, lo, hi, x_dev, st));
+    if (itn_out || istop_out) {
+        LsmrScalars hS;
+        NSOL_CUDA(ctx, cudaMemcpyAsync(&hS, pl->S, sizeof(hS), cudaMemcpyDeviceToHost, st));
+        NSOL_CUDA(ctx, cudaStreamSynchronize(st));
+        if (itn_out) *itn_out = hS.itn;
+        if (istop_out) *istop_out = hS.istop;
+    }
+    return NSOL_OK;
+}
+
+static int lsq_ensure_stage(nsol_lsmr_plan *pl, size_t bytes) {
+    if (pl->stage_bytes >= bytes) return NSOL_OK;
+    nsol_ctx *ctx = pl->ctx;
+    if (pl->stage) {
+        NSOL_CUDA(ctx, cudaDeviceSynchronize());
+        NSOL_CUDA(ctx, cudaFree(pl->stage));
+        pl->stage = nullptr;
+        pl->stage_bytes = 0;
+    }
+    NSOL_CUDA(ctx, cudaMalloc(&pl->stage, bytes));
+    pl->stage_bytes = bytes;
+    return NSOL_OK;
+}
+
+static int lsq_download(nsol_lsmr_plan *pl, const void *x_dev, double x_scale, double *x_host, cudaStream_t st) {
+    nsol_ctx *ctx = pl->ctx;
+    const size_t n = (size_t)pl->gv.n;
+    NSOL_CHECK(lsq_ensure_stage(pl, n * sizeof(double)));
+    NSOL_CHECK(nsol_scale_convert(ctx, (int64_t)n, pl->gv.dtype, x_dev, NSOL_F64, pl->stage, x_scale, 0, st));
+    NSOL_CUDA(ctx, cudaMemcpyAsync(x_host, pl->stage, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NSOL_CUDA(ctx, cudaStreamSynchronize(st));
+    return NSOL_OK;
+}
+
+// TikhonovLinearSolver.run() + get_x(): b, b_reg unscaled; solver works on b/x_scale, b_reg/x_scale
+// (linear_solver.py:80-89, tikhonov_linear_solver.py:88-89); result multiplied back (solver.py:117-118).
+extern "C" int nsol_tikhonov_run_host(nsol_lsmr_plan *pl, double alpha, double in_scale, double out_scale, const double *b_host,
+                                      const double *b_reg_host, int maxiter, double lo, double hi, double *x_host, nsol_stream s) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    if (!b_host || !x_host) return nsol_fail(ctx, NSOL_EINVAL, "tikhonov run: NULL array");
+    if (in_scale == 0.0 || out_scale == 0.0) return nsol_fail(ctx, NSOL_EINVAL, "tikhonov run: scales must be non-zero");
+    NSOL_CHECK(nsol_bind_device(ctx));
+    cudaStream_t st = (cudaStream_t)s;
+    const size_t n = (size_t)pl->gv.n;
+    const size_t nreg = b_reg_host ? n * (pl->rows_b ? pl->rows_b : 1) : 0;
+    NSOL_CHECK(lsq_ensure_stage(pl, (n + nreg) * sizeof(double)));
+    double *sb = (double *)pl->stage;
+    NSOL_CUDA(ctx, cudaMemcpyAsync(sb, b_host, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    NSOL_CHECK(nsol_scale_convert(ctx, (int64_t)n, NSOL_F64, sb, pl->gv.dtype, pl->bbuf, in_scale, 1, st));
+    const void *breg = nullptr;
+    if (b_reg_host && pl->rows_b) {
+        NSOL_CUDA(ctx, cudaMemcpyAsync(sb + n, b_reg_host, nreg * sizeof(double), cudaMemcpyHostToDevice, st));
+        NSOL_CHECK(nsol_scale_convert(ctx, (int64_t)nreg, NSOL_F64, sb + n, pl->gv.dtype, pl->breg, in_scale, 1, st));
+        breg = pl->breg;
+    }
+    NSOL_CHECK(lsmr_solve_any(pl, alpha, pl->bbuf, breg, maxiter, lo, hi, pl->xbuf, st));
+    return lsq_download(pl, pl->xbuf, out_scale, x_host, st);
+}
+
+template <typename T>
+static int admm_iterations_t(nsol_lsmr_plan *pl, double alpha, double rho, int iterations, int iter_max, const void *b_dev, void *x_dev,
+                             double x_scale, double *iterates_host, cudaStream_t s) {
+    nsol_ctx *ctx = pl->ctx;
+    const LsqGeom<T> g = make_geom<T>(pl);
+    const int nb = pl->nblocks, th = LSMR_THREADS;
+    const size_t n = (size_t)pl->gv.n;
+    T *v = (T *)pl->admm_v, *w = (T *)pl->admm_w, *breg = (T *)pl->breg;
+    // v = B(x0) - b_reg (b_reg = 0), w = 0  (admm_linear_solver.py:171-172): shrink with ell < 0 keeps v = t
+    // -> do it explicitly: v = grad(x0), w = 0, b_reg_next = v - w = v
+    NSOL_CHECK(nsol_grad(ctx, &pl->grid, x_dev, v, s));
+    NSOL_CUDA(ctx, cudaMemsetAsync(w, 0, n * pl->gv.dim * sizeof(T), s));
+    NSOL_CUDA(ctx, cudaMemcpyAsync(breg, v, n * pl->gv.dim * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    if (iterates_host) NSOL_CHECK(lsq_download(pl, x_dev, x_scale, iterates_host, s));
+    for (int it = 0; it < iterations; ++it) {
+        // x <- clip(lsmr([A; sqrt(rho) B], [b; sqrt(rho)(v - w)]), 0, inf)   (:205, :220-237; x0 is not passed to lsmr)
+        NSOL_CHECK(lsmr_solve_any(pl, rho, b_dev, breg, iter_max, 0.0, INFINITY, x_dev, s));
+        // t = B x + w ; v = prox_g(t, alpha/rho) ; w = t - v   (:208-216)
+        admm_shrink_kernel<T><<<nb, th, 0, s>>>(g, (const T *)x_dev, w, (T)(alpha / rho), v, w, breg);
+        NSOL_LAUNCH_CHECK(ctx);
+        if (iterates_host) NSOL_CHECK(lsq_download(pl, x_dev, x_scale, iterates_host + (size_t)(it + 1) * n, s));
+    }
+    return NSOL_OK;
+}
+
+static int admm_check(nsol_lsmr_plan *pl, double alpha, double rho, int iterations, int iter_max) {
+    nsol_ctx *ctx = pl->ctx;
+    if (pl->desc.b_op != NSOL_B_GRAD) return nsol_fail(ctx, NSOL_EINVAL, "admm: the plan's B must be the gradient");
+    if (!(rho > 1e-10)) return nsol_fail(ctx, NSOL_EINVAL, "admm: rho must be > 0");
+    if (!(alpha >= 0.0)) return nsol_fail(ctx, NSOL_EINVAL, "admm: alpha must be >= 0");
+    if (iterations < 0 || iter_max < 0) return nsol_fail(ctx, NSOL_EINVAL, "admm: iterations and iter_max must be >= 0");
+    return NSOL_OK;
+}
+
+extern "C" int nsol_admm_run_dev(nsol_lsmr_plan *pl, double alpha, double rho, int iterations, int iter_max, const void *b_dev,
+                                 const void *x0_dev, void *x_dev, nsol_stream s) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    if (!b_dev || !x0_dev || !x_dev) return nsol_fail(ctx, NSOL_EINVAL, "admm run: NULL array");
+    NSOL_CHECK(admm_check(pl, alpha, rho, iterations, iter_max));
+    NSOL_CHECK(nsol_bind_device(ctx));
+    cudaStream_t st = (cudaStream_t)s;
+    if (x_dev != x0_dev) NSOL_CUDA(ctx, cudaMemcpyAsync(x_dev, x0_dev, (size_t)pl->gv.n * pl->esz, cudaMemcpyDeviceToDevice, st));
+    if (pl->gv.dtype == NSOL_F32) return admm_iterations_t<float>(pl, alpha, rho, iterations, iter_max, b_dev, x_dev, 1.0, nullptr, st);
+    return admm_iterations_t<double>(pl, alpha, rho, iterations, iter_max, b_dev, x_dev, 1.0, nullptr, st);
+}
+
+extern "C" int nsol_admm_run_host(nsol_lsmr_plan *pl, double alpha, double rho, int iterations, int iter_max, double in_scale,
+                                  double out_scale, const double *b_host, const double *x0_host, double *x_host, double *iterates_host,
+                                  nsol_stream s) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    if (!b_host || !x0_host || !x_host) return nsol_fail(ctx, NSOL_EINVAL, "admm run: NULL array");
+    if (in_scale == 0.0 || out_scale == 0.0) return nsol_fail(ctx, NSOL_EINVAL, "admm run: scales must be non-zero");
+    NSOL_CHECK(admm_check(pl, alpha, rho, iterations, iter_max));
+    NSOL_CHECK(nsol_bind_device(ctx));
+    cudaStream_t st = (cudaStream_t)s;
+    const size_t n = (size_t)pl->gv.n;
+    NSOL_CHECK(lsq_ensure_stage(pl, 2 * n * sizeof(double)));
+    double *sb = (double *)pl->stage;
+    // b / x_scale, x0 / x_scale  (linear_solver.py:83, solver.py:37)
+    NSOL_CUDA(ctx, cudaMemcpyAsync(sb, b_host, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    NSOL_CUDA(ctx, cudaMemcpyAsync(sb + n, x0_host, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    NSOL_CHECK(nsol_scale_convert(ctx, (int64_t)n, NSOL_F64, sb, pl->gv.dtype, pl->bbuf, in_scale, 1, st));
+    NSOL_CHECK(nsol_scale_convert(ctx, (int64_t)n, NSOL_F64, sb + n, pl->gv.dtype, pl->xbuf, in_scale, 1, st));
+    int rc;
+    if (pl->gv.dtype == NSOL_F32) rc = admm_iterations_t<float>(pl, alpha, rho, iterations, iter_max, pl->bbuf, pl->xbuf, out_scale, iterates_host, st);
+    else rc = admm_iterations_t<double>(pl, alpha, rho, iterations, iter_max, pl->bbuf, pl->xbuf, out_scale, iterates_host, st);
+    NSOL_CHECK(rc);
+    return lsq_download(pl, pl->xbuf, out_scale, x_host, st);
+}
+
+extern "C" int nsol_admm_shrink(nsol_ctx *ctx, const nsol_grid *grid, const void *x_dev, const void *w_in_dev, double ell, void *v_dev,
+                                void *w_dev, nsol_stream s) {
+    if (!ctx) return NSOL_EINVAL;
+    if (!x_dev || !v_dev || !w_dev) return nsol_fail(ctx, NSOL_EINVAL, "nsol_admm_shrink: NULL array");
+    NSOL_CHECK(nsol_bind_device(ctx));
+    nsol_lsmr_plan tmp;
+    tmp.ctx = ctx;
+    tmp.desc.b_op = NSOL_B_GRAD;
+    NSOL_CHECK(nsol_grid_view(ctx, grid, &tmp.gv));
+    if (tmp.gv.batch != 1) return nsol_fail(ctx, NSOL_EINVAL, "nsol_admm_shrink: grid.batch must be 1");
+    long long want = (tmp.gv.n + LSMR_THREADS - 1) / LSMR_THREADS;
+    long long cap = (long long)ctx->sm_count * 8;
+    const int nb = (int)(want < cap ? (want > 0 ? want : 1) : cap);
+    if (tmp.gv.dtype == NSOL_F32)
+        admm_shrink_kernel<float><<<nb, LSMR_THREADS, 0, (cudaStream_t)s>>>(make_geom<float>(&tmp), (const float *)x_dev, (const float *)w_in_dev,
+                                                                           (float)ell, (float *)v_dev, (float *)w_dev, (float *)nullptr);
+    else
+        admm_shrink_kernel<double><<<nb, LSMR_THREADS, 0, (cudaStream_t)s>>>(make_geom<double>(&tmp), (const double *)x_dev, (const double *)w_in_dev,
+                                                                            ell, (double *)v_dev, (double *)w_dev, (double *)nullptr);
+    NSOL_LAUNCH_CHECK(ctx);
+    return NSOL_OK;
+}

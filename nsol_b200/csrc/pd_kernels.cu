@@ -1,0 +1,665 @@
+// pd_kernels.cu -- fused Chambolle-Pock iteration (one launch per iteration) and the
+// primal-dual plan behind nsol_pd_*.
+//
+// Replaces the body of PrimalDualSolver._run (reference nsol/primal_dual_solver.py:232-261)
+// for B = grad / B_conj = grad_adj (nsol/linear_operators.py:121-169), the dual
+// projections nsol/proximal_operators.py:139-140, :157-159 and the denoising
+// prox maps :96-98, :118-120.
+//
+// Single-pass kernel.  Each thread owns VEC consecutive x-voxels of one (y, x)
+// column position and marches through a chunk of z-planes:
+//     p'   = proj((p + sigma * grad(xbar)) / den_g)           (dual, 3 components)
+//     x'   = prox_f(x - tau * grad_adj(p'))                    (primal)
+//     xbar'= x' + theta (x' - x)
+// grad_adj at voxel i needs p' at i - e_k: along x it comes from the neighbouring
+// lane (warp shuffle), along y from the warp below (shared memory, one
+// __syncthreads per plane), along z from the thread's own previous plane
+// (register).  On the low side of a tile p' is recomputed from the old p and xbar
+// (one-voxel halo), so p and xbar are ping-pong buffered and x is updated in
+// place.  Compulsory traffic: read xbar, p[d], x, b; write p[d], x, xbar
+// = 5 + 2d words per voxel (11 words in 3-D = 88 B fp64 / 44 B fp32).
+//
+// Arithmetic keeps the reference's operation order and is compiled without FMA
+// contraction (-fmad=false), so the float64 path is bit-identical to numpy.
+#include <vector>
+
+#include "common.cuh"
+
+template <typename T>
+struct PdArgs {
+    const T *xbar_in;
+    T *xbar_out;
+    T *x;
+    const T *b;
+    const T *px_in, *py_in, *pz_in;   // kernel axis roles (see GridView)
+    T *px_out, *py_out, *pz_out;
+    const double *sched;              // [it][batch][8]
+    const T *halo_xbar_above, *halo_xbar_below, *halo_pz_below;  // z-slab neighbours (or NULL)
+    long long n;                      // voxels per problem
+    long long b_stride;               // 0 (shared observation) or n
+    int nx, ny, nz, zc, nchunks;
+    int has_z;
+    T wx, wy, wz;
+    int it, batch;
+};
+
+template <typename T, int REG>
+__device__ __forceinline__ T dual_update(T p, T hi, T lo, T w, T sigma, T den) {
+    // grad: fl(fl(w*x[i+1]) + fl((-w)*x[i]))   (scipy.ndimage.convolve order)
+    T g = w * hi + (-w) * lo;
+    T q = p + sigma * g;                                     // primal_dual_solver.py:242-243
+    if (REG != NSOL_REG_TV) q = q / den;                     // proximal_operators.py:158 / TK1
+    if (REG != NSOL_REG_TK1) q = q / max_t(T(1), abs_t(q));  // proximal_operators.py:140,159
+    return q;
+}
+
+template <typename T, int DATA>
+__device__ __forceinline__ void primal_update(T xv, T bv, T div, T tau, T tl, T theta, T den_f, T &xn, T &xbn) {
+    T yv = xv - tau * div;                                   // primal_dual_solver.py:246
+    if (DATA == NSOL_DATA_L2) {
+        xn = (yv + tl * bv) / den_f;                         // proximal_operators.py:120
+    } else {
+        T d = yv - bv;                                       // proximal_operators.py:98
+        T m = max_t(abs_t(d) - tl, T(0));
+        T sgn = d > T(0) ? T(1) : (d < T(0) ? T(-1) : T(0));
+        xn = bv + m * sgn;
+    }
+    xbn = xn + theta * (xn - xv);                            // primal_dual_solver.py:253
+}
+
+template <typename T, int VEC, bool HAS_Y, int REG, int DATA>
+__global__ void __launch_bounds__(512) pd_iter_kernel(const PdArgs<T> a) {
+    using V = Vec<T, VEC>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    const int lane = threadIdx.x & 31;
+    const int TY = HAS_Y ? (int)blockDim.y : 1;
+    const int ty = HAS_Y ? (int)threadIdx.y : 0;
+    const int tile_w = (int)blockDim.x * VEC;
+    const int x0 = (int)blockIdx.x * tile_w + (int)threadIdx.x * VEC;
+    const int y0 = HAS_Y ? (int)blockIdx.y * TY : 0;
+    const int y = y0 + ty;
+    const int chunk = (int)(blockIdx.z % (unsigned)a.nchunks);
+    const int bz = (int)(blockIdx.z / (unsigned)a.nchunks);
+    const int z0 = chunk * a.zc;
+    const int z1 = min(a.nz, z0 + a.zc);
+    const bool xin = x0 < a.nx;
+    const bool active = xin && (y < a.ny);
+
+    const double *srow = a.sched + ((long long)a.it * a.batch + bz) * 8;
+    const T sigma = (T)srow[0], tau = (T)srow[1], tl = (T)srow[2], theta = (T)srow[3];
+    const T den_g = (T)srow[4], den_f = (T)srow[5];
+    const T wx = a.wx, wy = a.wy, wz = a.wz;
+
+    const long long sz = (long long)a.nx * a.ny;
+    const long long vol = (long long)bz * a.n;
+    const long long row = (long long)y * a.nx + x0;          // offset inside a plane
+    const long long hrow = (long long)bz * sz + row;          // offset inside a halo plane array
+
+    const T *xbar = a.xbar_in + vol;
+    const T *bobs = a.b + (long long)bz * a.b_stride;
+
+    // shared tiles (3-D only): xbar rows [2][TY+2][tile_w], p'_y rows [2][TY+1][tile_w]
+    T *s_xb = reinterpret_cast<T *>(smem_raw);
+    T *s_py = s_xb + 2 * (TY + 2) * tile_w;
+    const int s_col = (int)threadIdx.x * VEC;
+
+    // edge roles
+    const bool need_r = active && lane == 31 && (x0 + VEC < a.nx);   // right x-halo
+    const bool need_l = active && lane == 0 && (x0 > 0);             // left x-halo
+    const bool up_warp = HAS_Y && ty == TY - 1;
+    const bool dn_warp = HAS_Y && ty == 0;
+    const bool need_up = up_warp && xin && (y + 1 < a.ny);
+    const bool need_dn = dn_warp && active && (y > 0);
+
+    // xbar plane z of this problem; planes -1 and nz come from the slab halos (or are 0)
+    auto load_xbar_own = [&](int z) -> V {
+        if (!active) return vec_zero<T, VEC>();
+        if (z >= 0 && z < a.nz) return vec_load<T, VEC>(xbar + (long long)z * sz + row);
+        if (z < 0 && a.halo_xbar_below) return vec_load<T, VEC>(a.halo_xbar_below + hrow);
+        if (z >= a.nz && a.halo_xbar_above) return vec_load<T, VEC>(a.halo_xbar_above + hrow);
+        return vec_zero<T, VEC>();
+    };
+
+    // ---- prologue: plane z0 --------------------------------------------------
+    V xb_c = load_xbar_own(z0);
+    T xr_c = need_r ? xbar[(long long)z0 * sz + row + VEC] : T(0);
+    T xl_c = need_l ? xbar[(long long)z0 * sz + row - 1] : T(0);
+    V pz_prev = vec_zero<T, VEC>();
+    if (a.has_z && active && (z0 > 0 || a.halo_pz_below)) {
+        V xb_m = load_xbar_own(z0 - 1);
+        V pz_m = z0 > 0 ? vec_load<T, VEC>(a.pz_in + vol + (long long)(z0 - 1) * sz + row)
+                        : vec_load<T, VEC>(a.halo_pz_below + hrow);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) pz_prev.v[v] = dual_update<T, REG>(pz_m.v[v], xb_c.v[v], xb_m.v[v], wz, sigma, den_g);
+    }
+    if (HAS_Y) {
+        T *buf = s_xb + (z0 & 1) * (TY + 2) * tile_w;
+        vec_store<T, VEC>(buf + (ty + 1) * tile_w + s_col, xb_c);
+        if (up_warp) {
+            V h = need_up ? vec_load<T, VEC>(xbar + (long long)z0 * sz + row + a.nx) : vec_zero<T, VEC>();
+            vec_store<T, VEC>(buf + (TY + 1) * tile_w + s_col, h);
+        }
+        if (dn_warp) {
+            V h = need_dn ? vec_load<T, VEC>(xbar + (long long)z0 * sz + row - a.nx) : vec_zero<T, VEC>();
+            vec_store<T, VEC>(buf + s_col, h);
+        }
+        __syncthreads();
+    }
+
+    // ---- march through the chunk ---------------------------------------------
+    for (int z = z0; z < z1; ++z) {
+        const long long pl = vol + (long long)z * sz + row;
+        const bool more = (z + 1 < z1);   // plane z+1 is processed by this CTA
+
+        // global loads: next xbar plane (own voxels), this plane's p, x, b
+        V xb_n = a.has_z ? load_xbar_own(z + 1) : vec_zero<T, VEC>();
+        V pxv = vec_zero<T, VEC>(), pyv = vec_zero<T, VEC>(), pzv = vec_zero<T, VEC>();
+        V xv = vec_zero<T, VEC>(), bv = vec_zero<T, VEC>();
+        T pxl = T(0);
+        V pydn = vec_zero<T, VEC>();
+        if (active) {
+            pxv = vec_load<T, VEC>(a.px_in + pl);
+            if (HAS_Y) pyv = vec_load<T, VEC>(a.py_in + pl);
+            if (a.has_z) pzv = vec_load<T, VEC>(a.pz_in + pl);
+            xv = vec_load<T, VEC>(a.x + pl);
+            bv = vec_load<T, VEC>(bobs + (long long)z * sz + row);
+        }
+        if (need_l) pxl = a.px_in[pl - 1];
+        if (need_dn) pydn = vec_load<T, VEC>(a.py_in + pl - a.nx);
+        // halos of the next plane (only if this CTA processes it)
+        T xr_n = T(0), xl_n = T(0);
+        V hup_n = vec_zero<T, VEC>(), hdn_n = vec_zero<T, VEC>();
+        if (more) {
+            const long long pn = (long long)(z + 1) * sz + row;
+            if (need_r) xr_n = xbar[pn + VEC];
+            if (need_l) xl_n = xbar[pn - 1];
+            if (need_up) hup_n = vec_load<T, VEC>(xbar + pn + a.nx);
+            if (need_dn) hdn_n = vec_load<T, VEC>(xbar + pn - a.nx);
+        }
+
+        // neighbours of the current plane
+        V xup = vec_zero<T, VEC>(), xdn = vec_zero<T, VEC>();
+        T *xbuf_c = s_xb + (z & 1) * (TY + 2) * tile_w;
+        T *xbuf_n = s_xb + ((z + 1) & 1) * (TY + 2) * tile_w;
+        T *pbuf = s_py + (z & 1) * (TY + 1) * tile_w;
+        if (HAS_Y) {
+            xup = vec_load<T, VEC>(xbuf_c + (ty + 2) * tile_w + s_col);
+            if (dn_warp) xdn = vec_load<T, VEC>(xbuf_c + s_col);
+        }
+        T x_right = shfl_down_t(xb_c.v[0], 1);
+        if (lane == 31) x_right = xr_c;
+
+        // dual update
+        V pnx, pny = vec_zero<T, VEC>(), pnz = vec_zero<T, VEC>();
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            T hi = (v + 1 < VEC) ? xb_c.v[(v + 1) % VEC] : x_right;
+            pnx.v[v] = dual_update<T, REG>(pxv.v[v], hi, xb_c.v[v], wx, sigma, den_g);
+            if (HAS_Y) pny.v[v] = dual_update<T, REG>(pyv.v[v], xup.v[v], xb_c.v[v], wy, sigma, den_g);
+            if (a.has_z) pnz.v[v] = dual_update<T, REG>(pzv.v[v], xb_n.v[v], xb_c.v[v], wz, sigma, den_g);
+        }
+        if (active) {
+            vec_store<T, VEC>(a.px_out + pl, pnx);
+            if (HAS_Y) vec_store<T, VEC>(a.py_out + pl, pny);
+            if (a.has_z) vec_store<T, VEC>(a.pz_out + pl, pnz);
+        }
+        // p'_x of the voxel left of this thread's first voxel
+        T pnx_left = shfl_up_t(pnx.v[VEC - 1], 1);
+        if (lane == 0) pnx_left = need_l ? dual_update<T, REG>(pxl, xb_c.v[0], xl_c, wx, sigma, den_g) : T(0);
+
+        V pny_dn = vec_zero<T, VEC>();
+        if (HAS_Y) {
+            // publish p'_y of this row (and of the halo row below the tile), and the next xbar plane
+            vec_store<T, VEC>(pbuf + (ty + 1) * tile_w + s_col, pny);
+            if (dn_warp) {
+                V h = vec_zero<T, VEC>();
+                if (need_dn) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) h.v[v] = dual_update<T, REG>(pydn.v[v], xb_c.v[v], xdn.v[v], wy, sigma, den_g);
+                }
+                vec_store<T, VEC>(pbuf + s_col, h);
+            }
+            if (more) {
+                vec_store<T, VEC>(xbuf_n + (ty + 1) * tile_w + s_col, xb_n);
+                if (up_warp) vec_store<T, VEC>(xbuf_n + (TY + 1) * tile_w + s_col, hup_n);
+                if (dn_warp) vec_store<T, VEC>(xbuf_n + s_col, hdn_n);
+            }
+            __syncthreads();
+            pny_dn = vec_load<T, VEC>(pbuf + ty * tile_w + s_col);
+        }
+
+        // primal update + over-relaxation
+        V xnew, xbnew;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            T lo = (v == 0) ? pnx_left : pnx.v[(v + VEC - 1) % VEC];
+            T div = wx * lo + (-wx) * pnx.v[v];                          // Dx^T p_x
+            if (HAS_Y) div = div + (wy * pny_dn.v[v] + (-wy) * pny.v[v]);   // += Dy^T p_y
+            if (a.has_z) div = div + (wz * pz_prev.v[v] + (-wz) * pnz.v[v]); // += Dz^T p_z
+            primal_update<T, DATA>(xv.v[v], bv.v[v], div, tau, tl, theta, den_f, xnew.v[v], xbnew.v[v]);
+        }
+        if (active) {
+            vec_store<T, VEC>(a.x + pl, xnew);
+            vec_store<T, VEC>(a.xbar_out + pl, xbnew);
+        }
+
+        xb_c = xb_n;
+        pz_prev = pnz;
+        xr_c = xr_n;
+        xl_c = xl_n;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------
+struct nsol_pd_plan {
+    nsol_ctx *ctx = nullptr;
+    nsol_pd_desc desc;
+    GridView gv;
+    std::vector<double> alpha;
+    size_t esz = 8;
+    // device state
+    void *x = nullptr, *b = nullptr;
+    void *xbar[2] = {nullptr, nullptr};
+    void *p[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    void *stage = nullptr;        // float64 staging for host transfers
+    size_t stage_bytes = 0;
+    double *sched = nullptr;      // device schedule table
+    int sched_cap = 0;            // iterations covered by the table
+    int cur = 0;                  // ping-pong index holding the current xbar/p
+    int it = 0;
+    bool ready = false;
+    size_t bytes = 0;
+    const void *halo_above = nullptr, *halo_below = nullptr, *halo_pz_below = nullptr;
+};
+
+// step sizes: reference nsol/primal_dual_solver.py:278-283, :302-306 (ALG2), :321-337, :356-358
+// (ALG3), :374-379, :398-403 (AHMOD); float64 host arithmetic in the reference's order.
+static void pd_schedule_rows(const nsol_pd_desc &d, double alpha, int iterations, double *rows /* [iterations][8] */) {
+    const double L2 = d.L2;
+    const double lmbda = 1.0 / alpha;
+    double tau, sigma, gamma;
+    if (d.alg == NSOL_ALG3) {
+        double g = lmbda, delta = 0.05;
+        double mu = 2.0 * sqrt(g * delta / L2);
+        gamma = 1.0 / (1.0 + mu);       // theta, carried in the gamma slot
+        sigma = mu / (2.0 * delta);
+        tau = mu / (2.0 * g);
+    } else if (d.alg == NSOL_ALG2_AHMOD) {
+        tau = 0.02;
+        sigma = 4.0 / (L2 * tau);
+        gamma = 0.35 * lmbda;
+    } else {
+        tau = 1.0 / sqrt(L2);
+        sigma = 1.0 / (L2 * tau);
+        gamma = 0.35 * lmbda;
+    }
+    for (int i = 0; i < iterations; ++i) {
+        double *r = rows + (size_t)i * 8;
+        double theta;
+        r[0] = sigma;
+        r[1] = tau;
+        r[2] = tau * lmbda;
+        if (d.alg == NSOL_ALG3) {
+            theta = gamma;
+        } else {
+            theta = 1.0 / sqrt(1.0 + 2.0 * gamma * tau);
+            tau = tau * theta;
+            sigma = sigma / theta;
+            if (d.alg == NSOL_ALG2_AHMOD) theta = 0.0;
+        }
+        r[3] = theta;
+        r[4] = d.reg == NSOL_REG_HUBER ? 1.0 + r[0] * d.huber_gamma : (d.reg == NSOL_REG_TK1 ? 1.0 + r[0] : 1.0);
+        r[5] = 1.0 + r[2];
+        r[6] = 0.0;
+        r[7] = 0.0;
+    }
+}
+
+static int pd_ensure_schedule(nsol_pd_plan *pl, int upto) {
+    if (upto <= pl->sched_cap) return NSOL_OK;
+    nsol_ctx *ctx = pl->ctx;
+    int cap = pl->sched_cap ? pl->sched_cap : 128;
+    while (cap < upto) cap *= 2;
+    const int batch = pl->gv.batch;
+    std::vector<double> rows((size_t)cap * batch * 8);
+    std::vector<double> one((size_t)cap * 8);
+    for (int bi = 0; bi < batch; ++bi) {
+        pd_schedule_rows(pl->desc, pl->alpha[bi], cap, one.data());
+        for (int i = 0; i < cap; ++i) memcpy(&rows[((size_t)i * batch + bi) * 8], &one[(size_t)i * 8], 8 * sizeof(double));
+    }
+    double *dev = nullptr;
+    NSOL_CUDA(ctx, cudaMalloc(&dev, rows.size() * sizeof(double)));
+    // synchronous copy: the old table may still be read by queued launches, so it is
+    // released only after the device is idle
+    cudaError_t e = cudaMemcpy(dev, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(dev);
+        return nsol_fail(ctx, NSOL_ECUDA, "schedule upload: %s", cudaGetErrorString(e));
+    }
+    if (pl->sched) {
+        cudaDeviceSynchronize();
+        cudaFree(pl->sched);
+    }
+    pl->sched = dev;
+    pl->sched_cap = cap;
+    return NSOL_OK;
+}
+
+extern "C" void nsol_pd_plan_destroy(nsol_pd_plan *pl) {
+    if (!pl) return;
+    if (pl->ctx) nsol_bind_device(pl->ctx);
+    cudaFree(pl->x);
+    cudaFree(pl->b);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(pl->xbar[i]);
+        for (int k = 0; k < 3; ++k) cudaFree(pl->p[i][k]);
+    }
+    cudaFree(pl->stage);
+    cudaFree(pl->sched);
+    delete pl;
+}
+
+extern "C" int nsol_pd_plan_create(nsol_ctx *ctx, const nsol_pd_desc *desc, nsol_pd_plan **out) {
+    if (!ctx) return NSOL_EINVAL;
+    if (!desc || !out) return nsol_fail(ctx, NSOL_EINVAL, "nsol_pd_plan_create: NULL argument");
+    *out = nullptr;
+    NSOL_CHECK(nsol_bind_device(ctx));
+    GridView gv;
+    NSOL_CHECK(nsol_grid_view(ctx, &desc->grid, &gv));
+    if (desc->reg < NSOL_REG_TV || desc->reg > NSOL_REG_TK1) return nsol_fail(ctx, NSOL_EINVAL, "pd: unknown regulariser %d", desc->reg);
+    if (desc->data != NSOL_DATA_L1 && desc->data != NSOL_DATA_L2) return nsol_fail(ctx, NSOL_EINVAL, "pd: unknown data term %d", desc->data);
+    if (desc->alg < NSOL_ALG2 || desc->alg > NSOL_ALG3) return nsol_fail(ctx, NSOL_EINVAL, "pd: unknown alg_type %d", desc->alg);
+    if (!(desc->L2 > 0.0)) return nsol_fail(ctx, NSOL_EINVAL, "pd: L2 must be > 0");
+    if (desc->x_scale == 0.0 || desc->x0_scale == 0.0 || desc->b_scale == 0.0)
+        return nsol_fail(ctx, NSOL_EINVAL, "pd: x_scale, x0_scale and b_scale must be non-zero");
+    if (!desc->alpha) return nsol_fail(ctx, NSOL_EINVAL, "pd: alpha is NULL");
+    for (int i = 0; i < gv.batch; ++i)
+        if (!(desc->alpha[i] > 0.0)) return nsol_fail(ctx, NSOL_EINVAL, "pd: alpha[%d] must be > 0", i);
+
+    nsol_pd_plan *pl = new nsol_pd_plan();
+    pl->ctx = ctx;
+    pl->desc = *desc;
+    pl->gv = gv;
+    pl->alpha.assign(desc->alpha, desc->alpha + gv.batch);
+    pl->desc.alpha = nullptr;
+    pl->esz = nsol_dtype_size(gv.dtype);
+    const size_t vol_bytes = (size_t)gv.n * gv.batch * pl->esz;
+    const size_t b_bytes = (size_t)gv.n * (desc->b_batched ? gv.batch : 1) * pl->esz;
+    auto alloc = [&](void **ptr, size_t bytes) -> bool {
+        cudaError_t e = cudaMalloc(ptr, bytes);
+        if (e != cudaSuccess) {
+            nsol_fail(ctx, NSOL_ENOMEM, "pd plan: cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e));
+            return false;
+        }
+        pl->bytes += bytes;
+        return true;
+    };
+    bool ok = alloc(&pl->x, vol_bytes) && alloc(&pl->b, b_bytes) && alloc(&pl->xbar[0], vol_bytes) && alloc(&pl->xbar[1], vol_bytes);
+    for (int i = 0; ok && i < 2; ++i)
+        for (int k = 0; ok && k < gv.dim; ++k) ok = alloc(&pl->p[i][k], vol_bytes);
+    if (!ok) {
+        nsol_pd_plan_destroy(pl);
+        return NSOL_ENOMEM;
+    }
+    int rc = pd_ensure_schedule(pl, 128);
+    if (rc != NSOL_OK) {
+        nsol_pd_plan_destroy(pl);
+        return rc;
+    }
+    *out = pl;
+    return NSOL_OK;
+}
+
+extern "C" size_t nsol_pd_plan_bytes(const nsol_pd_plan *pl) { return pl ? pl->bytes + pl->stage_bytes : 0; }
+extern "C" int nsol_pd_plan_iterations_done(const nsol_pd_plan *pl) { return pl ? pl->it : 0; }
+
+static int pd_ensure_stage(nsol_pd_plan *pl, size_t bytes) {
+    if (pl->stage_bytes >= bytes) return NSOL_OK;
+    nsol_ctx *ctx = pl->ctx;
+    if (pl->stage) {
+        NSOL_CUDA(ctx, cudaDeviceSynchronize());
+        NSOL_CUDA(ctx, cudaFree(pl->stage));
+        pl->stage = nullptr;
+        pl->stage_bytes = 0;
+    }
+    NSOL_CUDA(ctx, cudaMalloc(&pl->stage, bytes));
+    pl->stage_bytes = bytes;
+    return NSOL_OK;
+}
+
+// x = xbar = x0 / x0_scale, b' = b / b_scale (nsol/solver.py:35-41, proximal_operators.py:97,119), p = 0
+static int pd_reset_common(nsol_pd_plan *pl, int src_dtype, const void *b_src, const void *x0_src, cudaStream_t s) {
+    nsol_ctx *ctx = pl->ctx;
+    const GridView &gv = pl->gv;
+    const long long nb = gv.n * (pl->desc.b_batched ? gv.batch : 1);
+    const long long nv = gv.n * gv.batch;
+    NSOL_CHECK(nsol_scale_convert(ctx, nb, src_dtype, b_src, gv.dtype, pl->b, pl->desc.b_scale, 1, s));
+    if (!pl->desc.b_batched && gv.batch > 1 && x0_src) {
+        // a sweep shares one start value: replicate it across the batch
+        for (int bi = 0; bi < gv.batch; ++bi)
+            NSOL_CHECK(nsol_scale_convert(ctx, gv.n, src_dtype, x0_src, gv.dtype, (char *)pl->x + (size_t)bi * gv.n * pl->esz,
+                                          pl->desc.x0_scale, 1, s));
+    } else {
+        NSOL_CHECK(nsol_scale_convert(ctx, nv, src_dtype, x0_src, gv.dtype, pl->x, pl->desc.x0_scale, 1, s));
+    }
+    NSOL_CUDA(ctx, cudaMemcpyAsync(pl->xbar[0], pl->x, (size_t)nv * pl->esz, cudaMemcpyDeviceToDevice, s));
+    for (int k = 0; k < gv.dim; ++k) NSOL_CUDA(ctx, cudaMemsetAsync(pl->p[0][k], 0, (size_t)nv * pl->esz, s));
+    pl->cur = 0;
+    pl->it = 0;
+    pl->ready = true;
+    return NSOL_OK;
+}
+
+extern "C" int nsol_pd_plan_reset_dev(nsol_pd_plan *pl, const void *b_dev, const void *x0_dev, nsol_stream s) {
+    if (!pl) return NSOL_EINVAL;
+    if (!b_dev) return nsol_fail(pl->ctx, NSOL_EINVAL, "pd reset: b is NULL");
+    NSOL_CHECK(nsol_bind_device(pl->ctx));
+    return pd_reset_common(pl, pl->gv.dtype, b_dev, x0_dev ? x0_dev : b_dev, (cudaStream_t)s);
+}
+
+extern "C" int nsol_pd_plan_reset_host(nsol_pd_plan *pl, const double *b_host, const double *x0_host, nsol_stream s) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    if (!b_host) return nsol_fail(ctx, NSOL_EINVAL, "pd reset: b is NULL");
+    NSOL_CHECK(nsol_bind_device(ctx));
+    const GridView &gv = pl->gv;
+    cudaStream_t st = (cudaStream_t)s;
+    const size_t nb = (size_t)gv.n * (pl->desc.b_batched ? gv.batch : 1);
+    const bool same = (x0_host == nullptr) || (x0_host == b_host);
+    const size_t nx0 = same ? 0 : (pl->desc.b_batched || gv.batch == 1 ? (size_t)gv.n * gv.batch : (size_t)gv.n);
+    NSOL_CHECK(pd_ensure_stage(pl, (nb + nx0) * sizeof(double)));
+    double *sb = (double *)pl->stage;
+    double *sx = same ? sb : sb + nb;
+    NSOL_CUDA(ctx, cudaMemcpyAsync(sb, b_host, nb * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (!same) NSOL_CUDA(ctx, cudaMemcpyAsync(sx, x0_host, nx0 * sizeof(double), cudaMemcpyHostToDevice, st));
+    return pd_reset_common(pl, NSOL_F64, sb, sx, st);
+}
+
+extern "C" int nsol_pd_plan_set_halo(nsol_pd_plan *pl, const void *xbar_above, const void *xbar_below, const void *p_below) {
+    if (!pl) return NSOL_EINVAL;
+    if ((xbar_below == nullptr) != (p_below == nullptr))
+        return nsol_fail(pl->ctx, NSOL_EINVAL, "pd halo: xbar_below and p_below must be given together");
+    if ((xbar_above || xbar_below) && pl->gv.dim < 2)
+        return nsol_fail(pl->ctx, NSOL_EINVAL, "pd halo: slab decomposition needs dim >= 2");
+    pl->halo_above = xbar_above;
+    pl->halo_below = xbar_below;
+    pl->halo_pz_below = p_below;
+    return NSOL_OK;
+}
+
+extern "C" int nsol_pd_plan_boundary_planes(nsol_pd_plan *pl, const void **xbar_first, const void **xbar_last, const void **pz_last) {
+    if (!pl) return NSOL_EINVAL;
+    if (pl->gv.batch != 1) return nsol_fail(pl->ctx, NSOL_EINVAL, "pd boundary planes: batch must be 1");
+    const GridView &gv = pl->gv;
+    const size_t plane = (size_t)gv.nx * gv.ny * pl->esz;
+    const char *xb = (const char *)pl->xbar[pl->cur];
+    if (xbar_first) *xbar_first = xb;
+    if (xbar_last) *xbar_last = xb + (size_t)(gv.nz - 1) * plane;
+    if (pz_last) *pz_last = gv.comp_z >= 0 ? (const char *)pl->p[pl->cur][gv.comp_z] + (size_t)(gv.nz - 1) * plane : nullptr;
+    return NSOL_OK;
+}
+
+template <typename T, int VEC, bool HAS_Y>
+static void pd_launch_rd(const nsol_pd_plan *pl, const PdArgs<T> &a, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
+    const int reg = pl->desc.reg, data = pl->desc.data;
+#define NSOL_PD_CASE(R, D)                                                                 \
+    if (reg == R && data == D) {                                                           \
+        pd_iter_kernel<T, VEC, HAS_Y, R, D><<<grid, block, smem, s>>>(a);                  \
+        return;                                                                            \
+    }
+    NSOL_PD_CASE(NSOL_REG_TV, NSOL_DATA_L2)
+    NSOL_PD_CASE(NSOL_REG_TV, NSOL_DATA_L1)
+    NSOL_PD_CASE(NSOL_REG_HUBER, NSOL_DATA_L2)
+    NSOL_PD_CASE(NSOL_REG_HUBER, NSOL_DATA_L1)
+    NSOL_PD_CASE(NSOL_REG_TK1, NSOL_DATA_L2)
+    NSOL_PD_CASE(NSOL_REG_TK1, NSOL_DATA_L1)
+#undef NSOL_PD_CASE
+}
+
+template <typename T, int VECW>
+static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s) {
+    nsol_ctx *ctx = pl->ctx;
+    const GridView &gv = pl->gv;
+    const int cur = pl->cur, nxt = cur ^ 1;
+    PdArgs<T> a;
+    a.xbar_in = (const T *)pl->xbar[cur];
+    a.xbar_out = (T *)pl->xbar[nxt];
+    a.x = (T *)pl->x;
+    a.b = (const T *)pl->b;
+    a.px_in = (const T *)pl->p[cur][gv.comp_x];
+    a.px_out = (T *)pl->p[nxt][gv.comp_x];
+    a.py_in = gv.comp_y >= 0 ? (const T *)pl->p[cur][gv.comp_y] : nullptr;
+    a.py_out = gv.comp_y >= 0 ? (T *)pl->p[nxt][gv.comp_y] : nullptr;
+    a.pz_in = gv.comp_z >= 0 ? (const T *)pl->p[cur][gv.comp_z] : nullptr;
+    a.pz_out = gv.comp_z >= 0 ? (T *)pl->p[nxt][gv.comp_z] : nullptr;
+    a.sched = pl->sched;
+    a.halo_xbar_above = (const T *)pl->halo_above;
+    a.halo_xbar_below = (const T *)pl->halo_below;
+    a.halo_pz_below = (const T *)pl->halo_pz_below;
+    a.n = gv.n;
+    a.b_stride = pl->desc.b_batched ? gv.n : 0;
+    a.nx = gv.nx;
+    a.ny = gv.ny;
+    a.nz = gv.nz;
+    a.has_z = gv.comp_z >= 0;
+    a.wx = (T)gv.w[gv.comp_x];
+    a.wy = gv.comp_y >= 0 ? (T)gv.w[gv.comp_y] : T(0);
+    a.wz = gv.comp_z >= 0 ? (T)gv.w[gv.comp_z] : T(0);
+    a.it = pl->it;
+    a.batch = gv.batch;
+
+    const bool has_y = gv.comp_y >= 0;
+    dim3 block, grid;
+    size_t smem = 0;
+    int ty = 1;
+    if (has_y) {
+        ty = ctx->pd_ty ? ctx->pd_ty : 8;
+        if (ty < 2) ty = 2;
+        if (ty > 16) ty = 16;
+        block = dim3(32, ty, 1);
+        smem = (size_t)(2 * (ty + 2) + 2 * (ty + 1)) * 32 * VECW * sizeof(T);
+    } else {
+        block = dim3(128, 1, 1);
+    }
+    const int tile_w = block.x * VECW;
+    grid.x = (gv.nx + tile_w - 1) / tile_w;
+    grid.y = has_y ? (gv.ny + ty - 1) / ty : 1;
+    // z-chunk length: long enough to amortise the one-plane halo recompute, short enough
+    // to give every SM several CTAs
+    int zc = ctx->pd_zc;
+    if (zc <= 0) {
+        const long long tiles = (long long)grid.x * grid.y * gv.batch;
+        const long long want = (long long)ctx->sm_count * 16;   // CTAs
+        long long chunks = (want + tiles - 1) / tiles;
+        if (chunks < 1) chunks = 1;
+        zc = (int)((gv.nz + chunks - 1) / chunks);
+        if (zc < 8) zc = 8;
+        if (zc > 64) zc = 64;
+    }
+    if (zc > gv.nz) zc = gv.nz;
+    a.zc = zc;
+    a.nchunks = (gv.nz + zc - 1) / zc;
+    const long long gz = (long long)a.nchunks * gv.batch;
+    if (gz > 65535) return nsol_fail(ctx, NSOL_EINVAL, "pd: nchunks*batch = %lld exceeds the grid limit; raise pd_zc", gz);
+    grid.z = (unsigned)gz;
+    if (has_y) pd_launch_rd<T, VECW, true>(pl, a, grid, block, smem, s);
+    else pd_launch_rd<T, VECW, false>(pl, a, grid, block, smem, s);
+    NSOL_LAUNCH_CHECK(ctx);
+    pl->cur = nxt;
+    pl->it += 1;
+    return NSOL_OK;
+}
+
+extern "C" int nsol_pd_plan_iterate(nsol_pd_plan *pl, int n, nsol_stream s) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    if (!pl->ready) return nsol_fail(ctx, NSOL_ESTATE, "pd iterate: plan has not been reset with an observation");
+    if (n < 0) return nsol_fail(ctx, NSOL_EINVAL, "pd iterate: n must be >= 0");
+    NSOL_CHECK(nsol_bind_device(ctx));
+    NSOL_CHECK(pd_ensure_schedule(pl, pl->it + n));
+    const GridView &gv = pl->gv;
+    cudaStream_t st = (cudaStream_t)s;
+    const int vecw = gv.dtype == NSOL_F32 ? 4 : 2;
+    const bool vec_ok = (gv.nx % vecw) == 0;
+    for (int i = 0; i < n; ++i) {
+        int rc;
+        if (gv.dtype == NSOL_F32) rc = vec_ok ? pd_launch_iteration<float, 4>(pl, st) : pd_launch_iteration<float, 1>(pl, st);
+        else rc = vec_ok ? pd_launch_iteration<double, 2>(pl, st) : pd_launch_iteration<double, 1>(pl, st);
+        if (rc != NSOL_OK) return rc;
+    }
+    return NSOL_OK;
+}
+
+extern "C" int nsol_pd_plan_x_dev(nsol_pd_plan *pl, const void **x_dev) {
+    if (!pl || !x_dev) return NSOL_EINVAL;
+    *x_dev = pl->x;
+    return NSOL_OK;
+}
+
+extern "C" int nsol_pd_plan_get_x_dev(nsol_pd_plan *pl, int dtype_out, void *out_dev, nsol_stream s) {
+    if (!pl) return NSOL_EINVAL;
+    if (!pl->ready) return nsol_fail(pl->ctx, NSOL_ESTATE, "pd get_x: plan has not been reset");
+    NSOL_CHECK(nsol_bind_device(pl->ctx));
+    // get_x(): x * x_scale (nsol/solver.py:117-118)
+    return nsol_scale_convert(pl->ctx, pl->gv.n * pl->gv.batch, pl->gv.dtype, pl->x, dtype_out, out_dev, pl->desc.x_scale, 0, s);
+}
+
+extern "C" int nsol_pd_plan_get_x_host(nsol_pd_plan *pl, double *x_host, nsol_stream s) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    if (!x_host) return nsol_fail(ctx, NSOL_EINVAL, "pd get_x: output is NULL");
+    if (!pl->ready) return nsol_fail(ctx, NSOL_ESTATE, "pd get_x: plan has not been reset");
+    NSOL_CHECK(nsol_bind_device(ctx));
+    const size_t nv = (size_t)pl->gv.n * pl->gv.batch;
+    NSOL_CHECK(pd_ensure_stage(pl, nv * sizeof(double)));
+    cudaStream_t st = (cudaStream_t)s;
+    NSOL_CHECK(nsol_scale_convert(ctx, (int64_t)nv, pl->gv.dtype, pl->x, NSOL_F64, pl->stage, pl->desc.x_scale, 0, s));
+    NSOL_CUDA(ctx, cudaMemcpyAsync(x_host, pl->stage, nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NSOL_CUDA(ctx, cudaStreamSynchronize(st));
+    return NSOL_OK;
+}
+
+extern "C" int nsol_pd_run_host(nsol_ctx *ctx, const nsol_pd_desc *desc, int iterations, const double *b_host,
+                                const double *x0_host, double *x_host, double *iterates_host, nsol_stream s) {
+    if (!ctx) return NSOL_EINVAL;
+    if (iterations < 0) return nsol_fail(ctx, NSOL_EINVAL, "pd run: iterations must be >= 0");
+    nsol_pd_plan *pl = nullptr;
+    NSOL_CHECK(nsol_pd_plan_create(ctx, desc, &pl));
+    int rc = nsol_pd_plan_reset_host(pl, b_host, x0_host, s);
+    const size_t nv = (size_t)pl->gv.n * pl->gv.batch;
+    if (rc == NSOL_OK && iterates_host) {
+        rc = nsol_pd_plan_get_x_host(pl, iterates_host, s);
+        for (int i = 0; rc == NSOL_OK && i < iterations; ++i) {
+            rc = nsol_pd_plan_iterate(pl, 1, s);
+            if (rc == NSOL_OK) rc = nsol_pd_plan_get_x_host(pl, iterates_host + (size_t)(i + 1) * nv, s);
+        }
+    } else if (rc == NSOL_OK) {
+        rc = nsol_pd_plan_iterate(pl, iterations, s);
+    }
+    if (rc == NSOL_OK) rc = nsol_pd_plan_get_x_host(pl, x_host, s);
+    nsol_pd_plan_destroy(pl);
+    return rc;
+}

@@ -1,0 +1,125 @@
+"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL over NVLink /
+NVSwitch on the GPUs, gloo in the CPU tests).
+
+The reference is single-process, so everything here is new.  Two ways
+the path shards:
+
+* independent units -- parameter-sweep points / image batches: ``partition_round_robin``;
+  no data-path communication at all;
+* one large volume -- z-slab decomposition of the primal-dual iteration: rank r owns the
+  contiguous planes [z_lo, z_hi) of every array.  The fused iteration kernel needs, per
+  iteration, from the upper neighbour the first xbar plane (forward difference at the
+  slab top) and from the lower neighbour the last xbar and p_z planes (to recompute
+  p'_z[z_lo-1] for the adjoint): 3 planes per interior boundary, exchanged with
+  send/recv between neighbours.  The global ends keep the reference's zero (Dirichlet)
+  boundary: no wrap-around.
+"""
+import numpy as np
+
+
+def slab_bounds(nz, rank, world):
+    """Contiguous balanced split of nz planes: returns (z_lo, z_hi) of ``rank``."""
+    base, rem = divmod(int(nz), int(world))
+    z_lo = rank * base + min(rank, rem)
+    return z_lo, z_lo + base + (1 if rank < rem else 0)
+
+
+def partition_round_robin(n_items, rank, world):
+    """Indices of the independent work items (sweep points, images) owned by ``rank``."""
+    return list(range(int(rank), int(n_items), int(world)))
+
+
+class HaloExchanger(object):
+    """Neighbour exchange of the three boundary planes of a z-slab.
+
+    ``exchange(xbar_first, xbar_last, pz_last)`` sends this rank's boundary planes and
+    fills ``xbar_above`` (from rank+1), ``xbar_below`` and ``pz_below`` (from rank-1).
+    Tensors are torch tensors on the communicator's device.  Ranks at the global ends
+    simply skip the missing neighbour (their halos stay unused: zero boundary)."""
+
+    def __init__(self, rank, world, plane_numel, dtype, device, group=None):
+        import torch
+        self.torch = torch
+        self.rank, self.world, self.group = rank, world, group
+        self.has_below = rank > 0
+        self.has_above = rank < world - 1
+        mk = lambda: torch.zeros(plane_numel, dtype=dtype, device=device)
+        self.xbar_above = mk() if self.has_above else None
+        self.xbar_below = mk() if self.has_below else None
+        self.pz_below = mk() if self.has_below else None
+
+    def exchange(self, xbar_first, xbar_last, pz_last):
+        dist = self.torch.distributed
+        ops = []
+        if self.has_above:
+            ops.append(dist.P2POp(dist.isend, xbar_last, self.rank + 1, self.group))
+            ops.append(dist.P2POp(dist.isend, pz_last, self.rank + 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, self.xbar_above, self.rank + 1, self.group))
+        if self.has_below:
+            ops.append(dist.P2POp(dist.isend, xbar_first, self.rank - 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, self.xbar_below, self.rank - 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, self.pz_below, self.rank - 1, self.group))
+        if not ops:
+            return
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+class _DevicePtr(object):
+    """Expose a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr, numel, np_dtype):
+        self.__cuda_array_interface__ = {
+            "shape": (int(numel),), "typestr": np.dtype(np_dtype).str, "data": (int(ptr), False),
+            "version": 2, "strides": None}
+
+
+def tensor_from_ptr(ptr, numel, np_dtype, device):
+    import torch
+    return torch.as_tensor(_DevicePtr(ptr, numel, np_dtype), device=device)
+
+
+class SlabPrimalDual(object):
+    """z-slab sharded fused primal-dual iteration on one GPU per rank.
+
+    Wraps an ``nsol_pd_plan`` built for the local slab, wires its halo pointers to the
+    exchanger's receive buffers and alternates  exchange -> one fused iteration."""
+
+    def __init__(self, ctx, desc, plane_numel, np_dtype, rank, world, device):
+        import ctypes as C
+        self.C = C
+        self.ctx = ctx
+        self.np_dtype = np_dtype
+        self.plane_numel = plane_numel
+        self.device = device
+        h = C.c_void_p()
+        ctx.check(ctx.lib.nsol_pd_plan_create(ctx.handle, C.byref(desc), C.byref(h)))
+        self.plan = h
+        import torch
+        tdtype = torch.float32 if np.dtype(np_dtype) == np.float32 else torch.float64
+        self.halo = HaloExchanger(rank, world, plane_numel, tdtype, device)
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        ctx.check(ctx.lib.nsol_pd_plan_set_halo(self.plan, ptr(self.halo.xbar_above), ptr(self.halo.xbar_below),
+                                               ptr(self.halo.pz_below)))
+        self._views = {}
+
+    def _boundary_tensors(self):
+        C = self.C
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self.ctx.check(self.ctx.lib.nsol_pd_plan_boundary_planes(self.plan, C.byref(a), C.byref(b), C.byref(c)))
+        key = (a.value, b.value, c.value)
+        if key not in self._views:
+            self._views[key] = tuple(tensor_from_ptr(p, self.plane_numel, self.np_dtype, self.device) for p in key)
+        return self._views[key]
+
+    def iterate(self, n, stream):
+        for _ in range(n):
+            if self.halo.world > 1:
+                first, last, pz_last = self._boundary_tensors()
+                self.halo.exchange(first, last, pz_last)
+            self.ctx.check(self.ctx.lib.nsol_pd_plan_iterate(self.plan, 1, stream))
+
+    def close(self):
+        if self.plan is not None:
+            self.ctx.lib.nsol_pd_plan_destroy(self.plan)
+            self.plan = None

@@ -1,0 +1,189 @@
+"""First-order primal-dual (Chambolle-Pock) solver of the reference API, on the GPU.
+
+Same constructor, setters/getters and ``run()/get_x()`` contract as
+``nsol.primal_dual_solver.PrimalDualSolver`` (nsol/primal_dual_solver.py:26-403)
+for  min_x [f(x) + alpha g(Bx)].  ``_run`` does not call the Python callables
+per iteration: it probes them once (nsol_b200/_trace.py), recognises
+
+    B, B_conj      = LinearOperators*.get_gradient_operators()      (possibly lambda-wrapped)
+    prox_g_conj    = ProximalOperators.prox_tv_conj | prox_huber_conj | lambda q, s: q/(1+s)
+    prox_f         = prox_ell1_denoising | prox_ell2_denoising  (x0=b, x_scale)   [denoising]
+                   | prox_linear_least_squares (A = blur | identity)              [deconvolution]
+
+and runs the whole loop nsol/primal_dual_solver.py:232-261 on the device through
+the C ABI (``nsol_pd_*``): one fused kernel launch per iteration.  Callables that
+are not built from these pieces raise ``TypeError`` -- there is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from nsol_b200 import _lib
+from nsol_b200 import _trace
+from nsol_b200.solver import Solver
+
+_ALG_TYPES = ("ALG2", "ALG2_AHMOD", "ALG3")
+
+
+class PrimalDualSolver(Solver):
+
+    def __init__(self, prox_f, prox_g_conj, B, B_conj, L2, x0, alpha=0.01, iterations=10, x_scale=1.,
+                 verbose=0, alg_type="ALG2", dtype=None):
+        Solver.__init__(self, x0=x0, verbose=verbose, x_scale=x_scale)
+        self._prox_f = prox_f
+        self._prox_g_conj = prox_g_conj
+        self._B = B
+        self._B_conj = B_conj
+        self._L2 = float(L2)
+        self._alpha = float(alpha)
+        self._iterations = iterations
+        self._alg_type = alg_type
+        self._dtype = dtype          # additive option: "float64" (default) | "float32"
+        self._config = None          # cached result of probing the callables
+
+    # -- setters / getters (nsol/primal_dual_solver.py:120-197) ------------------
+    def set_alpha(self, alpha):
+        self._alpha = alpha
+
+    def get_alpha(self):
+        return self._alpha
+
+    def set_L2(self, L2):
+        self._L2 = L2
+
+    def get_L2(self):
+        return self._L2
+
+    def set_alg_type(self, alg_type):
+        self._alg_type = alg_type
+
+    def get_alg_type(self):
+        return self._alg_type
+
+    def set_iterations(self, iterations):
+        self._iterations = iterations
+
+    def get_iterations(self):
+        return self._iterations
+
+    def set_dtype(self, dtype):
+        self._dtype = dtype
+
+    def get_dtype(self):
+        return "float32" if _lib.dtype_code(self._dtype) == _lib.F32 else "float64"
+
+    def print_statistics(self, fmt="%.3e"):
+        pass
+
+    # -- probing -----------------------------------------------------------------
+    def _probe(self):
+        """Map the four callables to a kernel configuration (cached per solver)."""
+        if self._config is not None:
+            return self._config
+        n = self._x0.size
+        cfg = {}
+        out = _trace.probe(self._B, n)
+        if out.expr[0] != "grad" or out.expr[1] != ("arg",):
+            raise TypeError("PrimalDualSolver: B must be a LinearOperators gradient operator; supported: "
+                            + _trace.SUPPORTED)
+        _, _, dim, spacing, shape = out.expr
+        if int(np.prod(shape)) != n:
+            raise ValueError("PrimalDualSolver: B reshapes x0 (%d values) to %s" % (n, (shape,)))
+        cfg.update(dim=dim, spacing=spacing, shape=shape)
+        adj = _trace.probe(self._B_conj, dim * n)
+        if adj.expr[0] != "grad_adj" or adj.expr[1] != ("arg",) or adj.expr[2:5] != (dim, spacing, shape):
+            raise TypeError("PrimalDualSolver: B_conj must be the adjoint gradient of B's grid; supported: "
+                            + _trace.SUPPORTED)
+
+        s1, s2 = 0.37, 1.83
+        g1 = _trace.probe(self._prox_g_conj, dim * n, s1).expr
+        g2 = _trace.probe(self._prox_g_conj, dim * n, s2).expr
+        if g1[0] == "prox_tv_conj" and g1[1] == ("arg",):
+            cfg.update(reg="TV", huber_gamma=0.05)
+        elif g1[0] == "prox_huber_conj" and g1[1] == ("arg",) and g1[2] == s1 and g2[2] == s2:
+            cfg.update(reg="HUBER", huber_gamma=g1[3])
+        elif (g1[0] == "scale" and g1[1] == ("arg",) and g1[3] and g2[3]
+              and g1[2] == 1 + s1 and g2[2] == 1 + s2):
+            cfg.update(reg="TK1", huber_gamma=0.05)
+        else:
+            raise TypeError("PrimalDualSolver: unsupported prox_g_conj; supported: " + _trace.SUPPORTED)
+
+        t1 = 0.4321
+        f1 = _trace.probe(self._prox_f, n, t1).expr
+        if f1[0] in ("prox_ell1", "prox_ell2") and f1[1] == ("arg",) and f1[2] == t1:
+            b = np.asarray(f1[3], dtype=np.float64).reshape(-1)
+            if b.size != n:
+                raise ValueError("PrimalDualSolver: prox_f observation has %d values, x0 has %d" % (b.size, n))
+            cfg.update(kind="denoise", data="L1" if f1[0] == "prox_ell1" else "L2", b=b, b_scale=f1[4])
+        elif f1[0] == "prox_lls" and f1[1] == ("arg",) and f1[2] == t1:
+            cfg.update(kind="deconv", lls=f1)
+        else:
+            raise TypeError("PrimalDualSolver: unsupported prox_f; supported: " + _trace.SUPPORTED)
+        self._config = cfg
+        return cfg
+
+    # -- execution ---------------------------------------------------------------
+    def _make_desc(self, cfg, alphas):
+        dtype = _lib.dtype_code(self._dtype)
+        if self._alg_type not in _ALG_TYPES:
+            raise KeyError(self._alg_type)
+        desc = _lib.PdDesc()
+        desc.grid = _lib.make_grid(cfg["shape"], cfg["spacing"], dtype, batch=len(alphas))
+        desc.reg = _lib.REG[cfg["reg"]]
+        desc.data = _lib.DATA[cfg["data"]]
+        desc.alg = _lib.ALG[self._alg_type]
+        desc.b_batched = 0
+        desc.huber_gamma = cfg["huber_gamma"]
+        desc.L2 = float(self._L2)
+        desc.x_scale = float(self._x_scale)
+        desc.x0_scale = 1.0            # self._x0 is already x0 / x_scale (nsol/solver.py:37)
+        desc.b_scale = float(cfg["b_scale"])
+        arr = np.ascontiguousarray(alphas, dtype=np.float64)
+        desc.alpha = arr.ctypes.data_as(_lib.c_double_p)
+        desc._keep = arr
+        return desc
+
+    def _run(self):
+        cfg = self._probe()
+        if cfg["kind"] == "deconv":
+            from nsol_b200._pd_deconv import run_pd_deconvolution
+            return run_pd_deconvolution(self, cfg)
+        ctx = _lib.context()
+        n = self._x0.size
+        desc = self._make_desc(cfg, [float(self._alpha)])
+        x0 = np.ascontiguousarray(self._x0, dtype=np.float64)
+        b = np.ascontiguousarray(cfg["b"], dtype=np.float64)
+        iters = int(self._iterations)
+        x_out = np.empty(n, dtype=np.float64)
+        if self._observer is None:
+            ctx.check(ctx.lib.nsol_pd_run_host(ctx.handle, C.byref(desc), iters, b.ctypes.data, x0.ctypes.data,
+                                               x_out.ctypes.data, None, None))
+        else:
+            # nsol/primal_dual_solver.py:218-219, 260-261: the observer sees x0 and every iterate
+            its = np.empty((iters + 1, n), dtype=np.float64)
+            ctx.check(ctx.lib.nsol_pd_run_host(ctx.handle, C.byref(desc), iters, b.ctypes.data, x0.ctypes.data,
+                                               x_out.ctypes.data, its.ctypes.data, None))
+            for i in range(iters + 1):
+                self._observer.add_x(np.array(its[i]))
+        self._set_result(x_out)
+
+    def run_sweep(self, alphas):
+        """Batched parameter sweep: one fused launch per iteration advances every alpha.
+        Returns an array (len(alphas), N) of get_x() results.  (Additive API used by the
+        parameter-study driver; the reference runs the points one after another,
+        nsol/solver_parameter_study.py:170-221.)"""
+        cfg = self._probe()
+        if cfg["kind"] != "denoise":
+            raise TypeError("run_sweep is available for the denoising prox maps only")
+        if self._x0.ndim != 1:
+            raise ValueError("Initial value x0 must be a 1D array")
+        ctx = _lib.context()
+        n = self._x0.size
+        alphas = [float(a) for a in alphas]
+        desc = self._make_desc(cfg, alphas)
+        x0 = np.ascontiguousarray(self._x0, dtype=np.float64)
+        b = np.ascontiguousarray(cfg["b"], dtype=np.float64)
+        x_out = np.empty((len(alphas), n), dtype=np.float64)
+        ctx.check(ctx.lib.nsol_pd_run_host(ctx.handle, C.byref(desc), int(self._iterations), b.ctypes.data,
+                                           x0.ctypes.data, x_out.ctypes.data, None, None))
+        return x_out

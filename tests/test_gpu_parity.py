@@ -1,0 +1,357 @@
+"""GPU parity tests (run with ``-m gpu`` on a B200).
+
+Every test drives the CUDA path through the reference-shaped Python API, i.e.
+through the C ABI of libnsol_b200.so, and compares with
+  * the golden fixtures produced by the unmodified reference (tests/golden), and
+  * the CPU oracle (oracle/nsol_oracle.py) on seeded inputs.
+
+Bars (north_star): float64 primal-dual and stencils BIT-EXACT (stricter than the
+1e-10 the north star asks for); float64 LSMR/ADMM <= 1e-10 relative max-abs;
+float32 <= 1e-4 relative max-abs and PSNR/SSIM/NCC equal to three decimals.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_max
+from oracle import nsol_oracle as orc
+
+import nsol_b200.linear_operators as lo
+import nsol_b200.primal_dual_solver as pd
+import nsol_b200.admm_linear_solver as admm
+import nsol_b200.tikhonov_linear_solver as tk
+from nsol_b200 import _lib
+from nsol_b200.proximal_operators import ProximalOperators as prox
+
+pytestmark = pytest.mark.gpu
+
+F64_LSMR_TOL = 1e-10     # north_star: fp64 within 1e-10 relative max-abs
+F32_TOL = 1e-4           # north_star: fp32 within 1e-4 relative
+
+
+def linops(dim, spacing=None):
+    cls = getattr(lo, "LinearOperators%dD" % dim)
+    if spacing is None:
+        return cls()
+    return cls(spacing=np.asarray(spacing, dtype=float) if dim > 1 else float(spacing[0]))
+
+
+def make_pd(obs, reg, data, alpha, L2, iterations, alg_type="ALG2", spacing=None, x_scale=None, dtype=None):
+    """Wired exactly like nsol/application/run_denoising.py:95-154."""
+    dim = obs.ndim
+    b = obs.flatten()
+    x0 = obs.flatten()
+    x_scale = float(np.max(obs)) if x_scale is None else x_scale
+    grad, grad_adj = linops(dim, spacing).get_gradient_operators()
+    X_shape = obs.shape
+    Z_shape = (dim * obs.shape[0],) + obs.shape[1:]
+    D_1D = lambda x: grad(x.reshape(*X_shape)).flatten()
+    D_adj_1D = lambda x: grad_adj(x.reshape(*Z_shape)).flatten()
+    if data == "L1":
+        prox_f = lambda x, tau: prox.prox_ell1_denoising(x, tau, x0=b, x_scale=x_scale)
+    else:
+        prox_f = lambda x, tau: prox.prox_ell2_denoising(x, tau, x0=b, x_scale=x_scale)
+    prox_g_conj = {"TV": prox.prox_tv_conj, "HUBER": prox.prox_huber_conj, "TK1": lambda q, s: q / (1 + s)}[reg]
+    return pd.PrimalDualSolver(prox_f=prox_f, prox_g_conj=prox_g_conj, B=D_1D, B_conj=D_adj_1D, L2=L2, x0=x0,
+                               alpha=alpha, iterations=iterations, x_scale=x_scale, alg_type=alg_type, dtype=dtype)
+
+
+def run_pd(obs, **kw):
+    s = make_pd(obs, **kw)
+    s.run()
+    return s.get_x()
+
+
+def assert_measures_3dec(x, ref, clean):
+    for f in (orc.psnr, orc.ncc, orc.ssim_1d):
+        a, b = f(x, clean), f(ref, clean)
+        assert round(a, 3) == round(b, 3) or abs(a - b) < 5e-4, (f.__name__, a, b)
+
+
+# ------------------------------------------------------------------ operators
+def test_gradient_operators_bit_exact(golden):
+    for name, meta in sorted(golden.manifest["ops"].items()):
+        if not name.startswith("g"):
+            continue
+        x = golden("ops", name + "/x")
+        y = golden("ops", name + "/y")
+        ops = linops(x.ndim, meta["spacing"])
+        grad, grad_adj = ops.get_gradient_operators()
+        g = grad(x)
+        assert g.shape == golden("ops", name + "/grad").shape
+        assert np.array_equal(g, golden("ops", name + "/grad")), name
+        assert np.array_equal(grad_adj(y), golden("ops", name + "/grad_adj")), name
+        # grad == concat(dx, dy, dz), grad_adj == sum d*_adj  (tests/kernels_test.py:222-301)
+        parts, adj = [], None
+        blocks = np.array_split(y, x.ndim)
+        for k, nm in enumerate(["dx", "dy", "dz"][:x.ndim]):
+            D, D_adj = getattr(ops, "get_%s_operators" % nm)()
+            parts.append(D(x))
+            adj = D_adj(blocks[k]) if adj is None else adj + D_adj(blocks[k])
+        assert np.array_equal(np.concatenate(parts), g), name
+        assert np.array_equal(adj, golden("ops", name + "/grad_adj")), name
+
+
+def test_blur_operators(golden):
+    for name, meta in sorted(golden.manifest["ops"].items()):
+        if not name.startswith("b"):
+            continue
+        x = golden("ops", name + "/x")
+        dim = x.ndim
+        cov = meta["var"] if dim == 1 else np.diag(meta["var"])
+        ops = linops(dim, meta["spacing"])
+        A, A_adj = ops.get_gaussian_blurring_operators(cov)
+        ref = golden("ops", name + "/A")
+        assert rel_max(A(x), ref) < 1e-14, name
+        assert rel_max(A_adj(x), ref) < 1e-14, name
+        # dense path with the same mask
+        Ad, _ = ops.get_convolution_and_adjoint_convolution_operators(golden("ops", name + "/kernel"))
+        Ad.taps = None
+        assert rel_max(Ad(x), ref) < 1e-14, name
+
+
+def test_adjointness_properties():
+    """tests/kernels_test.py:138-335 on the CUDA operators: <Ax,y> == <x,A'y> to 1e-10."""
+    rng = np.random.RandomState(0)
+    for shape in [(50,), (50, 50), (50, 50, 10)]:
+        dim = len(shape)
+        spacing = rng.rand(dim) + 0.5
+        ops = linops(dim, spacing)
+        x = rng.rand(*shape)
+        grad, grad_adj = ops.get_gradient_operators()
+        y = rng.rand(*((dim * shape[0],) + shape[1:]))
+        assert round(abs(np.sum(grad(x) * y) - np.sum(x * grad_adj(y))), 10) == 0
+        A, A_adj = ops.get_gaussian_blurring_operators(1.5 if dim == 1 else np.eye(dim) * 1.5)
+        z = rng.rand(*shape)
+        assert round(abs(np.sum(A(x) * z) - np.sum(x * A_adj(z))), 10) == 0
+
+
+def test_standalone_prox_maps():
+    rng = np.random.RandomState(5)
+    x = rng.randn(1000) * 2
+    x0 = rng.rand(1000) * 3
+    assert np.array_equal(prox.prox_tv_conj(x, 0.3), orc.prox_tv_conj(x, 0.3))
+    assert np.array_equal(prox.prox_huber_conj(np.array(x), 0.3), orc.prox_huber_conj(x, 0.3))
+    assert np.array_equal(prox.prox_ell1_denoising(x, 0.4, x0, 1.7), orc.prox_ell1_denoising(x, 0.4, x0, 1.7))
+    assert np.array_equal(prox.prox_ell2_denoising(x, 0.4, x0, 1.7), orc.prox_ell2_denoising(x, 0.4, x0, 1.7))
+
+
+# ------------------------------------------------------------------ primal-dual vs reference fixtures
+def test_primal_dual_fp64_bit_exact_vs_reference(golden):
+    for name, meta in sorted(golden.manifest["pd"].items()):
+        if name.endswith("_iterates"):
+            continue
+        obs = golden("pd", "in/" + meta["input"])
+        x = run_pd(obs, reg=meta["reg"], data=meta["data"], alpha=meta["alpha"], L2=meta["L2"],
+                   iterations=meta["iterations"], alg_type=meta.get("alg_type", "ALG2"),
+                   spacing=meta.get("spacing"), x_scale=meta.get("x_scale"))
+        ref = golden("pd", name)
+        assert np.array_equal(x, ref), (name, rel_max(x, ref))
+
+
+def test_primal_dual_fp32_vs_reference(golden):
+    for name in ("c1_lena_TV_L2", "c2_man_HUBER_L1", "3d_TV_L2_L12", "3d_HUBER_L1", "2d_TK1_L2", "1d_TV_L2"):
+        meta = golden.manifest["pd"][name]
+        obs = golden("pd", "in/" + meta["input"])
+        x = run_pd(obs, reg=meta["reg"], data=meta["data"], alpha=meta["alpha"], L2=meta["L2"],
+                   iterations=meta["iterations"], dtype="float32")
+        ref = golden("pd", name)
+        assert rel_max(x, ref) < F32_TOL, (name, rel_max(x, ref))
+        assert_measures_3dec(x, ref, obs.reshape(-1))
+
+
+def test_primal_dual_observer_iterates(golden):
+    meta = golden.manifest["pd"]["2d_TV_L2_iterates"]
+    obs = golden("pd", "in/" + meta["input"])
+    from nsol_b200.observer import Observer
+    s = make_pd(obs, reg="TV", data="L2", alpha=meta["alpha"], L2=meta["L2"], iterations=meta["iterations"])
+    o = Observer()
+    s.set_observer(o)
+    s.run()
+    assert np.array_equal(np.array(o.get_x_list()), golden("pd", "2d_TV_L2_iterates"))
+    assert s.get_computational_time().total_seconds() > 0
+
+
+# ------------------------------------------------------------------ primal-dual vs oracle on seeded inputs
+@pytest.mark.parametrize("shape", [(1,), (2,), (333,), (1, 1), (1, 7), (9, 1), (3, 2), (67, 258), (130, 131),
+                                   (1, 1, 1), (2, 3, 1), (1, 4, 6), (5, 1, 6), (19, 21, 130), (33, 18, 66), (9, 40, 260)])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_primal_dual_ragged_shapes_vs_oracle(shape, dtype):
+    rng = np.random.RandomState(sum(shape))
+    obs = rng.rand(*shape) * 255
+    ctx = _lib.context()
+    ctx.set_tuning("pd_zc", 8)     # several z-chunks even for small volumes
+    ctx.set_tuning("pd_ty", 4)
+    try:
+        for reg, data, alpha in (("TV", "L2", 0.05), ("HUBER", "L1", 0.6)):
+            x = run_pd(obs, reg=reg, data=data, alpha=alpha, L2=8, iterations=12, dtype=dtype)
+            ref = orc.primal_dual_denoise(obs.reshape(-1), shape, reg=reg, data=data, alpha=alpha, L2=8, iterations=12,
+                                          x_scale=float(obs.max()))
+            if dtype == "float64":
+                assert np.array_equal(x, ref), (shape, reg, rel_max(x, ref))
+            else:
+                assert rel_max(x, ref) < F32_TOL, (shape, reg, rel_max(x, ref))
+    finally:
+        ctx.set_tuning("pd_zc", 0)
+        ctx.set_tuning("pd_ty", 0)
+
+
+def test_primal_dual_tiling_independent():
+    """idempotence property: the result does not depend on z-chunk length / rows per CTA."""
+    rng = np.random.RandomState(11)
+    obs = rng.rand(70, 45, 136) * 255
+    ctx = _lib.context()
+    outs = []
+    try:
+        for zc, ty in ((0, 0), (8, 4), (16, 16), (64, 2), (3, 8)):
+            ctx.set_tuning("pd_zc", zc)
+            ctx.set_tuning("pd_ty", ty)
+            outs.append(run_pd(obs, reg="TV", data="L2", alpha=0.05, L2=12, iterations=10))
+    finally:
+        ctx.set_tuning("pd_zc", 0)
+        ctx.set_tuning("pd_ty", 0)
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0])
+
+
+def test_primal_dual_sweep_batched_vs_oracle(golden):
+    """BASELINE config 5 shape of work: alpha sweep batched into one launch per iteration."""
+    obs = golden("pd", "in/man_sp")
+    alphas = np.linspace(0.001, 0.05, 7)
+    for reg in ("TV", "HUBER", "TK1"):
+        s = make_pd(obs, reg=reg, data="L2", alpha=0.01, L2=8, iterations=40)
+        xs = s.run_sweep(alphas)
+        for i, a in enumerate(alphas):
+            ref = orc.primal_dual_denoise(obs.reshape(-1), obs.shape, reg=reg, data="L2", alpha=a, L2=8, iterations=40,
+                                          x_scale=float(obs.max()))
+            assert np.array_equal(xs[i], ref), (reg, a)
+
+
+def test_x_scale_invariance_pd():
+    """tests/solvers_test.py:102-352 property for the denoising wiring."""
+    rng = np.random.RandomState(2)
+    obs = rng.rand(40, 37) * 200 + 1
+    xs = float(obs.max())
+    r1 = run_pd(obs / xs, reg="TV", data="L2", alpha=0.05, L2=8, iterations=20, x_scale=1.0)
+    r2 = run_pd(obs, reg="TV", data="L2", alpha=0.05, L2=8, iterations=20, x_scale=xs)
+    assert round(np.linalg.norm(r2 - r1 * xs), 7) == 0
+
+
+def test_full_size_512_cube_locality_vs_oracle():
+    """BASELINE config 4 size (512^3): after k iterations a voxel depends on a radius-k
+    neighbourhood, so corners/faces of the full volume can be checked against the oracle run
+    on a crop with a (k+1)-voxel margin -- including the zero boundary on the low/high sides."""
+    n, k, core, m = 512, 3, 20, 5
+    rng = np.random.RandomState(1)
+    obs = rng.rand(n, n, n).astype(np.float64) * 255
+    xs = float(obs.max())
+    x = run_pd(obs, reg="TV", data="L2", alpha=0.05, L2=8, iterations=k, x_scale=xs).reshape(n, n, n)
+    x32 = run_pd(obs, reg="TV", data="L2", alpha=0.05, L2=8, iterations=k, x_scale=xs, dtype="float32").reshape(n, n, n)
+    for lo_side in (True, False):
+        sl = slice(0, core + m) if lo_side else slice(n - core - m, n)
+        inner = slice(0, core) if lo_side else slice(m, core + m)
+        crop = np.ascontiguousarray(obs[sl, sl, sl])
+        ref = orc.primal_dual_denoise(crop.reshape(-1), crop.shape, reg="TV", data="L2", alpha=0.05, L2=8,
+                                      iterations=k, x_scale=xs).reshape(crop.shape)
+        got = x[sl, sl, sl]
+        assert np.array_equal(got[inner, inner, inner], ref[inner, inner, inner])
+        assert rel_max(x32[sl, sl, sl][inner, inner, inner], ref[inner, inner, inner]) < F32_TOL
+    # interior block straddling tile (x: 64/128), row (y: 8) and chunk (z) seams
+    sl = slice(240, 240 + core + 2 * m)
+    crop = np.ascontiguousarray(obs[sl, sl, sl])
+    ref = orc.primal_dual_denoise(crop.reshape(-1), crop.shape, reg="TV", data="L2", alpha=0.05, L2=8,
+                                  iterations=k, x_scale=xs).reshape(crop.shape)
+    inner = slice(m, m + core)
+    assert np.array_equal(x[sl, sl, sl][inner, inner, inner], ref[inner, inner, inner])
+
+
+# ------------------------------------------------------------------ LSMR / Tikhonov / ADMM
+def deconv_callables(shape, var, spacing=None):
+    """nsol/application/run_deconvolution.py:109-129."""
+    dim = len(shape)
+    ops = linops(dim, spacing)
+    cov = var if dim == 1 else np.diag(var)
+    A, A_adj = ops.get_gaussian_blurring_operators(cov)
+    grad, grad_adj = ops.get_gradient_operators()
+    Z_shape = (dim * shape[0],) + tuple(shape[1:])
+    return (lambda x: A(x.reshape(*shape)).flatten(), lambda x: A_adj(x.reshape(*shape)).flatten(),
+            lambda x: grad(x.reshape(*shape)).flatten(), lambda x: grad_adj(x.reshape(*Z_shape)).flatten())
+
+
+@pytest.mark.parametrize("name", ["admm_1d", "admm_1d_xs1", "admm_2d", "admm_2d_c3crop", "admm_3d"])
+def test_admm_vs_reference(golden, name):
+    meta = golden.manifest["lsmr"][name]
+    obs = golden("lsmr", "in/" + meta["input"])
+    A, A_adj, D, D_adj = deconv_callables(obs.shape, meta["var"], meta["spacing"])
+    xs = meta["x_scale"] or float(obs.max())
+    s = admm.ADMMLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=D, B_adj=D_adj, x0=obs.flatten(), dimension=obs.ndim,
+                              alpha=meta["alpha"], rho=meta["rho"], iterations=meta["iterations"],
+                              iter_max=meta["iter_max"], x_scale=xs)
+    s.run()
+    ref = golden("lsmr", name)
+    assert rel_max(s.get_x(), ref) < F64_LSMR_TOL, (name, rel_max(s.get_x(), ref))
+    s32 = admm.ADMMLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=D, B_adj=D_adj, x0=obs.flatten(), dimension=obs.ndim,
+                                alpha=meta["alpha"], rho=meta["rho"], iterations=meta["iterations"],
+                                iter_max=meta["iter_max"], x_scale=xs, dtype="float32")
+    s32.run()
+    assert rel_max(s32.get_x(), ref) < 2e-3, (name, rel_max(s32.get_x(), ref))
+
+
+def test_admm_config3_lena512(golden):
+    """BASELINE config 3 at full size (5 outer x 10 LSMR iterations; float32 fixture -> 1e-6)."""
+    meta = golden.manifest["lsmr"]["admm_c3_lena512"]
+    obs = golden("lsmr", "in/lena512_f32").astype(np.float64)
+    A, A_adj, D, D_adj = deconv_callables(obs.shape, meta["var"])
+    s = admm.ADMMLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=D, B_adj=D_adj, x0=obs.flatten(), dimension=2,
+                              alpha=meta["alpha"], rho=meta["rho"], iterations=meta["iterations"],
+                              iter_max=meta["iter_max"], x_scale=float(obs.max()))
+    s.run()
+    # the stored input was rounded to float32, so compare with the oracle on the same rounded input
+    Ao, Ao_adj, Do, Do_adj = orc.deconvolution_operators(obs.shape, np.diag(meta["var"]))
+    ref = orc.admm_tv(Ao, Ao_adj, Do, Do_adj, obs.reshape(-1), obs.reshape(-1), 2, alpha=meta["alpha"], rho=meta["rho"],
+                      iterations=meta["iterations"], iter_max=meta["iter_max"], x_scale=float(obs.max()))
+    assert rel_max(s.get_x(), ref) < F64_LSMR_TOL
+    assert rel_max(s.get_x(), golden("lsmr", "admm_c3_lena512")) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["tk_1d_TK0", "tk_1d_TK1", "tk_2d_TK0", "tk_2d_TK1", "tk_3d_TK0", "tk_3d_TK1"])
+def test_tikhonov_vs_reference(golden, name):
+    meta = golden.manifest["lsmr"][name]
+    obs = golden("lsmr", "in/" + meta["input"])
+    A, A_adj, D, D_adj = deconv_callables(obs.shape, meta["var"])
+    ident = lambda x: x.flatten()
+    B, B_adj = (D, D_adj) if meta["reg"] == "TK1" else (ident, ident)
+    s = tk.TikhonovLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=B, B_adj=B_adj, x0=obs.flatten(), alpha=meta["alpha"],
+                                iter_max=meta["iter_max"], x_scale=float(obs.max()))
+    s.run()
+    assert rel_max(s.get_x(), golden("lsmr", name)) < F64_LSMR_TOL, (name, rel_max(s.get_x(), golden("lsmr", name)))
+
+
+def test_x_scale_invariance_admm_and_tikhonov(golden):
+    """tests/solvers_test.py:102-224 (1-D case), default hyper-parameters, accuracy 1e-7."""
+    obs = golden("lsmr", "in/spike1d")
+    xs = float(obs.max())
+    A, A_adj, D, D_adj = deconv_callables(obs.shape, 1.5)
+    res = {}
+    for tag, data, scale in (("scaled", obs / xs, 1.0), ("raw", obs, xs)):
+        t = tk.TikhonovLinearSolver(A=A, A_adj=A_adj, B=D, B_adj=D_adj, b=data.flatten(), x0=data.flatten(), x_scale=scale)
+        t.run()
+        a = admm.ADMMLinearSolver(A=A, A_adj=A_adj, B=D, B_adj=D_adj, b=data.flatten(), x0=data.flatten(), x_scale=scale,
+                                  dimension=1)
+        a.run()
+        res[tag] = (t.get_x(), a.get_x())
+    for i in range(2):
+        assert round(np.linalg.norm(res["raw"][i] - res["scaled"][i] * xs), 7) == 0
+
+
+def test_lsmr_edge_cases():
+    """zero right-hand side (lsmr.py:307-315) and maxiter = 0 return x = 0."""
+    shape = (12, 10)
+    A, A_adj, D, D_adj = deconv_callables(shape, [1.0, 1.0])
+    z = np.zeros(120)
+    t = tk.TikhonovLinearSolver(A=A, A_adj=A_adj, B=D, B_adj=D_adj, b=z, x0=z)
+    t.run()
+    assert np.array_equal(t.get_x(), z)
+    b = np.random.RandomState(0).rand(120)
+    t = tk.TikhonovLinearSolver(A=A, A_adj=A_adj, B=D, B_adj=D_adj, b=b, x0=b, iter_max=0)
+    t.run()
+    assert np.array_equal(t.get_x(), z)
