@@ -19,7 +19,7 @@ SOURCES = ["capi.cu", "ops_kernels.cu", "pd_kernels.cu", "lsmr_kernels.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: keep the reference's mul/add rounding sequence (float64 path is bit-identical to numpy)
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
-         "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+         "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC] + os.environ.get("NSOL_NVCC_FLAGS", "").split()
 
 
 def _digest():

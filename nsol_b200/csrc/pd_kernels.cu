@@ -43,32 +43,83 @@ struct PdArgs {
     int it, batch;
 };
 
+// a*b + c with the reference's two roundings in float64 (no contraction: the float64 path is
+// bit-identical to numpy); a fused multiply-add in float32 (tolerance 1e-4)
+__device__ __forceinline__ double madd(double a, double b, double c) { return __dadd_rn(__dmul_rn(a, b), c); }
+__device__ __forceinline__ float madd(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+
+// Division by a launch constant d.  float64: r = RN(1/d) once per thread, then q = x*r and two
+// FMA-exact Newton corrections (Markstein): the result is the correctly rounded quotient, i.e.
+// bit-identical to IEEE x / d, at 5 instructions instead of the ~30 of a DDIV sequence.
+// float32: x * r (within 1 ulp; the float32 mode is specified to 1e-4).
+template <typename T>
+struct ConstDiv;
+template <>
+struct ConstDiv<double> {
+    double d, r;
+    __device__ __forceinline__ explicit ConstDiv(double d_) : d(d_), r(1.0 / d_) {}
+    __device__ __forceinline__ double operator()(double x) const {
+        double q = __dmul_rn(x, r);
+        double e = __fma_rn(-q, d, x);
+        q = __fma_rn(e, r, q);
+        e = __fma_rn(-q, d, x);
+        return __fma_rn(e, r, q);
+    }
+};
+template <>
+struct ConstDiv<float> {
+    float r;
+    __device__ __forceinline__ explicit ConstDiv(float d_) : r(1.0f / d_) {}
+    __device__ __forceinline__ float operator()(float x) const { return x * r; }
+};
+
+// projection onto [-1, 1]: q / max(1, |q|) is q itself for |q| <= 1 and q/|q| = +-1 exactly
+// otherwise, so the reference's division (proximal_operators.py:140,159) is a clamp, bit for bit
+__device__ __forceinline__ double clamp_unit(double q) { return fmin(fmax(q, -1.0), 1.0); }
+__device__ __forceinline__ float clamp_unit(float q) { return fminf(fmaxf(q, -1.0f), 1.0f); }
+
 template <typename T, int REG>
-__device__ __forceinline__ T dual_update(T p, T hi, T lo, T w, T sigma, T den) {
+__device__ __forceinline__ T dual_update(T p, T hi, T lo, T w, T sigma, const ConstDiv<T> &div_g) {
     // grad: fl(fl(w*x[i+1]) + fl((-w)*x[i]))   (scipy.ndimage.convolve order)
-    T g = w * hi + (-w) * lo;
-    T q = p + sigma * g;                                     // primal_dual_solver.py:242-243
-    if (REG != NSOL_REG_TV) q = q / den;                     // proximal_operators.py:158 / TK1
-    if (REG != NSOL_REG_TK1) q = q / max_t(T(1), abs_t(q));  // proximal_operators.py:140,159
+    T g = madd(w, hi, (-w) * lo);
+    T q = madd(sigma, g, p);                                 // primal_dual_solver.py:242-243
+    if (REG != NSOL_REG_TV) q = div_g(q);                    // proximal_operators.py:158 / TK1
+    if (REG != NSOL_REG_TK1) q = clamp_unit(q);              // proximal_operators.py:140,159
     return q;
 }
 
 template <typename T, int DATA>
-__device__ __forceinline__ void primal_update(T xv, T bv, T div, T tau, T tl, T theta, T den_f, T &xn, T &xbn) {
-    T yv = xv - tau * div;                                   // primal_dual_solver.py:246
+__device__ __forceinline__ void primal_update(T xv, T bv, T div, T tau, T tl, T theta, const ConstDiv<T> &div_f, T &xn, T &xbn) {
+    T yv = madd(-tau, div, xv);                              // x - tau*div  (primal_dual_solver.py:246)
     if (DATA == NSOL_DATA_L2) {
-        xn = (yv + tl * bv) / den_f;                         // proximal_operators.py:120
+        xn = div_f(madd(tl, bv, yv));                        // (y + t b)/(1 + t)  (proximal_operators.py:120)
     } else {
         T d = yv - bv;                                       // proximal_operators.py:98
         T m = max_t(abs_t(d) - tl, T(0));
         T sgn = d > T(0) ? T(1) : (d < T(0) ? T(-1) : T(0));
-        xn = bv + m * sgn;
+        xn = madd(m, sgn, bv);
     }
-    xbn = xn + theta * (xn - xv);                            // primal_dual_solver.py:253
+    xbn = madd(theta, xn - xv, xn);                          // primal_dual_solver.py:253
 }
 
+// everything one thread loads for plane z: p, x, b at z; xbar at z+1 (own voxels and, if the CTA
+// also processes plane z+1, its x/y halos); the low-side halos of p needed to recompute p'
+template <typename T, int VEC>
+struct PdStep {
+    Vec<T, VEC> px, py, pz, x, b, xbn, hup, hdn, pydn;
+    T pxl, xr, xl;
+};
+
+// register budget: the float32 kernel fits 128 registers without spills (2 x 256 threads per SM
+// resident), the float64 kernel needs ~160 for its two in-flight planes of double2 loads
+#ifndef NSOL_PD_MINB_F64
+#define NSOL_PD_MINB_F64 1
+#endif
+#ifndef NSOL_PD_MINB_F32
+#define NSOL_PD_MINB_F32 2
+#endif
 template <typename T, int VEC, bool HAS_Y, int REG, int DATA>
-__global__ void __launch_bounds__(512) pd_iter_kernel(const PdArgs<T> a) {
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : NSOL_PD_MINB_F64) pd_iter_kernel(const PdArgs<T> a) {
     using V = Vec<T, VEC>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -85,19 +136,19 @@ __global__ void __launch_bounds__(512) pd_iter_kernel(const PdArgs<T> a) {
     const int z1 = min(a.nz, z0 + a.zc);
     const bool xin = x0 < a.nx;
     const bool active = xin && (y < a.ny);
+    const bool has_z = a.has_z != 0;
 
     const double *srow = a.sched + ((long long)a.it * a.batch + bz) * 8;
     const T sigma = (T)srow[0], tau = (T)srow[1], tl = (T)srow[2], theta = (T)srow[3];
-    const T den_g = (T)srow[4], den_f = (T)srow[5];
+    const ConstDiv<T> div_g((T)srow[4]), div_f((T)srow[5]);
     const T wx = a.wx, wy = a.wy, wz = a.wz;
 
     const long long sz = (long long)a.nx * a.ny;
-    const long long vol = (long long)bz * a.n;
-    const long long row = (long long)y * a.nx + x0;          // offset inside a plane
-    const long long hrow = (long long)bz * sz + row;          // offset inside a halo plane array
-
-    const T *xbar = a.xbar_in + vol;
-    const T *bobs = a.b + (long long)bz * a.b_stride;
+    const long long row = (long long)y * a.nx + x0;               // offset inside a plane
+    const long long hrow = (long long)bz * sz + row;               // offset inside a halo plane array
+    // running element offsets of plane z (advanced by sz per plane: no 64-bit multiplies in the loop)
+    long long off = (long long)bz * a.n + (long long)z0 * sz + row;   // into x, xbar, p
+    long long boff = (long long)bz * a.b_stride + (long long)z0 * sz + row;   // into b
 
     // shared tiles (3-D only): xbar rows [2][TY+2][tile_w], p'_y rows [2][TY+1][tile_w]
     T *s_xb = reinterpret_cast<T *>(smem_raw);
@@ -112,71 +163,69 @@ __global__ void __launch_bounds__(512) pd_iter_kernel(const PdArgs<T> a) {
     const bool need_up = up_warp && xin && (y + 1 < a.ny);
     const bool need_dn = dn_warp && active && (y > 0);
 
-    // xbar plane z of this problem; planes -1 and nz come from the slab halos (or are 0)
-    auto load_xbar_own = [&](int z) -> V {
-        if (!active) return vec_zero<T, VEC>();
-        if (z >= 0 && z < a.nz) return vec_load<T, VEC>(xbar + (long long)z * sz + row);
-        if (z < 0 && a.halo_xbar_below) return vec_load<T, VEC>(a.halo_xbar_below + hrow);
-        if (z >= a.nz && a.halo_xbar_above) return vec_load<T, VEC>(a.halo_xbar_above + hrow);
-        return vec_zero<T, VEC>();
+    // own voxels of xbar plane zq located at element offset o; planes -1 / nz come from the z-slab
+    // halos of the neighbouring rank (or are the zero boundary)
+    auto load_xbar_own = [&](int zq, long long o) -> V {
+        const T *ptr = a.xbar_in + o;
+        if (zq < 0) ptr = a.halo_xbar_below ? a.halo_xbar_below + hrow : nullptr;
+        if (zq >= a.nz) ptr = a.halo_xbar_above ? a.halo_xbar_above + hrow : nullptr;
+        return (active && ptr) ? vec_load<T, VEC>(ptr) : vec_zero<T, VEC>();
+    };
+    // loads of plane zq whose offsets are o (x, xbar, p) and bo (b).  Only xbn must be zero in
+    // inactive threads (it supplies the Dirichlet zero to the neighbours); the other fields of an
+    // inactive thread are never stored.
+    auto load_step = [&](int zq, long long o, long long bo, PdStep<T, VEC> &s) {
+        s.xbn = has_z ? load_xbar_own(zq + 1, o + sz) : vec_zero<T, VEC>();
+        if (active) {
+            s.px = vec_load<T, VEC>(a.px_in + o);
+            if (HAS_Y) s.py = vec_load<T, VEC>(a.py_in + o);
+            if (has_z) s.pz = vec_load<T, VEC>(a.pz_in + o);
+            s.x = vec_load<T, VEC>(a.x + o);
+            s.b = vec_load<T, VEC>(a.b + bo);
+        }
+        s.pxl = need_l ? a.px_in[o - 1] : T(0);
+        if (need_dn) s.pydn = vec_load<T, VEC>(a.py_in + o - a.nx);
+        const bool nx_plane = zq + 1 < z1;     // halos of the next plane (only if this CTA processes it)
+        s.xr = (need_r && nx_plane) ? a.xbar_in[o + sz + VEC] : T(0);
+        s.xl = (need_l && nx_plane) ? a.xbar_in[o + sz - 1] : T(0);
+        s.hup = (need_up && nx_plane) ? vec_load<T, VEC>(a.xbar_in + o + sz + a.nx) : vec_zero<T, VEC>();
+        s.hdn = (need_dn && nx_plane) ? vec_load<T, VEC>(a.xbar_in + o + sz - a.nx) : vec_zero<T, VEC>();
     };
 
     // ---- prologue: plane z0 --------------------------------------------------
-    V xb_c = load_xbar_own(z0);
-    T xr_c = need_r ? xbar[(long long)z0 * sz + row + VEC] : T(0);
-    T xl_c = need_l ? xbar[(long long)z0 * sz + row - 1] : T(0);
+    PdStep<T, VEC> cur;
+    load_step(z0, off, boff, cur);
+    V xb_c = load_xbar_own(z0, off);
+    T xr_c = need_r ? a.xbar_in[off + VEC] : T(0);
+    T xl_c = need_l ? a.xbar_in[off - 1] : T(0);
     V pz_prev = vec_zero<T, VEC>();
-    if (a.has_z && active && (z0 > 0 || a.halo_pz_below)) {
-        V xb_m = load_xbar_own(z0 - 1);
-        V pz_m = z0 > 0 ? vec_load<T, VEC>(a.pz_in + vol + (long long)(z0 - 1) * sz + row)
-                        : vec_load<T, VEC>(a.halo_pz_below + hrow);
+    if (has_z && active && (z0 > 0 || a.halo_pz_below)) {
+        V xb_m = load_xbar_own(z0 - 1, off - sz);
+        V pz_m = z0 > 0 ? vec_load<T, VEC>(a.pz_in + off - sz) : vec_load<T, VEC>(a.halo_pz_below + hrow);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) pz_prev.v[v] = dual_update<T, REG>(pz_m.v[v], xb_c.v[v], xb_m.v[v], wz, sigma, den_g);
+        for (int v = 0; v < VEC; ++v) pz_prev.v[v] = dual_update<T, REG>(pz_m.v[v], xb_c.v[v], xb_m.v[v], wz, sigma, div_g);
     }
     if (HAS_Y) {
         T *buf = s_xb + (z0 & 1) * (TY + 2) * tile_w;
         vec_store<T, VEC>(buf + (ty + 1) * tile_w + s_col, xb_c);
         if (up_warp) {
-            V h = need_up ? vec_load<T, VEC>(xbar + (long long)z0 * sz + row + a.nx) : vec_zero<T, VEC>();
+            V h = need_up ? vec_load<T, VEC>(a.xbar_in + off + a.nx) : vec_zero<T, VEC>();
             vec_store<T, VEC>(buf + (TY + 1) * tile_w + s_col, h);
         }
         if (dn_warp) {
-            V h = need_dn ? vec_load<T, VEC>(xbar + (long long)z0 * sz + row - a.nx) : vec_zero<T, VEC>();
+            V h = need_dn ? vec_load<T, VEC>(a.xbar_in + off - a.nx) : vec_zero<T, VEC>();
             vec_store<T, VEC>(buf + s_col, h);
         }
         __syncthreads();
     }
 
-    // ---- march through the chunk ---------------------------------------------
-    for (int z = z0; z < z1; ++z) {
-        const long long pl = vol + (long long)z * sz + row;
+    // ---- march through the chunk (software pipelined: loads of plane z+1 are in flight
+    //      while plane z is computed) ------------------------------------------------------
+    // One plane: `cur` holds the loads of plane z, `nxt` receives those of plane z+1.  The loop
+    // below calls it with the two register sets swapped on alternate planes, so no state is copied.
+    auto plane_step = [&](int z, PdStep<T, VEC> &cur, PdStep<T, VEC> &nxt) {
         const bool more = (z + 1 < z1);   // plane z+1 is processed by this CTA
-
-        // global loads: next xbar plane (own voxels), this plane's p, x, b
-        V xb_n = a.has_z ? load_xbar_own(z + 1) : vec_zero<T, VEC>();
-        V pxv = vec_zero<T, VEC>(), pyv = vec_zero<T, VEC>(), pzv = vec_zero<T, VEC>();
-        V xv = vec_zero<T, VEC>(), bv = vec_zero<T, VEC>();
-        T pxl = T(0);
-        V pydn = vec_zero<T, VEC>();
-        if (active) {
-            pxv = vec_load<T, VEC>(a.px_in + pl);
-            if (HAS_Y) pyv = vec_load<T, VEC>(a.py_in + pl);
-            if (a.has_z) pzv = vec_load<T, VEC>(a.pz_in + pl);
-            xv = vec_load<T, VEC>(a.x + pl);
-            bv = vec_load<T, VEC>(bobs + (long long)z * sz + row);
-        }
-        if (need_l) pxl = a.px_in[pl - 1];
-        if (need_dn) pydn = vec_load<T, VEC>(a.py_in + pl - a.nx);
-        // halos of the next plane (only if this CTA processes it)
-        T xr_n = T(0), xl_n = T(0);
-        V hup_n = vec_zero<T, VEC>(), hdn_n = vec_zero<T, VEC>();
-        if (more) {
-            const long long pn = (long long)(z + 1) * sz + row;
-            if (need_r) xr_n = xbar[pn + VEC];
-            if (need_l) xl_n = xbar[pn - 1];
-            if (need_up) hup_n = vec_load<T, VEC>(xbar + pn + a.nx);
-            if (need_dn) hdn_n = vec_load<T, VEC>(xbar + pn - a.nx);
-        }
+        if (more) load_step(z + 1, off + sz, boff + sz, nxt);
 
         // neighbours of the current plane
         V xup = vec_zero<T, VEC>(), xdn = vec_zero<T, VEC>();
@@ -195,18 +244,18 @@ __global__ void __launch_bounds__(512) pd_iter_kernel(const PdArgs<T> a) {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             T hi = (v + 1 < VEC) ? xb_c.v[(v + 1) % VEC] : x_right;
-            pnx.v[v] = dual_update<T, REG>(pxv.v[v], hi, xb_c.v[v], wx, sigma, den_g);
-            if (HAS_Y) pny.v[v] = dual_update<T, REG>(pyv.v[v], xup.v[v], xb_c.v[v], wy, sigma, den_g);
-            if (a.has_z) pnz.v[v] = dual_update<T, REG>(pzv.v[v], xb_n.v[v], xb_c.v[v], wz, sigma, den_g);
+            pnx.v[v] = dual_update<T, REG>(cur.px.v[v], hi, xb_c.v[v], wx, sigma, div_g);
+            if (HAS_Y) pny.v[v] = dual_update<T, REG>(cur.py.v[v], xup.v[v], xb_c.v[v], wy, sigma, div_g);
+            if (has_z) pnz.v[v] = dual_update<T, REG>(cur.pz.v[v], cur.xbn.v[v], xb_c.v[v], wz, sigma, div_g);
         }
         if (active) {
-            vec_store<T, VEC>(a.px_out + pl, pnx);
-            if (HAS_Y) vec_store<T, VEC>(a.py_out + pl, pny);
-            if (a.has_z) vec_store<T, VEC>(a.pz_out + pl, pnz);
+            vec_store<T, VEC>(a.px_out + off, pnx);
+            if (HAS_Y) vec_store<T, VEC>(a.py_out + off, pny);
+            if (has_z) vec_store<T, VEC>(a.pz_out + off, pnz);
         }
         // p'_x of the voxel left of this thread's first voxel
         T pnx_left = shfl_up_t(pnx.v[VEC - 1], 1);
-        if (lane == 0) pnx_left = need_l ? dual_update<T, REG>(pxl, xb_c.v[0], xl_c, wx, sigma, den_g) : T(0);
+        if (lane == 0) pnx_left = need_l ? dual_update<T, REG>(cur.pxl, xb_c.v[0], xl_c, wx, sigma, div_g) : T(0);
 
         V pny_dn = vec_zero<T, VEC>();
         if (HAS_Y) {
@@ -216,14 +265,14 @@ __global__ void __launch_bounds__(512) pd_iter_kernel(const PdArgs<T> a) {
                 V h = vec_zero<T, VEC>();
                 if (need_dn) {
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) h.v[v] = dual_update<T, REG>(pydn.v[v], xb_c.v[v], xdn.v[v], wy, sigma, den_g);
+                    for (int v = 0; v < VEC; ++v) h.v[v] = dual_update<T, REG>(cur.pydn.v[v], xb_c.v[v], xdn.v[v], wy, sigma, div_g);
                 }
                 vec_store<T, VEC>(pbuf + s_col, h);
             }
             if (more) {
-                vec_store<T, VEC>(xbuf_n + (ty + 1) * tile_w + s_col, xb_n);
-                if (up_warp) vec_store<T, VEC>(xbuf_n + (TY + 1) * tile_w + s_col, hup_n);
-                if (dn_warp) vec_store<T, VEC>(xbuf_n + s_col, hdn_n);
+                vec_store<T, VEC>(xbuf_n + (ty + 1) * tile_w + s_col, cur.xbn);
+                if (up_warp) vec_store<T, VEC>(xbuf_n + (TY + 1) * tile_w + s_col, cur.hup);
+                if (dn_warp) vec_store<T, VEC>(xbuf_n + s_col, cur.hdn);
             }
             __syncthreads();
             pny_dn = vec_load<T, VEC>(pbuf + ty * tile_w + s_col);
@@ -234,20 +283,27 @@ __global__ void __launch_bounds__(512) pd_iter_kernel(const PdArgs<T> a) {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             T lo = (v == 0) ? pnx_left : pnx.v[(v + VEC - 1) % VEC];
-            T div = wx * lo + (-wx) * pnx.v[v];                          // Dx^T p_x
-            if (HAS_Y) div = div + (wy * pny_dn.v[v] + (-wy) * pny.v[v]);   // += Dy^T p_y
-            if (a.has_z) div = div + (wz * pz_prev.v[v] + (-wz) * pnz.v[v]); // += Dz^T p_z
-            primal_update<T, DATA>(xv.v[v], bv.v[v], div, tau, tl, theta, den_f, xnew.v[v], xbnew.v[v]);
+            T div = madd(wx, lo, (-wx) * pnx.v[v]);                                   // Dx^T p_x
+            if (HAS_Y) div = div + madd(wy, pny_dn.v[v], (-wy) * pny.v[v]);            // += Dy^T p_y
+            if (has_z) div = div + madd(wz, pz_prev.v[v], (-wz) * pnz.v[v]);           // += Dz^T p_z
+            primal_update<T, DATA>(cur.x.v[v], cur.b.v[v], div, tau, tl, theta, div_f, xnew.v[v], xbnew.v[v]);
         }
         if (active) {
-            vec_store<T, VEC>(a.x + pl, xnew);
-            vec_store<T, VEC>(a.xbar_out + pl, xbnew);
+            vec_store<T, VEC>(a.x + off, xnew);
+            vec_store<T, VEC>(a.xbar_out + off, xbnew);
         }
 
-        xb_c = xb_n;
+        xb_c = cur.xbn;
         pz_prev = pnz;
-        xr_c = xr_n;
-        xl_c = xl_n;
+        xr_c = cur.xr;
+        xl_c = cur.xl;
+        off += sz;
+        boff += sz;
+    };
+    PdStep<T, VEC> alt;
+    for (int z = z0; z < z1; z += 2) {
+        plane_step(z, cur, alt);
+        if (z + 1 < z1) plane_step(z + 1, alt, cur);
     }
 }
 
@@ -556,9 +612,9 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s) {
     size_t smem = 0;
     int ty = 1;
     if (has_y) {
-        ty = ctx->pd_ty ? ctx->pd_ty : 8;
-        if (ty < 2) ty = 2;
-        if (ty > 16) ty = 16;
+        ty = ctx->pd_ty ? ctx->pd_ty : 2;
+        if (ty < 1) ty = 1;
+        if (ty > 8) ty = 8;
         block = dim3(32, ty, 1);
         smem = (size_t)(2 * (ty + 2) + 2 * (ty + 1)) * 32 * VECW * sizeof(T);
     } else {
@@ -571,13 +627,11 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s) {
     // to give every SM several CTAs
     int zc = ctx->pd_zc;
     if (zc <= 0) {
+        // measured on B200 at 512^3 (profiles/r1_tuning.md): 16 planes per chunk for float32, 32 for
+        // float64; shorter chunks only when the volume would otherwise give fewer than ~4 CTAs per SM
+        zc = sizeof(T) == 4 ? 16 : 32;
         const long long tiles = (long long)grid.x * grid.y * gv.batch;
-        const long long want = (long long)ctx->sm_count * 16;   // CTAs
-        long long chunks = (want + tiles - 1) / tiles;
-        if (chunks < 1) chunks = 1;
-        zc = (int)((gv.nz + chunks - 1) / chunks);
-        if (zc < 8) zc = 8;
-        if (zc > 64) zc = 64;
+        while (zc > 4 && tiles * ((gv.nz + zc - 1) / zc) < (long long)ctx->sm_count * 4) zc /= 2;
     }
     if (zc > gv.nz) zc = gv.nz;
     a.zc = zc;
