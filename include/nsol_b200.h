@@ -96,6 +96,7 @@ int nsol_host_alloc(nsol_ctx *ctx, size_t bytes, void **host); /* pinned */
 int nsol_host_free(nsol_ctx *ctx, void *host);
 int nsol_memcpy_h2d(nsol_ctx *ctx, void *dev, const void *host, size_t bytes, nsol_stream s);
 int nsol_memcpy_d2h(nsol_ctx *ctx, void *host, const void *dev, size_t bytes, nsol_stream s);
+int nsol_memcpy_d2d(nsol_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes, nsol_stream s);
 int nsol_memset_dev(nsol_ctx *ctx, void *dev, int value, size_t bytes, nsol_stream s);
 int nsol_stream_sync(nsol_ctx *ctx, nsol_stream s);
 /* out[i] = (T_out)(in[i] * mul)  resp.  (T_out)(in[i] / div); dtypes are nsol_dtype */

@@ -58,6 +58,7 @@ SIGNATURES = {
     "nsol_host_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nsol_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nsol_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nsol_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nsol_memset_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),
     "nsol_stream_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nsol_scale_convert": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p,

@@ -89,6 +89,12 @@ extern "C" int nsol_memcpy_d2h(nsol_ctx *ctx, void *host, const void *dev, size_
     NSOL_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)s));
     return NSOL_OK;
 }
+extern "C" int nsol_memcpy_d2d(nsol_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes, nsol_stream s) {
+    if (!ctx) return NSOL_EINVAL;
+    NSOL_CHECK(nsol_bind_device(ctx));
+    NSOL_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)s));
+    return NSOL_OK;
+}
 extern "C" int nsol_memset_dev(nsol_ctx *ctx, void *dev, int value, size_t bytes, nsol_stream s) {
     if (!ctx) return NSOL_EINVAL;
     NSOL_CHECK(nsol_bind_device(ctx));

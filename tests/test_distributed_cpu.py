@@ -1,0 +1,140 @@
+"""Multi-process host logic on CPU (gloo, world_size 2 and 3): z-slab bounds, the 3-plane
+halo exchange protocol of nsol_b200/distributed.py and the round-robin partition of sweep
+points.  The local compute is a numpy slab iteration built from the oracle (test
+infrastructure); the sharded run must reproduce the unsharded oracle bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import nsol_oracle as orc
+from nsol_b200.distributed import HaloExchanger, partition_round_robin, slab_bounds
+
+
+def test_slab_bounds_and_partition():
+    for nz, world in ((512, 8), (10, 3), (5, 5), (7, 2)):
+        spans = [slab_bounds(nz, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == nz
+        for a, b in zip(spans[:-1], spans[1:]):
+            assert a[1] == b[0]
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+    items = sorted(i for r in range(8) for i in partition_round_robin(192, r, 8))
+    assert items == list(range(192))
+    assert len(partition_round_robin(192, 3, 8)) == 24     # BASELINE config 5: 24 runs per GPU
+
+
+def slab_iteration(x, xbar, p, b, sched_row, xbar_above, xbar_below, pz_below, data="L2"):
+    """One primal-dual iteration on a z-slab given the neighbours' boundary planes (or None at
+    the global ends).  Same arithmetic as oracle.primal_dual_denoise, unit spacing, TV."""
+    sigma, tau, tl, theta = sched_row
+    nzl = x.shape[0]
+    top = np.zeros_like(xbar[:1]) if xbar_above is None else xbar_above[None]
+    ext = np.concatenate([xbar, top])                       # planes z_lo .. z_hi
+    g = orc.grad(ext)
+    n_ext = ext.shape[0]
+    gx, gy, gz = g[:n_ext][:nzl], g[n_ext:2 * n_ext][:nzl], g[2 * n_ext:][:nzl]
+    pn = [orc.prox_tv_conj(p[k] + sigma * gk, sigma) for k, gk in enumerate((gx, gy, gz))]
+    if pz_below is None:
+        pz_m = np.zeros_like(xbar[:1])
+    else:
+        pz_m = orc.prox_tv_conj(pz_below[None] + sigma * (1.0 * xbar[:1] + (-1.0) * xbar_below[None]), sigma)
+    div = orc.forward_difference_adj(pn[0], 0) + orc.forward_difference_adj(pn[1], 1)
+    div = div + orc.forward_difference_adj(np.concatenate([pz_m, pn[2]]), 2)[1:]
+    y = x - tau * div
+    xn = (y + tl * b) / (1.0 + tl)
+    xbn = xn + theta * (xn - x)
+    return xn, xbn, pn
+
+
+def _worker(rank, world, port, shape, iterations, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.RandomState(7)
+    vol = rng.rand(*shape) * 255
+    xs = float(vol.max())
+    z_lo, z_hi = slab_bounds(shape[0], rank, world)
+    b = vol[z_lo:z_hi] / xs
+    x = b.copy()
+    xbar = b.copy()
+    p = [np.zeros_like(b) for _ in range(3)]
+    sched = orc.pd_schedule("ALG2", 8.0, 0.05, iterations)
+    plane = shape[1] * shape[2]
+    halo = HaloExchanger(rank, world, plane, torch.float64, torch.device("cpu"))
+    as_t = lambda a: torch.from_numpy(np.ascontiguousarray(a).reshape(-1))
+    for it in range(iterations):
+        halo.exchange(as_t(xbar[0]), as_t(xbar[-1]), as_t(p[2][-1]))
+        above = halo.xbar_above.numpy().reshape(shape[1:]) if halo.has_above else None
+        below = halo.xbar_below.numpy().reshape(shape[1:]) if halo.has_below else None
+        pzb = halo.pz_below.numpy().reshape(shape[1:]) if halo.has_below else None
+        x, xbar, p = slab_iteration(x, xbar, p, b, sched[it], above, below, pzb)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (z_lo, x * xs))
+    if rank == 0:
+        full = np.concatenate([g[1] for g in sorted(gathered, key=lambda t: t[0])])
+        np.save(out, full)
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_zslab_halo_exchange_reproduces_unsharded_oracle(tmp_path, world):
+    import torch.multiprocessing as mp
+    shape, iterations = (11, 6, 7), 6
+    out = str(tmp_path / "sharded.npy")
+    mp.spawn(_worker, args=(world, _free_port(), shape, iterations, out), nprocs=world, join=True)
+    rng = np.random.RandomState(7)
+    vol = rng.rand(*shape) * 255
+    ref = orc.primal_dual_denoise(vol.reshape(-1), shape, reg="TV", data="L2", alpha=0.05, L2=8.0,
+                                  iterations=iterations, x_scale=float(vol.max()))
+    assert np.array_equal(np.load(out).reshape(-1), ref)
+
+
+def _study_worker(rank, world, port, directory):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from test_parameter_study import _make
+    solver, study = _make(directory)
+    study.run()
+    # every rank ran only its round-robin share of the 6 points
+    runs = [c for c in solver.calls if c != "set_x0"]
+    assert len(runs) == len(partition_round_robin(6, rank, world))
+    dist.destroy_process_group()
+
+
+def test_parameter_study_fans_out_over_ranks(tmp_path):
+    """BASELINE config 5: sweep points are independent -> dealt round-robin to the ranks, no
+    data-path communication; rank 0 gathers and writes the same files as a single process."""
+    import torch.multiprocessing as mp
+    from nsol_b200.reader_parameter_study import ReaderParameterStudy
+    from test_parameter_study import _make
+    multi = tmp_path / "multi"
+    single = tmp_path / "single"
+    multi.mkdir()
+    single.mkdir()
+    mp.spawn(_study_worker, args=(2, _free_port(), str(multi)), nprocs=2, join=True)
+    _, study = _make(str(single))
+    study.run()
+    a = ReaderParameterStudy(str(multi), "Stub")
+    b = ReaderParameterStudy(str(single), "Stub")
+    a.read_study()
+    b.read_study()
+    assert a.get_parameters_to_line() == b.get_parameters_to_line()
+    assert np.array_equal(a.get_results("SUM"), b.get_results("SUM"))
+    ra, rb = a.get_reconstructions(), b.get_reconstructions()
+    assert sorted(ra.files) == sorted(rb.files)
+    for k in ra.files:
+        assert np.array_equal(ra[k], rb[k])

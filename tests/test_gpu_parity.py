@@ -355,3 +355,71 @@ def test_lsmr_edge_cases():
     t = tk.TikhonovLinearSolver(A=A, A_adj=A_adj, B=D, B_adj=D_adj, b=b, x0=b, iter_max=0)
     t.run()
     assert np.array_equal(t.get_x(), z)
+
+
+# ------------------------------------------------------------------ z-slab decomposition (single-GPU emulation)
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("nslabs", [2, 3])
+def test_zslab_emulation_matches_unsharded(dtype, nslabs):
+    """run S z-slabs one after another on one GPU with explicit halo planes
+    (exactly the buffers the NCCL exchange fills on S GPUs) and compare with the unsharded run
+    bit for bit."""
+    import ctypes as C
+    from nsol_b200.distributed import slab_bounds
+    rng = np.random.RandomState(3)
+    shape = (23, 10, 68)
+    iters = 9
+    obs = rng.rand(*shape) * 255
+    xs = float(obs.max())
+    ref = run_pd(obs, reg="TV", data="L2", alpha=0.05, L2=8, iterations=iters, x_scale=xs, dtype=dtype)
+
+    ctx = _lib.context()
+    lib = ctx.lib
+    dcode = _lib.dtype_code(dtype)
+    esz = 4 if dcode == _lib.F32 else 8
+    plane = shape[1] * shape[2]
+    alpha = np.array([0.05])
+    plans, halos, spans = [], [], []
+    for r in range(nslabs):
+        z_lo, z_hi = slab_bounds(shape[0], r, nslabs)
+        spans.append((z_lo, z_hi))
+        desc = _lib.PdDesc()
+        desc.grid = _lib.make_grid((z_hi - z_lo,) + shape[1:], None, dcode, 1)
+        desc.reg, desc.data, desc.alg = _lib.REG["TV"], _lib.DATA["L2"], _lib.ALG["ALG2"]
+        desc.huber_gamma, desc.L2 = 0.05, 8.0
+        desc.x_scale = desc.x0_scale = desc.b_scale = xs
+        desc.alpha = alpha.ctypes.data_as(_lib.c_double_p)
+        h = C.c_void_p()
+        ctx.check(lib.nsol_pd_plan_create(ctx.handle, C.byref(desc), C.byref(h)))
+        plans.append(h)
+        bufs = {k: ctx.device_alloc(plane * esz) for k in ("above", "below", "pz_below")}
+        halos.append(bufs)
+        ctx.check(lib.nsol_pd_plan_set_halo(h, bufs["above"].ptr if r < nslabs - 1 else None,
+                                            bufs["below"].ptr if r > 0 else None,
+                                            bufs["pz_below"].ptr if r > 0 else None))
+        slab = np.ascontiguousarray(obs[z_lo:z_hi]).reshape(-1)
+        ctx.check(lib.nsol_pd_plan_reset_host(h, slab.ctypes.data, None, None))
+    try:
+        for _ in range(iters):
+            bounds = []
+            for h in plans:
+                a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+                ctx.check(lib.nsol_pd_plan_boundary_planes(h, C.byref(a), C.byref(b), C.byref(c)))
+                bounds.append((a, b, c))
+            for r in range(nslabs):
+                if r < nslabs - 1:      # from the upper neighbour: its first xbar plane
+                    ctx.check(lib.nsol_memcpy_d2d(ctx.handle, halos[r]["above"].ptr, bounds[r + 1][0], plane * esz, None))
+                if r > 0:               # from the lower neighbour: its last xbar and p_z planes
+                    ctx.check(lib.nsol_memcpy_d2d(ctx.handle, halos[r]["below"].ptr, bounds[r - 1][1], plane * esz, None))
+                    ctx.check(lib.nsol_memcpy_d2d(ctx.handle, halos[r]["pz_below"].ptr, bounds[r - 1][2], plane * esz, None))
+            for h in plans:
+                ctx.check(lib.nsol_pd_plan_iterate(h, 1, None))
+        parts = []
+        for (z_lo, z_hi), h in zip(spans, plans):
+            out = np.empty((z_hi - z_lo) * plane)
+            ctx.check(lib.nsol_pd_plan_get_x_host(h, out.ctypes.data, None))
+            parts.append(out)
+    finally:
+        for h in plans:
+            lib.nsol_pd_plan_destroy(h)
+    assert np.array_equal(np.concatenate(parts), ref)
