@@ -1,4 +1,6 @@
 // capi.cu -- context, memory/stream helpers and element-wise conversion kernels.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 thread_local std::string g_nsol_create_error;
@@ -30,6 +32,10 @@ extern "C" int nsol_create(int device, nsol_ctx **out) {
     nsol_ctx *ctx = new nsol_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    // tuning overrides from the environment (same keys as nsol_set_tuning, upper case)
+    if (const char *v = getenv("NSOL_PD_VARIANT")) ctx->pd_variant = atoi(v);
+    if (const char *v = getenv("NSOL_PD_TY")) ctx->pd_ty = atoi(v);
+    if (const char *v = getenv("NSOL_PD_ZC")) ctx->pd_zc = atoi(v);
     *out = ctx;
     return NSOL_OK;
 }

@@ -307,6 +307,15 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : NSOL_
     }
 }
 
+#include "pd_bulk_kernel.cuh"
+
+#ifndef NSOL_PD_DEFAULT_VARIANT_F64
+#define NSOL_PD_DEFAULT_VARIANT_F64 2
+#endif
+#ifndef NSOL_PD_DEFAULT_VARIANT_F32
+#define NSOL_PD_DEFAULT_VARIANT_F32 1
+#endif
+
 // ---------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------
@@ -575,6 +584,32 @@ static void pd_launch_rd(const nsol_pd_plan *pl, const PdArgs<T> &a, dim3 grid, 
 #undef NSOL_PD_CASE
 }
 
+// bulk-async (TMA) staged variant: 3-D, vector path only
+template <typename T, int VEC>
+static int pd_launch_bulk(const nsol_pd_plan *pl, const PdArgs<T> &a, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
+    const int reg = pl->desc.reg, data = pl->desc.data;
+#define NSOL_PD_CASE(R, D)                                                                              \
+    if (reg == R && data == D) {                                                                        \
+        static size_t configured = 0;                                                                   \
+        if (smem > configured) {                                                                        \
+            cudaError_t e = cudaFuncSetAttribute(pd_iter_bulk_kernel<T, VEC, R, D>,                     \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return nsol_fail(pl->ctx, NSOL_ECUDA, "pd bulk: smem opt-in %zu -> %s", smem, cudaGetErrorString(e)); \
+            configured = smem;                                                                          \
+        }                                                                                               \
+        pd_iter_bulk_kernel<T, VEC, R, D><<<grid, block, smem, s>>>(a);                                 \
+        return NSOL_OK;                                                                                 \
+    }
+    NSOL_PD_CASE(NSOL_REG_TV, NSOL_DATA_L2)
+    NSOL_PD_CASE(NSOL_REG_TV, NSOL_DATA_L1)
+    NSOL_PD_CASE(NSOL_REG_HUBER, NSOL_DATA_L2)
+    NSOL_PD_CASE(NSOL_REG_HUBER, NSOL_DATA_L1)
+    NSOL_PD_CASE(NSOL_REG_TK1, NSOL_DATA_L2)
+    NSOL_PD_CASE(NSOL_REG_TK1, NSOL_DATA_L1)
+#undef NSOL_PD_CASE
+    return NSOL_EINVAL;
+}
+
 template <typename T, int VECW>
 static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s) {
     nsol_ctx *ctx = pl->ctx;
@@ -627,9 +662,9 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s) {
     // to give every SM several CTAs
     int zc = ctx->pd_zc;
     if (zc <= 0) {
-        // measured on B200 at 512^3 (profiles/r1_tuning.md): 16 planes per chunk for float32, 32 for
-        // float64; shorter chunks only when the volume would otherwise give fewer than ~4 CTAs per SM
-        zc = sizeof(T) == 4 ? 16 : 32;
+        // measured on B200 at 512^3 (profiles/r1_tuning.md): 16 planes per chunk; shorter chunks only
+        // when the volume would otherwise give fewer than ~4 CTAs per SM
+        zc = 16;
         const long long tiles = (long long)grid.x * grid.y * gv.batch;
         while (zc > 4 && tiles * ((gv.nz + zc - 1) / zc) < (long long)ctx->sm_count * 4) zc /= 2;
     }
@@ -639,8 +674,18 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s) {
     const long long gz = (long long)a.nchunks * gv.batch;
     if (gz > 65535) return nsol_fail(ctx, NSOL_EINVAL, "pd: nchunks*batch = %lld exceeds the grid limit; raise pd_zc", gz);
     grid.z = (unsigned)gz;
-    if (has_y) pd_launch_rd<T, VECW, true>(pl, a, grid, block, smem, s);
-    else pd_launch_rd<T, VECW, false>(pl, a, grid, block, smem, s);
+    // kernel variant: 1 = register-pipelined loads (LDG), 2 = TMA bulk-async staged tiles;
+    // default: bulk for float64 3-D volumes (issue-bound with LDG), LDG otherwise
+    int variant = ctx->pd_variant;
+    if (variant == 0) variant = (sizeof(T) == 8) ? NSOL_PD_DEFAULT_VARIANT_F64 : NSOL_PD_DEFAULT_VARIANT_F32;
+    if (variant == 2 && has_y && VECW > 1) {
+        smem = PdBulkLayout<T, (VECW > 1 ? VECW : 2)>::bytes(ty, NSOL_PD_STAGES);
+        NSOL_CHECK((pd_launch_bulk<T, (VECW > 1 ? VECW : 2)>(pl, a, grid, block, smem, s)));
+    } else if (has_y) {
+        pd_launch_rd<T, VECW, true>(pl, a, grid, block, smem, s);
+    } else {
+        pd_launch_rd<T, VECW, false>(pl, a, grid, block, smem, s);
+    }
     NSOL_LAUNCH_CHECK(ctx);
     pl->cur = nxt;
     pl->it += 1;

@@ -181,6 +181,7 @@ def test_primal_dual_ragged_shapes_vs_oracle(shape, dtype):
     ctx = _lib.context()
     ctx.set_tuning("pd_zc", 8)     # several z-chunks even for small volumes
     ctx.set_tuning("pd_ty", 4)
+    ctx.set_tuning("pd_variant", 2 if sum(shape) % 2 else 1)   # exercise both kernel variants
     try:
         for reg, data, alpha in (("TV", "L2", 0.05), ("HUBER", "L1", 0.6)):
             x = run_pd(obs, reg=reg, data=data, alpha=alpha, L2=8, iterations=12, dtype=dtype)
@@ -195,22 +196,32 @@ def test_primal_dual_ragged_shapes_vs_oracle(shape, dtype):
         ctx.set_tuning("pd_ty", 0)
 
 
-def test_primal_dual_tiling_independent():
-    """idempotence property: the result does not depend on z-chunk length / rows per CTA."""
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_primal_dual_tiling_and_variant_independent(dtype):
+    """idempotence property: the result does not depend on z-chunk length, rows per CTA or on
+    the kernel variant (1 = register-pipelined LDG loads, 2 = TMA bulk-async staged tiles)."""
     rng = np.random.RandomState(11)
     obs = rng.rand(70, 45, 136) * 255
     ctx = _lib.context()
     outs = []
     try:
-        for zc, ty in ((0, 0), (8, 4), (16, 16), (64, 2), (3, 8)):
-            ctx.set_tuning("pd_zc", zc)
-            ctx.set_tuning("pd_ty", ty)
-            outs.append(run_pd(obs, reg="TV", data="L2", alpha=0.05, L2=12, iterations=10))
+        for variant in (1, 2):
+            for zc, ty in ((0, 0), (8, 4), (16, 8), (64, 2), (3, 1)):
+                ctx.set_tuning("pd_variant", variant)
+                ctx.set_tuning("pd_zc", zc)
+                ctx.set_tuning("pd_ty", ty)
+                for reg, data in (("TV", "L2"), ("HUBER", "L1")):
+                    outs.append((reg, run_pd(obs, reg=reg, data=data, alpha=0.05 if data == "L2" else 0.6, L2=12,
+                                             iterations=10, dtype=dtype)))
     finally:
-        ctx.set_tuning("pd_zc", 0)
-        ctx.set_tuning("pd_ty", 0)
-    for o in outs[1:]:
-        assert np.array_equal(o, outs[0])
+        for key in ("pd_variant", "pd_zc", "pd_ty"):
+            ctx.set_tuning(key, 0)
+    for reg, o in outs[2:]:
+        ref = outs[0][1] if reg == "TV" else outs[1][1]
+        if dtype == "float64":
+            assert np.array_equal(o, ref)
+        else:
+            assert rel_max(o, ref) < 1e-5
 
 
 def test_primal_dual_sweep_batched_vs_oracle(golden):
