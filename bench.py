@@ -154,6 +154,92 @@ def run_reference_arm(args, rank):
     print(json.dumps(line))
 
 
+def other_configs(ctx, stream, peak):
+    """Short device-timed runs of the other BASELINE configurations (1, 2, 3, 5) on one GPU:
+    latency-bound 2-D single images, the ADMM/LSMR deconvolution and the batched alpha sweep.
+    Inputs are the reference's test images (tests/golden/inputs.npz) with seeded synthetic noise."""
+    import torch
+    from nsol_b200 import _lib
+    import nsol_b200.linear_operators as lo
+    import nsol_b200.admm_linear_solver as admm
+    z = np.load(os.path.join(ROOT, "tests", "golden", "inputs.npz"))
+    rng = np.random.RandomState(1)
+    lib = ctx.lib
+    out = {}
+
+    def time_events(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def pd_case(img, reg, data, alphas, iters, dtype="float64"):
+        dcode = _lib.dtype_code(dtype)
+        esz = 4 if dcode == _lib.F32 else 8
+        desc = _lib.PdDesc()
+        desc.grid = _lib.make_grid(img.shape, None, dcode, len(alphas))
+        desc.reg, desc.data, desc.alg = _lib.REG[reg], _lib.DATA[data], _lib.ALG["ALG2"]
+        desc.huber_gamma, desc.L2 = 0.05, 8.0
+        desc.x_scale = desc.x0_scale = desc.b_scale = float(img.max())
+        al = np.ascontiguousarray(alphas, dtype=np.float64)
+        desc.alpha = al.ctypes.data_as(_lib.c_double_p)
+        plan = C.c_void_p()
+        ctx.check(lib.nsol_pd_plan_create(ctx.handle, C.byref(desc), C.byref(plan)))
+        host = np.ascontiguousarray(img.reshape(-1), dtype=np.float64)
+
+        def solve():
+            ctx.check(lib.nsol_pd_plan_reset_host(plan, host.ctypes.data, None, stream))
+            ctx.check(lib.nsol_pd_plan_iterate(plan, iters, stream))
+        ms = time_events(solve, 3)
+        lib.nsol_pd_plan_destroy(plan)
+        vox_it = img.size * len(alphas) * iters
+        words = 5 + 2 * img.ndim
+        return {"ms_per_solve": ms, "voxel_iters_per_s": vox_it / (ms * 1e-3), "iterations": iters, "batch": len(alphas),
+                "hbm_frac_of_measured": words * esz * vox_it / (ms * 1e-3) / 1e9 / peak, "dtype": dtype,
+                "note": "includes the H2D copy of the observation and the reset"}
+
+    lena = z["lena_256_noise"].astype(np.float64)
+    out["C1_2D_TVL2_PD_lena256_100it"] = pd_case(lena, "TV", "L2", [0.05], 100)
+    man = z["man_1024"].astype(np.float64)
+    sp = man.copy().reshape(-1)
+    idx = rng.choice(sp.size, size=int(0.1 * sp.size), replace=False)
+    sp[idx[:idx.size // 2]] = man.max()
+    sp[idx[idx.size // 2:]] = man.min()
+    out["C2_2D_HuberL1_PD_man1024_200it"] = pd_case(sp.reshape(man.shape), "HUBER", "L1", [0.6], 200)
+    noisy = man + 0.05 * man.max() * rng.standard_normal(man.shape)
+    alphas = np.linspace(0.001, 0.05, 64)
+    for reg in ("TV", "HUBER", "TK1"):
+        out["C5_sweep64_%sL2_PD_man1024_200it" % reg] = pd_case(noisy, reg, "L2", alphas, 200)
+
+    # config 3: ADMM TV-L2 deconvolution, 512^2, sigma=1 periodic blur, 50 outer x 10 LSMR iterations
+    img = z["lena_512"].astype(np.float64)
+    ops = lo.LinearOperators2D()
+    A, A_adj = ops.get_gaussian_blurring_operators(np.eye(2))
+    grad, grad_adj = ops.get_gradient_operators()
+    obs = A(img) + 0.05 * img.max() * rng.standard_normal(img.shape)
+    shape = img.shape
+    zshape = (2 * shape[0], shape[1])
+    solver = admm.ADMMLinearSolver(
+        A=lambda x: A(x.reshape(*shape)).flatten(), A_adj=lambda x: A_adj(x.reshape(*shape)).flatten(), b=obs.flatten(),
+        B=lambda x: grad(x.reshape(*shape)).flatten(), B_adj=lambda x: grad_adj(x.reshape(*zshape)).flatten(),
+        x0=obs.flatten(), dimension=2, alpha=0.01, rho=0.1, iterations=50, iter_max=10, x_scale=float(obs.max()))
+    solver.run()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        solver.run()
+        solver.get_x()
+    dt = (time.perf_counter() - t0) / 3
+    out["C3_2D_TVL2_ADMM_lena512_50x10"] = {
+        "ms_per_solve": dt * 1e3, "pixel_lsmr_iters_per_s": img.size * 50 * 10 / dt,
+        "note": "ADMMLinearSolver.run()+get_x() wall clock (host buffers; outer iterations replayed as a CUDA graph)"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -169,6 +255,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--secondary-dtype", action="store_true", help="also time the other dtype (reported under 'other_dtype')")
+    ap.add_argument("--other-configs", action="store_true", help="also time BASELINE configs 1, 2, 3, 5 (reported under 'other_configs')")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -364,6 +451,11 @@ def main():
             oach = 11 * oesz * nvox_loc / (other["iter_ms"] * 1e-3) / 1e9
             line["other_dtype"] = {"dtype": "f32" if oesz == 4 else "f64", "value": other["value"], "iter_ms": other["iter_ms"],
                                    "roofline_frac": oach / peak, "achieved_gbs": oach}
+        if args.other_configs and world == 1:
+            try:
+                line["other_configs"] = other_configs(ctx, C.c_void_p(torch.cuda.current_stream().cuda_stream), peak)
+            except Exception as e:      # never lose the headline line
+                line["other_configs"] = {"error": "%s: %s" % (type(e).__name__, e)}
         if not args.no_cpu_baseline and world == 1:
             thr, dt = cpu_reference_throughput(args.ref_size, args.ref_iters)
             line["cpu_baseline"] = {

@@ -165,6 +165,9 @@ typedef struct {
 
 int nsol_pd_plan_create(nsol_ctx *ctx, const nsol_pd_desc *desc, nsol_pd_plan **out);
 void nsol_pd_plan_destroy(nsol_pd_plan *plan);
+/* change the solver parameters (reg, data, alg, gamma, L2, scales, alpha) of an existing plan
+ * without reallocating; grid, dtype and batch must be unchanged.  The plan must be reset again. */
+int nsol_pd_plan_update(nsol_pd_plan *plan, const nsol_pd_desc *desc);
 /* bytes of device memory owned by the plan */
 size_t nsol_pd_plan_bytes(const nsol_pd_plan *plan);
 /* (re)start: x = xbar = x0/x0_scale, b' = b/b_scale, p = 0, iteration counter = 0.

@@ -74,6 +74,7 @@ SIGNATURES = {
                                   C.c_double, C.c_void_p, C.c_void_p]),
     "nsol_pd_plan_create": (C.c_int, [C.c_void_p, C.POINTER(PdDesc), c_void_pp]),
     "nsol_pd_plan_destroy": (None, [C.c_void_p]),
+    "nsol_pd_plan_update": (C.c_int, [C.c_void_p, C.POINTER(PdDesc)]),
     "nsol_pd_plan_bytes": (C.c_size_t, [C.c_void_p]),
     "nsol_pd_plan_reset_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsol_pd_plan_reset_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -252,6 +253,12 @@ def context(device=None):
         with _lock:
             _contexts[key] = ctx
     return ctx
+
+
+def current_context():
+    """The already-created context of the current device, or None (never creates one)."""
+    with _lock:
+        return _contexts.get(-1) or (next(iter(_contexts.values())) if _contexts else None)
 
 
 def make_grid(shape, spacing=None, dtype=F64, batch=1):

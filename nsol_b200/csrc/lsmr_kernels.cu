@@ -402,6 +402,7 @@ __global__ void admm_shrink_kernel(LsqGeom<T> g, const T *__restrict__ x, const 
 // ---------------------------------------------------------------------------
 struct nsol_lsmr_plan {
     nsol_ctx *ctx = nullptr;
+    cudaStream_t own_stream = nullptr;   // used when the caller passes the legacy default stream
     nsol_lsq_desc desc;
     nsol_grid grid;
     GridView gv;
@@ -427,6 +428,7 @@ extern "C" void nsol_lsmr_plan_destroy(nsol_lsmr_plan *pl) {
     void *ptrs[] = {pl->u, pl->v, pl->h, pl->hbar, pl->x, pl->opbuf, pl->optmp, pl->breg, pl->admm_v, pl->admm_w,
                     pl->bbuf, pl->xbuf, pl->stage, pl->part, pl->S};
     for (void *p : ptrs) cudaFree(p);
+    if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
     delete pl;
 }
 
@@ -660,14 +662,59 @@ static int admm_iterations_t(nsol_lsmr_plan *pl, double alpha, double rho, int i
     NSOL_CUDA(ctx, cudaMemsetAsync(w, 0, n * pl->gv.dim * sizeof(T), s));
     NSOL_CUDA(ctx, cudaMemcpyAsync(breg, v, n * pl->gv.dim * sizeof(T), cudaMemcpyDeviceToDevice, s));
     if (iterates_host) NSOL_CHECK(lsq_download(pl, x_dev, x_scale, iterates_host, s));
-    for (int it = 0; it < iterations; ++it) {
+    auto outer_iteration = [&](cudaStream_t st) -> int {
         // x <- clip(lsmr([A; sqrt(rho) B], [b; sqrt(rho)(v - w)]), 0, inf)   (:205, :220-237; x0 is not passed to lsmr)
-        NSOL_CHECK(lsmr_solve_any(pl, rho, b_dev, breg, iter_max, 0.0, INFINITY, x_dev, s));
+        NSOL_CHECK(lsmr_solve_any(pl, rho, b_dev, breg, iter_max, 0.0, INFINITY, x_dev, st));
         // t = B x + w ; v = prox_g(t, alpha/rho) ; w = t - v   (:208-216)
-        admm_shrink_kernel<T><<<nb, th, 0, s>>>(g, (const T *)x_dev, w, (T)(alpha / rho), v, w, breg);
+        admm_shrink_kernel<T><<<nb, th, 0, st>>>(g, (const T *)x_dev, w, (T)(alpha / rho), v, w, breg);
         NSOL_LAUNCH_CHECK(ctx);
-        if (iterates_host) NSOL_CHECK(lsq_download(pl, x_dev, x_scale, iterates_host + (size_t)(it + 1) * n, s));
+        return NSOL_OK;
+    };
+    if (iterates_host || iterations < 2) {
+        // observer attached (one download per outer iteration), or nothing to replay
+        for (int it = 0; it < iterations; ++it) {
+            NSOL_CHECK(outer_iteration(s));
+            if (iterates_host) NSOL_CHECK(lsq_download(pl, x_dev, x_scale, iterates_host + (size_t)(it + 1) * n, s));
+        }
+        return NSOL_OK;
     }
+    // The launch sequence of one outer iteration is fixed (LSMR stops early through device-side
+    // flags, not by skipping launches), so it is captured once into a CUDA graph and replayed:
+    // ~10*iter_max small kernels per outer iteration stop paying individual launch latency.
+    const int64_t l0 = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    NSOL_CUDA(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    int rc = outer_iteration(s);
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (rc != NSOL_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    if (ce != cudaSuccess) return nsol_fail(ctx, NSOL_ECUDA, "admm: graph capture failed: %s", cudaGetErrorString(ce));
+    const int64_t per_iteration = ctx->launches - l0;
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return nsol_fail(ctx, NSOL_ECUDA, "admm: graph instantiation failed: %s", cudaGetErrorString(ce));
+    for (int it = 0; it < iterations && ce == cudaSuccess; ++it) ce = cudaGraphLaunch(exec, s);
+    ctx->launches += per_iteration * (iterations - 1);
+    // the executable graph must outlive its launches
+    cudaError_t se = cudaStreamSynchronize(s);
+    cudaGraphExecDestroy(exec);
+    if (ce != cudaSuccess) return nsol_fail(ctx, NSOL_ECUDA, "admm: graph launch failed: %s", cudaGetErrorString(ce));
+    if (se != cudaSuccess) return nsol_fail(ctx, NSOL_ECUDA, "admm: %s", cudaGetErrorString(se));
+    return NSOL_OK;
+}
+
+// stream the ADMM run is ordered on: the caller's, or a plan-owned blocking stream (which is
+// implicitly ordered with the legacy default stream) when the caller passed NULL
+static int admm_stream(nsol_lsmr_plan *pl, nsol_stream s, cudaStream_t *out) {
+    if (s) {
+        *out = (cudaStream_t)s;
+        return NSOL_OK;
+    }
+    if (!pl->own_stream) NSOL_CUDA(pl->ctx, cudaStreamCreate(&pl->own_stream));
+    *out = pl->own_stream;
     return NSOL_OK;
 }
 
@@ -687,7 +734,8 @@ extern "C" int nsol_admm_run_dev(nsol_lsmr_plan *pl, double alpha, double rho, i
     if (!b_dev || !x0_dev || !x_dev) return nsol_fail(ctx, NSOL_EINVAL, "admm run: NULL array");
     NSOL_CHECK(admm_check(pl, alpha, rho, iterations, iter_max));
     NSOL_CHECK(nsol_bind_device(ctx));
-    cudaStream_t st = (cudaStream_t)s;
+    cudaStream_t st;
+    NSOL_CHECK(admm_stream(pl, s, &st));
     if (x_dev != x0_dev) NSOL_CUDA(ctx, cudaMemcpyAsync(x_dev, x0_dev, (size_t)pl->gv.n * pl->esz, cudaMemcpyDeviceToDevice, st));
     if (pl->gv.dtype == NSOL_F32) return admm_iterations_t<float>(pl, alpha, rho, iterations, iter_max, b_dev, x_dev, 1.0, nullptr, st);
     return admm_iterations_t<double>(pl, alpha, rho, iterations, iter_max, b_dev, x_dev, 1.0, nullptr, st);
@@ -702,7 +750,8 @@ extern "C" int nsol_admm_run_host(nsol_lsmr_plan *pl, double alpha, double rho, 
     if (in_scale == 0.0 || out_scale == 0.0) return nsol_fail(ctx, NSOL_EINVAL, "admm run: scales must be non-zero");
     NSOL_CHECK(admm_check(pl, alpha, rho, iterations, iter_max));
     NSOL_CHECK(nsol_bind_device(ctx));
-    cudaStream_t st = (cudaStream_t)s;
+    cudaStream_t st;
+    NSOL_CHECK(admm_stream(pl, s, &st));
     const size_t n = (size_t)pl->gv.n;
     NSOL_CHECK(lsq_ensure_stage(pl, 2 * n * sizeof(double)));
     double *sb = (double *)pl->stage;

@@ -427,6 +427,8 @@ extern "C" void nsol_pd_plan_destroy(nsol_pd_plan *pl) {
     delete pl;
 }
 
+static int pd_validate_desc(nsol_ctx *ctx, const nsol_pd_desc *desc, const GridView &gv);
+
 extern "C" int nsol_pd_plan_create(nsol_ctx *ctx, const nsol_pd_desc *desc, nsol_pd_plan **out) {
     if (!ctx) return NSOL_EINVAL;
     if (!desc || !out) return nsol_fail(ctx, NSOL_EINVAL, "nsol_pd_plan_create: NULL argument");
@@ -434,15 +436,7 @@ extern "C" int nsol_pd_plan_create(nsol_ctx *ctx, const nsol_pd_desc *desc, nsol
     NSOL_CHECK(nsol_bind_device(ctx));
     GridView gv;
     NSOL_CHECK(nsol_grid_view(ctx, &desc->grid, &gv));
-    if (desc->reg < NSOL_REG_TV || desc->reg > NSOL_REG_TK1) return nsol_fail(ctx, NSOL_EINVAL, "pd: unknown regulariser %d", desc->reg);
-    if (desc->data != NSOL_DATA_L1 && desc->data != NSOL_DATA_L2) return nsol_fail(ctx, NSOL_EINVAL, "pd: unknown data term %d", desc->data);
-    if (desc->alg < NSOL_ALG2 || desc->alg > NSOL_ALG3) return nsol_fail(ctx, NSOL_EINVAL, "pd: unknown alg_type %d", desc->alg);
-    if (!(desc->L2 > 0.0)) return nsol_fail(ctx, NSOL_EINVAL, "pd: L2 must be > 0");
-    if (desc->x_scale == 0.0 || desc->x0_scale == 0.0 || desc->b_scale == 0.0)
-        return nsol_fail(ctx, NSOL_EINVAL, "pd: x_scale, x0_scale and b_scale must be non-zero");
-    if (!desc->alpha) return nsol_fail(ctx, NSOL_EINVAL, "pd: alpha is NULL");
-    for (int i = 0; i < gv.batch; ++i)
-        if (!(desc->alpha[i] > 0.0)) return nsol_fail(ctx, NSOL_EINVAL, "pd: alpha[%d] must be > 0", i);
+    NSOL_CHECK(pd_validate_desc(ctx, desc, gv));
 
     nsol_pd_plan *pl = new nsol_pd_plan();
     pl->ctx = ctx;
@@ -476,6 +470,40 @@ extern "C" int nsol_pd_plan_create(nsol_ctx *ctx, const nsol_pd_desc *desc, nsol
     }
     *out = pl;
     return NSOL_OK;
+}
+
+static int pd_validate_desc(nsol_ctx *ctx, const nsol_pd_desc *desc, const GridView &gv) {
+    if (desc->reg < NSOL_REG_TV || desc->reg > NSOL_REG_TK1) return nsol_fail(ctx, NSOL_EINVAL, "pd: unknown regulariser %d", desc->reg);
+    if (desc->data != NSOL_DATA_L1 && desc->data != NSOL_DATA_L2) return nsol_fail(ctx, NSOL_EINVAL, "pd: unknown data term %d", desc->data);
+    if (desc->alg < NSOL_ALG2 || desc->alg > NSOL_ALG3) return nsol_fail(ctx, NSOL_EINVAL, "pd: unknown alg_type %d", desc->alg);
+    if (!(desc->L2 > 0.0)) return nsol_fail(ctx, NSOL_EINVAL, "pd: L2 must be > 0");
+    if (desc->x_scale == 0.0 || desc->x0_scale == 0.0 || desc->b_scale == 0.0)
+        return nsol_fail(ctx, NSOL_EINVAL, "pd: x_scale, x0_scale and b_scale must be non-zero");
+    if (!desc->alpha) return nsol_fail(ctx, NSOL_EINVAL, "pd: alpha is NULL");
+    for (int i = 0; i < gv.batch; ++i)
+        if (!(desc->alpha[i] > 0.0)) return nsol_fail(ctx, NSOL_EINVAL, "pd: alpha[%d] must be > 0", i);
+    return NSOL_OK;
+}
+
+extern "C" int nsol_pd_plan_update(nsol_pd_plan *pl, const nsol_pd_desc *desc) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    if (!desc) return nsol_fail(ctx, NSOL_EINVAL, "pd update: desc is NULL");
+    NSOL_CHECK(nsol_bind_device(ctx));
+    GridView gv;
+    NSOL_CHECK(nsol_grid_view(ctx, &desc->grid, &gv));
+    if (gv.dim != pl->gv.dim || gv.nx != pl->gv.nx || gv.ny != pl->gv.ny || gv.nz != pl->gv.nz || gv.batch != pl->gv.batch ||
+        gv.dtype != pl->gv.dtype || (desc->b_batched != 0) != (pl->desc.b_batched != 0))
+        return nsol_fail(ctx, NSOL_EINVAL, "pd update: grid, dtype and batch of a plan cannot change");
+    NSOL_CHECK(pd_validate_desc(ctx, desc, gv));
+    pl->gv = gv;   // spacing may change
+    pl->desc = *desc;
+    pl->alpha.assign(desc->alpha, desc->alpha + gv.batch);
+    pl->desc.alpha = nullptr;
+    pl->sched_cap = 0;      // step-size table is rebuilt by the next iterate
+    pl->ready = false;
+    pl->it = 0;
+    return pd_ensure_schedule(pl, 128);
 }
 
 extern "C" size_t nsol_pd_plan_bytes(const nsol_pd_plan *pl) { return pl ? pl->bytes + pl->stage_bytes : 0; }

@@ -143,29 +143,70 @@ class PrimalDualSolver(Solver):
         desc._keep = arr
         return desc
 
+    # -- device plan (kept between runs of the same solver: no reallocation in a sweep) ---------
+    def _acquire_plan(self, ctx, cfg, desc):
+        key = (cfg["shape"], cfg["spacing"], int(desc.grid.dtype), int(desc.grid.batch))
+        plan = getattr(self, "_plan", None)
+        if plan is not None and self._plan_key == key:
+            ctx.check(ctx.lib.nsol_pd_plan_update(plan, C.byref(desc)))
+            return plan
+        self.release()
+        h = C.c_void_p()
+        ctx.check(ctx.lib.nsol_pd_plan_create(ctx.handle, C.byref(desc), C.byref(h)))
+        self._plan, self._plan_key, self._plan_ctx = h, key, ctx
+        return h
+
+    def release(self):
+        """Free the device memory held by this solver (plan + device-resident result)."""
+        plan = getattr(self, "_plan", None)
+        if plan is not None:
+            if self._fetch_result is not None:
+                self._x_unscaled = self._fetch_result()
+                self._fetch_result = None
+            self._plan_ctx.lib.nsol_pd_plan_destroy(plan)
+            self._plan = None
+
+    def __del__(self):
+        try:
+            plan = getattr(self, "_plan", None)
+            if plan is not None:
+                self._plan_ctx.lib.nsol_pd_plan_destroy(plan)
+                self._plan = None
+        except Exception:
+            pass
+
     def _run(self):
         cfg = self._probe()
         if cfg["kind"] == "deconv":
             from nsol_b200._pd_deconv import run_pd_deconvolution
             return run_pd_deconvolution(self, cfg)
         ctx = _lib.context()
+        lib = ctx.lib
         n = self._x0.size
         desc = self._make_desc(cfg, [float(self._alpha)])
         x0 = np.ascontiguousarray(self._x0, dtype=np.float64)
         b = np.ascontiguousarray(cfg["b"], dtype=np.float64)
         iters = int(self._iterations)
-        x_out = np.empty(n, dtype=np.float64)
+        if iters < 0:
+            raise ValueError("iterations must be >= 0")
+        plan = self._acquire_plan(ctx, cfg, desc)
+        ctx.check(lib.nsol_pd_plan_reset_host(plan, b.ctypes.data, x0.ctypes.data, None))
+
+        def fetch():
+            out = np.empty(n, dtype=np.float64)
+            ctx.check(lib.nsol_pd_plan_get_x_host(plan, out.ctypes.data, None))
+            return out
+
         if self._observer is None:
-            ctx.check(ctx.lib.nsol_pd_run_host(ctx.handle, C.byref(desc), iters, b.ctypes.data, x0.ctypes.data,
-                                               x_out.ctypes.data, None, None))
+            ctx.check(lib.nsol_pd_plan_iterate(plan, iters, None))
         else:
             # nsol/primal_dual_solver.py:218-219, 260-261: the observer sees x0 and every iterate
-            its = np.empty((iters + 1, n), dtype=np.float64)
-            ctx.check(ctx.lib.nsol_pd_run_host(ctx.handle, C.byref(desc), iters, b.ctypes.data, x0.ctypes.data,
-                                               x_out.ctypes.data, its.ctypes.data, None))
-            for i in range(iters + 1):
-                self._observer.add_x(np.array(its[i]))
-        self._set_result(x_out)
+            self._observer.add_x(fetch())
+            for _ in range(iters):
+                ctx.check(lib.nsol_pd_plan_iterate(plan, 1, None))
+                self._observer.add_x(fetch())
+        ctx.sync()      # run() returns when the solve is finished (computational time, errors)
+        self._set_device_result(fetch)
 
     def run_sweep(self, alphas):
         """Batched parameter sweep: one fused launch per iteration advances every alpha.

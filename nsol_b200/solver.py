@@ -11,15 +11,32 @@ from abc import ABCMeta, abstractmethod
 
 import numpy as np
 
+from nsol_b200 import _lib
+
+_PIN_MIN_ELEMENTS = 1 << 17
+
+
+def _scaled_host_copy(x0, x_scale):
+    """x0 / x_scale as float64 (nsol/solver.py:37).  Large arrays land in page-locked memory when a
+    CUDA context already exists, so the later host->device copy runs at full PCIe speed."""
+    x0 = np.asarray(x0, dtype=np.float64)
+    ctx = _lib.current_context() if x0.size >= _PIN_MIN_ELEMENTS else None
+    if ctx is None:
+        return np.array(x0, dtype=np.float64) / x_scale
+    out = ctx.pinned_empty(x0.shape, np.float64)
+    np.divide(x0, x_scale, out=out)
+    return out
+
 
 class Solver(object):
     __metaclass__ = ABCMeta
 
     def __init__(self, x0, x_scale, verbose):
         self._x_scale = float(x_scale)
-        self._x0 = np.array(x0, dtype=np.float64) / self._x_scale   # nsol/solver.py:37
+        self._x0 = _scaled_host_copy(x0, self._x_scale)             # nsol/solver.py:37
         self._x = np.array(self._x0)
         self._x_unscaled = None      # get_x() value produced on the device (x * x_scale)
+        self._fetch_result = None    # callable downloading the device-resident result
         self._verbose = verbose
         self._computational_time = datetime.timedelta(seconds=0)
         self._observer = None
@@ -37,9 +54,10 @@ class Solver(object):
         return self._verbose
 
     def set_x0(self, x0):
-        self._x0 = np.array(x0, dtype=np.float64) / self._x_scale
+        self._x0 = _scaled_host_copy(x0, self._x_scale)
         self._x = np.array(self._x0)
         self._x_unscaled = None
+        self._fetch_result = None
 
     def get_x0(self):
         return np.array(self._x0) * self._x_scale
@@ -48,6 +66,8 @@ class Solver(object):
         """Fresh copy of the solution in original units (nsol/solver.py:117-118).
         After a GPU run the multiplication by x_scale has already been done on the
         device in float64 (bit-identical to the host product)."""
+        if self._fetch_result is not None:
+            return self._fetch_result()          # fresh array straight from the device
         if self._x_unscaled is not None:
             return np.array(self._x_unscaled)
         return np.array(self._x) * self._x_scale
@@ -71,8 +91,16 @@ class Solver(object):
 
     # results coming back from the device
     def _set_result(self, x_unscaled):
+        self._fetch_result = None
         self._x_unscaled = x_unscaled
-        self._x = _LazyScaled(x_unscaled, self._x_scale)
+        self._x = _LazyScaled(lambda: x_unscaled, self._x_scale)
+
+    def _set_device_result(self, fetch):
+        """The solution stays on the device; every get_x() downloads a fresh float64 array
+        (x * x_scale evaluated on the device), like the reference returns a fresh array."""
+        self._x_unscaled = None
+        self._fetch_result = fetch
+        self._x = _LazyScaled(fetch, self._x_scale)
 
     @abstractmethod
     def _run(self):
@@ -87,8 +115,8 @@ class _LazyScaled(object):
     """``solver._x`` after a device run: materialises x_unscaled / x_scale on demand
     (only the diagnostic cost getters of LinearSolver read it)."""
 
-    def __init__(self, x_unscaled, x_scale):
-        self._u, self._s = x_unscaled, x_scale
+    def __init__(self, fetch, x_scale):
+        self._fetch, self._s = fetch, x_scale
 
     def __array__(self, dtype=None, copy=None):
-        return np.asarray(self._u / self._s, dtype=dtype)
+        return np.asarray(self._fetch() / self._s, dtype=dtype)
