@@ -254,6 +254,9 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--overlap", action="store_true",
+                    help="multi-GPU: split every iteration (boundary chunks, exchange || interior chunks); measured no faster "
+                         "than the plain exchange on 8 B200 (profiles/r1_scaling.md), so off by default")
     ap.add_argument("--secondary-dtype", action="store_true", help="also time the other dtype (reported under 'other_dtype')")
     ap.add_argument("--other-configs", action="store_true", help="also time BASELINE configs 1, 2, 3, 5 (reported under 'other_configs')")
     args = ap.parse_args()
@@ -332,9 +335,9 @@ def main():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 
         def solve_resident():
-            ctx.check(lib.nsol_pd_plan_reset_dev(plan, obs_dev.ptr, None, stream))
+            slab.reset_dev(obs_dev.ptr, None, stream)
             ev[1].record()
-            slab.iterate(args.iters, stream)
+            slab.iterate(args.iters, stream, overlap=args.overlap)
             ev[2].record()
 
         for _ in range(args.warmup):
@@ -350,9 +353,9 @@ def main():
         pairs = []
         for _ in range(args.steps):
             e1, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ctx.check(lib.nsol_pd_plan_reset_dev(plan, obs_dev.ptr, None, stream))
+            slab.reset_dev(obs_dev.ptr, None, stream)
             e1.record()
-            slab.iterate(args.iters, stream)
+            slab.iterate(args.iters, stream, overlap=args.overlap)
             e2.record()
             pairs.append((e1, e2))
         ev[3].record()
@@ -393,8 +396,8 @@ def main():
             else:
                 slab2 = SlabPrimalDual(ctx, desc, n * n, np_dt, rank, world, device)
                 def e2e_step():
-                    ctx.check(lib.nsol_pd_plan_reset_host(slab2.plan, obs_host.ctypes.data, None, stream))
-                    slab2.iterate(args.iters, stream)
+                    slab2.reset_host(obs_host.ctypes.data, None, stream)
+                    slab2.iterate(args.iters, stream, overlap=args.overlap)
                     ctx.check(lib.nsol_pd_plan_get_x_host(slab2.plan, out_host.ctypes.data, stream))
                     return out_host
             e2e_step()
@@ -436,7 +439,7 @@ def main():
             "config": {"workload": "C4: 3D TV-L2 primal-dual denoising %dx%dx%d, alpha=%g, L2=%g, ALG2, %d iterations per step"
                                    % (nz_global, n, n, ALPHA, L2, args.iters),
                        "input": "64^3 Shepp-Logan fixture repeated to size + Gaussian noise 0.05 (seeded)",
-                       "parallelism": "z-slab x%d, 3-plane halo exchange per iteration" % world if world > 1 else "single GPU",
+                       "parallelism": "z-slab x%d, 3-plane halo exchange per iteration%s" % (world, " overlapped with the interior chunks" if args.overlap else "") if world > 1 else "single GPU",
                        "l2_policy": "inputs larger than L2 (%.1f GiB of solver state per GPU)" % (main_res["plan_bytes"] / 2.0 ** 30)},
             "gpu_launches": main_res["launches"],
             "clocks": main_res["clocks"],

@@ -200,6 +200,13 @@ int nsol_pd_plan_set_halo(nsol_pd_plan *plan, const void *xbar_above, const void
                           const void *p_below);
 int nsol_pd_plan_boundary_planes(nsol_pd_plan *plan, const void **xbar_first, const void **xbar_last,
                                  const void **pz_last);
+/* Split iteration, to overlap the halo exchange with compute: part 1 launches only the first and
+ * last z-chunk (afterwards nsol_pd_plan_boundary_planes_next returns the planes of the NEW state to
+ * send), part 2 the interior chunks and advances the plan.  Needs nsol_pd_plan_chunks() >= 3. */
+int nsol_pd_plan_iterate_part(nsol_pd_plan *plan, int part, nsol_stream s);
+int nsol_pd_plan_boundary_planes_next(nsol_pd_plan *plan, const void **xbar_first, const void **xbar_last,
+                                      const void **pz_last);
+int nsol_pd_plan_chunks(nsol_pd_plan *plan);
 
 /* ---- stacked least squares: LSMR on [A; sqrt(alpha) B] ---------------------
  * Replaces TikhonovLinearSolver._run, lsmr/linear branch

@@ -87,6 +87,9 @@ SIGNATURES = {
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsol_pd_plan_set_halo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsol_pd_plan_boundary_planes": (C.c_int, [C.c_void_p, c_void_pp, c_void_pp, c_void_pp]),
+    "nsol_pd_plan_iterate_part": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "nsol_pd_plan_boundary_planes_next": (C.c_int, [C.c_void_p, c_void_pp, c_void_pp, c_void_pp]),
+    "nsol_pd_plan_chunks": (C.c_int, [C.c_void_p]),
     "nsol_lsmr_plan_create": (C.c_int, [C.c_void_p, C.POINTER(LsqDesc), c_void_pp]),
     "nsol_lsmr_plan_destroy": (None, [C.c_void_p]),
     "nsol_lsmr_plan_bytes": (C.c_size_t, [C.c_void_p]),

@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kern
     const int x0t = (int)blockIdx.x * W;                        // first voxel of the tile row
     const int x0 = x0t + lane * VEC;
     const int y = (int)blockIdx.y * TY + ty;
-    const int chunk = (int)(blockIdx.z % (unsigned)a.nchunks);
-    const int bz = (int)(blockIdx.z / (unsigned)a.nchunks);
+    const int chunk = a.chunk_first + (int)(blockIdx.z % (unsigned)a.nsel) * a.chunk_stride;
+    const int bz = (int)(blockIdx.z / (unsigned)a.nsel);
     const int z0 = chunk * a.zc;
     const int z1 = min(a.nz, z0 + a.zc);
     const bool row_in = (y < a.ny) && (x0t < a.nx);             // warp-uniform

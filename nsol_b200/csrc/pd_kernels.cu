@@ -38,6 +38,7 @@ struct PdArgs {
     long long n;                      // voxels per problem
     long long b_stride;               // 0 (shared observation) or n
     int nx, ny, nz, zc, nchunks;
+    int nsel, chunk_first, chunk_stride;   // chunks processed by this launch: chunk_first + i*chunk_stride, i < nsel
     int has_z;
     T wx, wy, wz;
     int it, batch;
@@ -130,8 +131,8 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : NSOL_
     const int x0 = (int)blockIdx.x * tile_w + (int)threadIdx.x * VEC;
     const int y0 = HAS_Y ? (int)blockIdx.y * TY : 0;
     const int y = y0 + ty;
-    const int chunk = (int)(blockIdx.z % (unsigned)a.nchunks);
-    const int bz = (int)(blockIdx.z / (unsigned)a.nchunks);
+    const int chunk = a.chunk_first + (int)(blockIdx.z % (unsigned)a.nsel) * a.chunk_stride;
+    const int bz = (int)(blockIdx.z / (unsigned)a.nsel);
     const int z0 = chunk * a.zc;
     const int z1 = min(a.nz, z0 + a.zc);
     const bool xin = x0 < a.nx;
@@ -583,15 +584,25 @@ extern "C" int nsol_pd_plan_set_halo(nsol_pd_plan *pl, const void *xbar_above, c
     return NSOL_OK;
 }
 
+static int pd_boundary_planes(nsol_pd_plan *pl, int which, const void **xbar_first, const void **xbar_last, const void **pz_last);
+
 extern "C" int nsol_pd_plan_boundary_planes(nsol_pd_plan *pl, const void **xbar_first, const void **xbar_last, const void **pz_last) {
+    return pd_boundary_planes(pl, pl ? pl->cur : 0, xbar_first, xbar_last, pz_last);
+}
+// the same planes of the buffers the running iteration writes (valid after nsol_pd_plan_iterate_part(plan, 1))
+extern "C" int nsol_pd_plan_boundary_planes_next(nsol_pd_plan *pl, const void **xbar_first, const void **xbar_last, const void **pz_last) {
+    return pd_boundary_planes(pl, pl ? (pl->cur ^ 1) : 0, xbar_first, xbar_last, pz_last);
+}
+
+static int pd_boundary_planes(nsol_pd_plan *pl, int which, const void **xbar_first, const void **xbar_last, const void **pz_last) {
     if (!pl) return NSOL_EINVAL;
     if (pl->gv.batch != 1) return nsol_fail(pl->ctx, NSOL_EINVAL, "pd boundary planes: batch must be 1");
     const GridView &gv = pl->gv;
     const size_t plane = (size_t)gv.nx * gv.ny * pl->esz;
-    const char *xb = (const char *)pl->xbar[pl->cur];
+    const char *xb = (const char *)pl->xbar[which];
     if (xbar_first) *xbar_first = xb;
     if (xbar_last) *xbar_last = xb + (size_t)(gv.nz - 1) * plane;
-    if (pz_last) *pz_last = gv.comp_z >= 0 ? (const char *)pl->p[pl->cur][gv.comp_z] + (size_t)(gv.nz - 1) * plane : nullptr;
+    if (pz_last) *pz_last = gv.comp_z >= 0 ? (const char *)pl->p[which][gv.comp_z] + (size_t)(gv.nz - 1) * plane : nullptr;
     return NSOL_OK;
 }
 
@@ -638,8 +649,34 @@ static int pd_launch_bulk(const nsol_pd_plan *pl, const PdArgs<T> &a, dim3 grid,
     return NSOL_EINVAL;
 }
 
+// rows per CTA (3-D only) and planes per z-chunk
+static void pd_tiling(const nsol_ctx *ctx, const GridView &gv, int vecw, int *ty_out, int *zc_out) {
+    const bool has_y = gv.comp_y >= 0;
+    int ty = 1;
+    if (has_y) {
+        ty = ctx->pd_ty ? ctx->pd_ty : 2;
+        if (ty < 1) ty = 1;
+        if (ty > 8) ty = 8;
+    }
+    const int tile_w = (has_y ? 32 : 128) * vecw;
+    int zc = ctx->pd_zc;
+    if (zc <= 0) {
+        // measured on B200 at 512^3 (profiles/r1_tuning.md): 16 planes per chunk; shorter chunks only
+        // when the volume would otherwise give fewer than ~4 CTAs per SM
+        zc = 16;
+        const long long tiles = (long long)((gv.nx + tile_w - 1) / tile_w) * (has_y ? (gv.ny + ty - 1) / ty : 1) * gv.batch;
+        while (zc > 4 && tiles * ((gv.nz + zc - 1) / zc) < (long long)ctx->sm_count * 4) zc /= 2;
+    }
+    if (zc > gv.nz) zc = gv.nz;
+    if (zc < 1) zc = 1;
+    *ty_out = ty;
+    *zc_out = zc;
+}
+
+// part: 0 = whole iteration; 1 = only the first and last z-chunk (the planes a z-slab neighbour
+// needs), no state advance; 2 = the remaining interior chunks, then advance.
 template <typename T, int VECW>
-static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s) {
+static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0) {
     nsol_ctx *ctx = pl->ctx;
     const GridView &gv = pl->gv;
     const int cur = pl->cur, nxt = cur ^ 1;
@@ -673,11 +710,9 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s) {
     const bool has_y = gv.comp_y >= 0;
     dim3 block, grid;
     size_t smem = 0;
-    int ty = 1;
+    int ty = 1, zc = 1;
+    pd_tiling(ctx, gv, VECW, &ty, &zc);
     if (has_y) {
-        ty = ctx->pd_ty ? ctx->pd_ty : 2;
-        if (ty < 1) ty = 1;
-        if (ty > 8) ty = 8;
         block = dim3(32, ty, 1);
         smem = (size_t)(2 * (ty + 2) + 2 * (ty + 1)) * 32 * VECW * sizeof(T);
     } else {
@@ -686,20 +721,22 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s) {
     const int tile_w = block.x * VECW;
     grid.x = (gv.nx + tile_w - 1) / tile_w;
     grid.y = has_y ? (gv.ny + ty - 1) / ty : 1;
-    // z-chunk length: long enough to amortise the one-plane halo recompute, short enough
-    // to give every SM several CTAs
-    int zc = ctx->pd_zc;
-    if (zc <= 0) {
-        // measured on B200 at 512^3 (profiles/r1_tuning.md): 16 planes per chunk; shorter chunks only
-        // when the volume would otherwise give fewer than ~4 CTAs per SM
-        zc = 16;
-        const long long tiles = (long long)grid.x * grid.y * gv.batch;
-        while (zc > 4 && tiles * ((gv.nz + zc - 1) / zc) < (long long)ctx->sm_count * 4) zc /= 2;
-    }
-    if (zc > gv.nz) zc = gv.nz;
     a.zc = zc;
     a.nchunks = (gv.nz + zc - 1) / zc;
-    const long long gz = (long long)a.nchunks * gv.batch;
+    a.nsel = a.nchunks;
+    a.chunk_first = 0;
+    a.chunk_stride = 1;
+    if (part != 0) {
+        if (a.nchunks < 3) return nsol_fail(ctx, NSOL_ESTATE, "pd: split iteration needs at least 3 z-chunks (nz=%d, zc=%d)", gv.nz, zc);
+        if (part == 1) {
+            a.nsel = 2;
+            a.chunk_stride = a.nchunks - 1;
+        } else {
+            a.nsel = a.nchunks - 2;
+            a.chunk_first = 1;
+        }
+    }
+    const long long gz = (long long)a.nsel * gv.batch;
     if (gz > 65535) return nsol_fail(ctx, NSOL_EINVAL, "pd: nchunks*batch = %lld exceeds the grid limit; raise pd_zc", gz);
     grid.z = (unsigned)gz;
     // kernel variant: 1 = register-pipelined loads (LDG), 2 = TMA bulk-async staged tiles;
@@ -715,8 +752,10 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s) {
         pd_launch_rd<T, VECW, false>(pl, a, grid, block, smem, s);
     }
     NSOL_LAUNCH_CHECK(ctx);
-    pl->cur = nxt;
-    pl->it += 1;
+    if (part != 1) {
+        pl->cur = nxt;
+        pl->it += 1;
+    }
     return NSOL_OK;
 }
 
@@ -738,6 +777,34 @@ extern "C" int nsol_pd_plan_iterate(nsol_pd_plan *pl, int n, nsol_stream s) {
         if (rc != NSOL_OK) return rc;
     }
     return NSOL_OK;
+}
+
+// Split iteration for overlapping the z-slab halo exchange with compute: part 1 computes the two
+// boundary chunks (whose first/last planes the neighbours need; fetch them with
+// nsol_pd_plan_boundary_planes(next=1)), part 2 the interior chunks and advances the plan.
+extern "C" int nsol_pd_plan_iterate_part(nsol_pd_plan *pl, int part, nsol_stream s) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    if (!pl->ready) return nsol_fail(ctx, NSOL_ESTATE, "pd iterate: plan has not been reset with an observation");
+    if (part != 1 && part != 2) return nsol_fail(ctx, NSOL_EINVAL, "pd iterate_part: part must be 1 (boundary) or 2 (interior)");
+    NSOL_CHECK(nsol_bind_device(ctx));
+    NSOL_CHECK(pd_ensure_schedule(pl, pl->it + 1));
+    const GridView &gv = pl->gv;
+    cudaStream_t st = (cudaStream_t)s;
+    const int vecw = gv.dtype == NSOL_F32 ? 4 : 2;
+    const bool vec_ok = (gv.nx % vecw) == 0;
+    if (gv.dtype == NSOL_F32) return vec_ok ? pd_launch_iteration<float, 4>(pl, st, part) : pd_launch_iteration<float, 1>(pl, st, part);
+    return vec_ok ? pd_launch_iteration<double, 2>(pl, st, part) : pd_launch_iteration<double, 1>(pl, st, part);
+}
+
+// number of z-chunks an iteration of this plan is cut into (>= 3 is needed for the split form)
+extern "C" int nsol_pd_plan_chunks(nsol_pd_plan *pl) {
+    if (!pl) return 0;
+    const GridView &gv = pl->gv;
+    const int vecw = gv.dtype == NSOL_F32 ? 4 : 2;
+    int ty, zc;
+    pd_tiling(pl->ctx, gv, (gv.nx % vecw) == 0 ? vecw : 1, &ty, &zc);
+    return (gv.nz + zc - 1) / zc;
 }
 
 extern "C" int nsol_pd_plan_x_dev(nsol_pd_plan *pl, const void **x_dev) {

@@ -48,7 +48,8 @@ class HaloExchanger(object):
         self.xbar_below = mk() if self.has_below else None
         self.pz_below = mk() if self.has_below else None
 
-    def exchange(self, xbar_first, xbar_last, pz_last):
+    def start_exchange(self, xbar_first, xbar_last, pz_last):
+        """Enqueue the sends/receives (non-blocking for the host); returns the requests."""
         dist = self.torch.distributed
         ops = []
         if self.has_above:
@@ -59,10 +60,15 @@ class HaloExchanger(object):
             ops.append(dist.P2POp(dist.isend, xbar_first, self.rank - 1, self.group))
             ops.append(dist.P2POp(dist.irecv, self.xbar_below, self.rank - 1, self.group))
             ops.append(dist.P2POp(dist.irecv, self.pz_below, self.rank - 1, self.group))
-        if not ops:
-            return
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    @staticmethod
+    def finish_exchange(reqs):
+        for req in reqs:
+            req.wait()      # NCCL: makes the current stream wait; gloo: blocks the host
+
+    def exchange(self, xbar_first, xbar_last, pz_last):
+        self.finish_exchange(self.start_exchange(xbar_first, xbar_last, pz_last))
 
 
 class _DevicePtr(object):
@@ -103,21 +109,49 @@ class SlabPrimalDual(object):
                                                ptr(self.halo.pz_below)))
         self._views = {}
 
-    def _boundary_tensors(self):
+    def _boundary_tensors(self, upcoming=False):
+        """Boundary planes of the current state, or (upcoming=True) of the state the running
+        split iteration is writing."""
         C = self.C
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        self.ctx.check(self.ctx.lib.nsol_pd_plan_boundary_planes(self.plan, C.byref(a), C.byref(b), C.byref(c)))
+        fn = self.ctx.lib.nsol_pd_plan_boundary_planes_next if upcoming else self.ctx.lib.nsol_pd_plan_boundary_planes
+        self.ctx.check(fn(self.plan, C.byref(a), C.byref(b), C.byref(c)))
         key = (a.value, b.value, c.value)
         if key not in self._views:
             self._views[key] = tuple(tensor_from_ptr(p, self.plane_numel, self.np_dtype, self.device) for p in key)
         return self._views[key]
 
-    def iterate(self, n, stream):
+    def iterate(self, n, stream, overlap=True):
+        """n iterations.  With overlap (default, needs >= 3 z-chunks) every iteration is split:
+        the two boundary chunks run first, their new boundary planes are exchanged while the
+        interior chunks compute, and the next iteration starts when both have finished.
+        Without overlap: exchange, then one full-iteration launch."""
+        lib, ctx, plan = self.ctx.lib, self.ctx, self.plan
+        if self.halo.world == 1:
+            ctx.check(lib.nsol_pd_plan_iterate(plan, n, stream))
+            return
+        if not overlap or lib.nsol_pd_plan_chunks(plan) < 3:
+            for _ in range(n):
+                self.halo.exchange(*self._boundary_tensors())
+                ctx.check(lib.nsol_pd_plan_iterate(plan, 1, stream))
+            self._halo_fresh = False
+            return
+        if not getattr(self, "_halo_fresh", False):
+            self.halo.exchange(*self._boundary_tensors())          # halos of the current state
         for _ in range(n):
-            if self.halo.world > 1:
-                first, last, pz_last = self._boundary_tensors()
-                self.halo.exchange(first, last, pz_last)
-            self.ctx.check(self.ctx.lib.nsol_pd_plan_iterate(self.plan, 1, stream))
+            ctx.check(lib.nsol_pd_plan_iterate_part(plan, 1, stream))          # boundary chunks
+            reqs = self.halo.start_exchange(*self._boundary_tensors(upcoming=True))
+            ctx.check(lib.nsol_pd_plan_iterate_part(plan, 2, stream))          # interior chunks + advance
+            self.halo.finish_exchange(reqs)
+        self._halo_fresh = True     # the halos now belong to the current state
+
+    def reset_host(self, b_host_ptr, x0_host_ptr, stream):
+        self._halo_fresh = False
+        self.ctx.check(self.ctx.lib.nsol_pd_plan_reset_host(self.plan, b_host_ptr, x0_host_ptr, stream))
+
+    def reset_dev(self, b_dev_ptr, x0_dev_ptr, stream):
+        self._halo_fresh = False
+        self.ctx.check(self.ctx.lib.nsol_pd_plan_reset_dev(self.plan, b_dev_ptr, x0_dev_ptr, stream))
 
     def close(self):
         if self.plan is not None:
