@@ -243,6 +243,19 @@ int nsol_tikhonov_run_host(nsol_lsmr_plan *plan, double alpha, double in_scale, 
 int nsol_admm_run_host(nsol_lsmr_plan *plan, double alpha, double rho, int iterations, int iter_max,
                        double in_scale, double out_scale, const double *b_host, const double *x0_host,
                        double *x_host, double *iterates_host, nsol_stream s);
+/* PrimalDualSolver.run() + get_x() for the deconvolution wiring
+ * (nsol/deconvolution_solver_parameter_study_interface.py:255-280, 303-325):
+ *   prox_g_conj in {tv, huber}, B = grad, and
+ *   prox_f = prox_linear_least_squares(x, tau, A, A_adj, b, x0, iter_max, x_scale=prox_scale)
+ * (nsol/proximal_operators.py:44-78): every iteration solves
+ *   min_y 1/2 ||A y - b''||^2 + 1/(2 t) ||y - x'/prox_scale||^2,  b'' = b / prox_scale^2, t = tau/alpha
+ * by LSMR (iter_max steps, cold start, clipped to [0, inf)) on [A; sqrt(1/t) I] and returns y * prox_scale.
+ * The plan's b_op must be NSOL_B_IDENTITY.  pd.grid must equal the plan's grid (batch 1); pd.x_scale is
+ * the solver's x_scale, x0_host is already divided by it (pd.x0_scale = 1); pd.b_scale is unused. */
+int nsol_pd_deconv_run_host(nsol_lsmr_plan *plan, const nsol_pd_desc *pd, int iterations, int iter_max,
+                            double prox_scale, const double *b_host /* raw observation of the prox */,
+                            const double *x0_host, double *x_host, double *iterates_host, nsol_stream s);
+
 /* device-resident ADMM used by bench.py: arrays in solver units, plan dtype */
 int nsol_admm_run_dev(nsol_lsmr_plan *plan, double alpha, double rho, int iterations, int iter_max,
                       const void *b_dev, const void *x0_dev, void *x_dev, nsol_stream s);

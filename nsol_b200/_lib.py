@@ -99,6 +99,8 @@ SIGNATURES = {
                                          C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "nsol_admm_run_host": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsol_pd_deconv_run_host": (C.c_int, [C.c_void_p, C.POINTER(PdDesc), C.c_int, C.c_int, C.c_double, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsol_admm_run_dev": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsol_admm_shrink": (C.c_int, [C.c_void_p, C.POINTER(Grid), C.c_void_p, C.c_void_p, C.c_double,

@@ -116,7 +116,7 @@ extern "C" int nsol_stream_sync(nsol_ctx *ctx, nsol_stream s) {
 
 // out[i] = (TO)(in[i] * f)  or  (TO)(in[i] / f), evaluated in the wider of the two types
 template <typename TI, typename TO, bool DIV>
-__global__ void scale_convert_kernel(long long n, const TI *__restrict__ in, TO *__restrict__ out, double f) {
+__global__ void scale_convert_kernel(long long n, const TI *in, TO *out, double f) {   // in == out is allowed
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {

@@ -112,6 +112,9 @@ inline int nsol_grid_view(nsol_ctx *ctx, const nsol_grid *g, GridView *v) {
     return NSOL_OK;
 }
 
+// primal-dual step sizes (pd_kernels.cu): rows of 8 doubles (sigma, tau, tau*lambda, theta, den_g, den_f, 0, 0)
+void pd_schedule_rows(const nsol_pd_desc &d, double alpha, int iterations, double *rows);
+
 #ifdef __CUDACC__
 // ---- small aligned vector type for 128-bit global/shared accesses ----------
 template <typename T, int VEC>

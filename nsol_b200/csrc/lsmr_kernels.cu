@@ -789,3 +789,130 @@ extern "C" int nsol_admm_shrink(nsol_ctx *ctx, const nsol_grid *grid, const void
     NSOL_LAUNCH_CHECK(ctx);
     return NSOL_OK;
 }
+
+// ---------------------------------------------------------------------------
+// primal-dual deconvolution: prox_f = prox_linear_least_squares (one LSMR solve per PD iteration)
+// ---------------------------------------------------------------------------
+// p <- prox_g*(p + sigma grad(xbar))   (primal_dual_solver.py:242-243; proximal_operators.py:139-140, 157-159)
+template <typename T>
+__global__ void pdd_dual_kernel(LsqGeom<T> g, const T *__restrict__ xbar, T *__restrict__ p, T sigma, T den, int reg) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += (long long)gridDim.x * blockDim.x) {
+        int idx[3];
+        lsq_decode(g, i, idx);
+        const T xc = xbar[i];
+        for (int k = 0; k < g.dim; ++k) {
+            const T hi = (idx[g.axis[k]] + 1 < g.extent[k]) ? xbar[i + g.stride[k]] : T(0);
+            const T gk = g.w[k] * hi + (-g.w[k]) * xc;
+            T q = p[(long long)k * g.n + i] + sigma * gk;
+            if (reg != NSOL_REG_TV) q = q / den;
+            if (reg != NSOL_REG_TK1) q = q / max_t(T(1), abs_t(q));
+            p[(long long)k * g.n + i] = q;
+        }
+    }
+}
+
+// b_reg <- (x - tau grad_adj(p)) / prox_scale   (primal_dual_solver.py:246; tikhonov b_reg / x_scale)
+template <typename T>
+__global__ void pdd_arg_kernel(LsqGeom<T> g, const T *__restrict__ x, const T *__restrict__ p, T tau, T prox_scale, T *__restrict__ breg) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += (long long)gridDim.x * blockDim.x) {
+        int idx[3];
+        lsq_decode(g, i, idx);
+        T div = T(0);
+        for (int k = 0; k < g.dim; ++k) {
+            const T *pk = p + (long long)k * g.n;
+            const T lo = (idx[g.axis[k]] > 0) ? pk[i - g.stride[k]] : T(0);
+            const T dk = g.w[k] * lo + (-g.w[k]) * pk[i];
+            div = (k == 0) ? dk : div + dk;
+        }
+        breg[i] = (x[i] - tau * div) / prox_scale;
+    }
+}
+
+// x+ = y * prox_scale ; xbar = x+ + theta (x+ - x) ; x = x+   (solver.py:117-118; primal_dual_solver.py:253)
+template <typename T>
+__global__ void pdd_relax_kernel(long long n, const T *__restrict__ y, T prox_scale, T theta, T *__restrict__ x, T *__restrict__ xbar) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const T xn = y[i] * prox_scale;
+        const T xo = x[i];
+        xbar[i] = xn + theta * (xn - xo);
+        x[i] = xn;
+    }
+}
+
+template <typename T>
+static int pd_deconv_t(nsol_lsmr_plan *pl, const nsol_pd_desc *pd, int iterations, int iter_max, double prox_scale, double *x_host,
+                       double *iterates_host, cudaStream_t s) {
+    nsol_ctx *ctx = pl->ctx;
+    LsqGeom<T> g = make_geom<T>(pl);
+    const int nb = pl->nblocks, th = LSMR_THREADS;
+    const size_t n = (size_t)pl->gv.n;
+    // state: x = pl->xbuf, xbar = pl->h reuse is not possible (LSMR owns h) -> admm_v holds [xbar | y | spare], admm_w holds p
+    T *x = (T *)pl->xbuf, *xbar = (T *)pl->admm_v, *p = (T *)pl->admm_w, *breg = (T *)pl->breg;
+    T *y = (pl->gv.dim >= 2) ? xbar + n : nullptr;
+    void *ybuf = y;
+    bool own_y = false;
+    if (!ybuf) {
+        NSOL_CUDA(ctx, cudaMalloc(&ybuf, n * sizeof(T)));
+        own_y = true;
+    }
+    std::vector<double> rows((size_t)(iterations > 0 ? iterations : 1) * 8);
+    pd_schedule_rows(*pd, pd->alpha[0], iterations, rows.data());
+    NSOL_CUDA(ctx, cudaMemcpyAsync(xbar, x, n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    NSOL_CUDA(ctx, cudaMemsetAsync(p, 0, n * pl->gv.dim * sizeof(T), s));
+    int rc = NSOL_OK;
+    if (iterates_host) rc = lsq_download(pl, x, pd->x_scale, iterates_host, s);
+    for (int it = 0; it < iterations && rc == NSOL_OK; ++it) {
+        const double *r = &rows[(size_t)it * 8];
+        pdd_dual_kernel<T><<<nb, th, 0, s>>>(g, xbar, p, (T)r[0], (T)r[4], pd->reg);
+        ctx->launches++;
+        pdd_arg_kernel<T><<<nb, th, 0, s>>>(g, x, p, (T)r[1], (T)prox_scale, breg);
+        ctx->launches++;
+        // tikhonov: alpha = 1 / (tau * lambda), b_reg = y / prox_scale, B = I  (proximal_operators.py:58-75)
+        rc = lsmr_solve_any(pl, 1.0 / r[2], pl->bbuf, breg, iter_max, 0.0, INFINITY, ybuf, s);
+        if (rc != NSOL_OK) break;
+        pdd_relax_kernel<T><<<nb, th, 0, s>>>((long long)n, (const T *)ybuf, (T)prox_scale, (T)r[3], x, xbar);
+        ctx->launches++;
+        if (iterates_host) rc = lsq_download(pl, x, pd->x_scale, iterates_host + (size_t)(it + 1) * n, s);
+    }
+    if (rc == NSOL_OK) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = nsol_fail(ctx, NSOL_ECUDA, "pd deconvolution: %s", cudaGetErrorString(e));
+    }
+    if (rc == NSOL_OK) rc = lsq_download(pl, x, pd->x_scale, x_host, s);
+    if (own_y) {
+        cudaStreamSynchronize(s);
+        cudaFree(ybuf);
+    }
+    return rc;
+}
+
+extern "C" int nsol_pd_deconv_run_host(nsol_lsmr_plan *pl, const nsol_pd_desc *pd, int iterations, int iter_max, double prox_scale,
+                                       const double *b_host, const double *x0_host, double *x_host, double *iterates_host, nsol_stream s) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    if (!pd || !b_host || !x0_host || !x_host || !pd->alpha) return nsol_fail(ctx, NSOL_EINVAL, "pd deconvolution: NULL argument");
+    if (pl->desc.b_op != NSOL_B_IDENTITY) return nsol_fail(ctx, NSOL_EINVAL, "pd deconvolution: the plan's B must be the identity");
+    if (iterations < 0 || iter_max < 0) return nsol_fail(ctx, NSOL_EINVAL, "pd deconvolution: iterations and iter_max must be >= 0");
+    if (prox_scale == 0.0 || pd->x_scale == 0.0 || !(pd->alpha[0] > 0.0) || !(pd->L2 > 0.0))
+        return nsol_fail(ctx, NSOL_EINVAL, "pd deconvolution: scales, alpha and L2 must be non-zero / positive");
+    if (pd->reg != NSOL_REG_TV && pd->reg != NSOL_REG_HUBER && pd->reg != NSOL_REG_TK1) return nsol_fail(ctx, NSOL_EINVAL, "pd deconvolution: unknown regulariser");
+    if (pd->alg < NSOL_ALG2 || pd->alg > NSOL_ALG3) return nsol_fail(ctx, NSOL_EINVAL, "pd deconvolution: unknown alg_type");
+    GridView gv;
+    NSOL_CHECK(nsol_grid_view(ctx, &pd->grid, &gv));
+    if (gv.dim != pl->gv.dim || gv.nx != pl->gv.nx || gv.ny != pl->gv.ny || gv.nz != pl->gv.nz || gv.dtype != pl->gv.dtype || gv.batch != 1)
+        return nsol_fail(ctx, NSOL_EINVAL, "pd deconvolution: pd.grid must equal the plan's grid (batch 1)");
+    NSOL_CHECK(nsol_bind_device(ctx));
+    cudaStream_t st;
+    NSOL_CHECK(admm_stream(pl, s, &st));
+    const size_t n = (size_t)pl->gv.n;
+    NSOL_CHECK(lsq_ensure_stage(pl, 2 * n * sizeof(double)));
+    double *sb = (double *)pl->stage;
+    NSOL_CUDA(ctx, cudaMemcpyAsync(sb, b_host, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    NSOL_CUDA(ctx, cudaMemcpyAsync(sb + n, x0_host, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    // the prox hands b / prox_scale to a solver that divides by prox_scale again (proximal_operators.py:62, linear_solver.py:83)
+    NSOL_CHECK(nsol_scale_convert(ctx, (int64_t)n, NSOL_F64, sb, NSOL_F64, sb, prox_scale, 1, st));
+    NSOL_CHECK(nsol_scale_convert(ctx, (int64_t)n, NSOL_F64, sb, pl->gv.dtype, pl->bbuf, prox_scale, 1, st));
+    NSOL_CHECK(nsol_scale_convert(ctx, (int64_t)n, NSOL_F64, sb + n, pl->gv.dtype, pl->xbuf, pd->x0_scale, 1, st));
+    if (pl->gv.dtype == NSOL_F32) return pd_deconv_t<float>(pl, pd, iterations, iter_max, prox_scale, x_host, iterates_host, st);
+    return pd_deconv_t<double>(pl, pd, iterations, iter_max, prox_scale, x_host, iterates_host, st);
+}

@@ -343,7 +343,7 @@ struct nsol_pd_plan {
 
 // step sizes: reference nsol/primal_dual_solver.py:278-283, :302-306 (ALG2), :321-337, :356-358
 // (ALG3), :374-379, :398-403 (AHMOD); float64 host arithmetic in the reference's order.
-static void pd_schedule_rows(const nsol_pd_desc &d, double alpha, int iterations, double *rows /* [iterations][8] */) {
+void pd_schedule_rows(const nsol_pd_desc &d, double alpha, int iterations, double *rows /* [iterations][8] */) {
     const double L2 = d.L2;
     const double lmbda = 1.0 / alpha;
     double tau, sigma, gamma;

@@ -289,6 +289,30 @@ def main():
         ls_manifest[name] = dict(kind="tikhonov", input=inp, var=ls_var[inp], alpha=alpha,
                                  iter_max=iter_max, reg=reg, x_scale=x_scale)
 
+    def add_pdd(name, inp, reg, alpha, iterations, iter_max, x_scale=None, L2=8):
+        """default deconvolution wiring: ...interface.py:255-280 (TV) / :303-325 (Huber); tests/solvers_test.py:138-150"""
+        obs = ls_inputs[inp]
+        dim = obs.ndim
+        cov = ls_var[inp] if dim == 1 else np.diag(ls_var[inp])
+        A, A_adj, D, D_adj = ref_deconv_ops(obs.shape, cov)
+        b = obs.flatten()
+        x0 = obs.flatten()
+        xs = float(np.max(obs)) if x_scale is None else x_scale
+        s = pd.PrimalDualSolver(
+            prox_f=lambda x, tau: prox.prox_linear_least_squares(x=x, tau=tau, A=A, A_adj=A_adj, b=b, x0=x0,
+                                                                 iter_max=iter_max, x_scale=xs),
+            prox_g_conj=prox.prox_tv_conj if reg == "TV" else prox.prox_huber_conj, B=D, B_conj=D_adj, L2=L2, x0=x0,
+            alpha=alpha, iterations=iterations, x_scale=xs)
+        s.run()
+        ls_out[name] = s.get_x()
+        ls_manifest[name] = dict(kind="pd_deconv", input=inp, var=ls_var[inp], reg=reg, alpha=alpha, iterations=iterations,
+                                 iter_max=iter_max, x_scale=x_scale, L2=L2)
+
+    add_pdd("pdd_1d_TV", "spike1d", "TV", 0.01, 10, 10)
+    add_pdd("pdd_1d_TV_xs1", "spike1d", "TV", 0.01, 10, 10, x_scale=1.0)
+    add_pdd("pdd_2d_TV", "bw2d", "TV", 0.01, 10, 10)
+    add_pdd("pdd_2d_HUBER", "lena64", "HUBER", 0.02, 12, 8)
+    add_pdd("pdd_3d_TV", "ph3d", "TV", 0.01, 6, 10)
     add_admm("admm_1d", "spike1d", 0.01, 0.5, 10, 10)
     add_admm("admm_1d_xs1", "spike1d", 0.01, 0.5, 10, 10, x_scale=1.0)
     add_admm("admm_2d", "bw2d", 0.01, 0.5, 10, 10)

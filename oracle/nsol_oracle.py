@@ -629,6 +629,34 @@ def admm_tv(A, A_adj, B, B_adj, b, x0, dim, alpha=0.01, rho=0.5, iterations=10,
     return x * x_scale
 
 
+def primal_dual_deconvolve(A, A_adj, D, D_adj, b, x0, dim, reg="TV", alpha=0.01, L2=8.0, iterations=10,
+                           iter_max=10, x_scale=1.0, alg_type="ALG2", huber_gamma=0.05):
+    """PrimalDualSolver with prox_f = prox_linear_least_squares -- the default TV-L2 / Huber-L2
+    deconvolution wiring, nsol/deconvolution_solver_parameter_study_interface.py:255-280, 303-325 and
+    nsol/proximal_operators.py:44-78 (the prox divides b and x0 by x_scale and hands them to a
+    Tikhonov solver that divides by x_scale again; restated literally)."""
+    x_scale = float(x_scale)
+    b = np.asarray(b, dtype=np.float64)
+    ident = lambda v: v.reshape(-1)
+
+    def prox_f(x, tau):
+        return tikhonov_lsmr(A, A_adj, ident, ident, b / x_scale, np.asarray(x0) / x_scale, alpha=1.0 / tau, b_reg=x,
+                             iter_max=iter_max, x_scale=x_scale)
+    prox_g = (lambda q, s: prox_huber_conj(q, s, huber_gamma)) if reg == "HUBER" else _PROX_G[reg]
+    lmbda = 1.0 / float(alpha)
+    tau_n, sigma_n, gamma = pd_initial_steps(alg_type, float(L2), lmbda)
+    x_n = np.asarray(x0, dtype=np.float64) / x_scale
+    x_mean = np.array(x_n)
+    p_n = 0
+    for _ in range(iterations):
+        p_n = prox_g(p_n + sigma_n * D(x_mean), sigma_n)
+        x_np1 = prox_f(x_n - tau_n * D_adj(p_n), tau_n * lmbda)
+        theta_n, tau_n, sigma_n = pd_update_steps(alg_type, float(L2), gamma, tau_n, sigma_n)
+        x_mean = x_np1 + theta_n * (x_np1 - x_n)
+        x_n = x_np1
+    return x_n * x_scale
+
+
 def deconvolution_operators(shape, cov, spacing=None, alpha_cut=3, separable=True):
     """1-D wrapped A, A_adj, D, D_adj as nsol/application/run_deconvolution.py:109-129
     builds them (A_adj reuses the same mask, nsol/linear_operators.py:63)."""

@@ -466,3 +466,56 @@ def test_zslab_emulation_matches_unsharded(dtype, nslabs, split):
         assert np.array_equal(np.concatenate(parts), ref)
     else:
         assert rel_max(np.concatenate(parts), ref) < 1e-5
+
+
+# ------------------------------------------------------------------ primal-dual deconvolution (prox_linear_least_squares)
+def make_pd_deconv(obs, var, reg, alpha, iterations, iter_max, x_scale, L2=8, dtype=None):
+    """nsol/deconvolution_solver_parameter_study_interface.py:255-280 (TV) / :303-325 (Huber)."""
+    A, A_adj, D, D_adj = deconv_callables(obs.shape, var)
+    b = obs.flatten()
+    x0 = obs.flatten()
+    return pd.PrimalDualSolver(
+        prox_f=lambda x, tau: prox.prox_linear_least_squares(x=x, tau=tau, A=A, A_adj=A_adj, b=b, x0=x0,
+                                                             iter_max=iter_max, x_scale=x_scale),
+        prox_g_conj=prox.prox_tv_conj if reg == "TV" else prox.prox_huber_conj, B=D, B_conj=D_adj, L2=L2, x0=x0,
+        alpha=alpha, iterations=iterations, x_scale=x_scale, dtype=dtype)
+
+
+@pytest.mark.parametrize("name", ["pdd_1d_TV", "pdd_1d_TV_xs1", "pdd_2d_TV", "pdd_2d_HUBER", "pdd_3d_TV"])
+def test_primal_dual_deconvolution_vs_reference(golden, name):
+    meta = golden.manifest["lsmr"][name]
+    obs = golden("lsmr", "in/" + meta["input"])
+    xs = meta["x_scale"] or float(obs.max())
+    s = make_pd_deconv(obs, meta["var"], meta["reg"], meta["alpha"], meta["iterations"], meta["iter_max"], xs, meta["L2"])
+    s.run()
+    ref = golden("lsmr", name)
+    assert rel_max(s.get_x(), ref) < F64_LSMR_TOL, (name, rel_max(s.get_x(), ref))
+    s32 = make_pd_deconv(obs, meta["var"], meta["reg"], meta["alpha"], meta["iterations"], meta["iter_max"], xs, meta["L2"],
+                         dtype="float32")
+    s32.run()
+    assert rel_max(s32.get_x(), ref) < 2e-3, (name, rel_max(s32.get_x(), ref))
+
+
+def test_x_scale_invariance_pd_deconvolution(golden):
+    """tests/solvers_test.py:138-150, 193-224 (Primal-Dual part), accuracy 1e-7."""
+    obs = golden("lsmr", "in/spike1d")
+    xs = float(obs.max())
+    r1 = make_pd_deconv(obs / xs, 1.5, "TV", 0.01, 10, 10, 1.0)
+    r1.run()
+    r2 = make_pd_deconv(obs, 1.5, "TV", 0.01, 10, 10, xs)
+    r2.run()
+    assert round(np.linalg.norm(r2.get_x() - r1.get_x() * xs), 7) == 0
+
+
+def test_standalone_prox_linear_least_squares(golden):
+    """prox_linear_least_squares called on arrays is a Tikhonov/LSMR solve (proximal_operators.py:44-78)."""
+    obs = golden("lsmr", "in/bw2d")
+    A, A_adj, _, _ = deconv_callables(obs.shape, [1.5, 1.5])
+    Ao, Ao_adj, _, _ = orc.deconvolution_operators(obs.shape, np.diag([1.5, 1.5]))
+    xs = float(obs.max())
+    x = obs.flatten() / xs * 0.9
+    got = prox.prox_linear_least_squares(x, 0.3, A, A_adj, obs.flatten(), obs.flatten(), iter_max=10, x_scale=xs)
+    ident = lambda v: v.reshape(-1)
+    ref = orc.tikhonov_lsmr(Ao, Ao_adj, ident, ident, obs.flatten() / xs, obs.flatten() / xs, alpha=1 / 0.3, b_reg=x,
+                            iter_max=10, x_scale=xs)
+    assert rel_max(got, ref) < F64_LSMR_TOL
