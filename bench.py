@@ -115,6 +115,20 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(dtype_key, nvox):
+    """DRAM bytes per launch of the iteration kernel from the committed ncu capture, scaled to the
+    number of voxels of this launch (the capture is at 512^3)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as fh:
+            t = json.load(fh)[dtype_key]
+        return t["bytes_per_launch"] * (nvox / float(t["voxels"]))
+    except Exception:
+        return None
+
+
+WORKLOAD = "C4: 3D TV-L2 primal-dual denoising %dx%dx%d, alpha=%g, L2=%g, ALG2, %d iterations per step"
+
+
 def cpu_reference_throughput(sample_n, iters):
     """The reference's CPU loop (oracle port, reference call structure) on a sample_n^3 sub-volume."""
     from oracle import nsol_oracle as orc
@@ -146,7 +160,10 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "voxel-iterations/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C4: 3D TV-L2 primal-dual denoising, alpha=0.05, L2=8, ALG2 (CPU sample %d^3)" % n},
+        "config": {"workload": WORKLOAD % (args.size * (args.gpus if args.scaling == "weak" else 1), args.size, args.size,
+                                           ALPHA, L2, args.iters),
+                   "input": "64^3 Shepp-Logan fixture repeated to size + Gaussian noise 0.05 (seeded)",
+                   "cpu_sample": "%d^3 sub-volume, %d iterations per step" % (n, args.ref_iters)},
         "cpu_baseline": {"value": value, "unit": "voxel-iterations/s", "cores": 1, "kind": "port", "sample": sample,
                          "host_cores": os.cpu_count()},
         "e2e": {"value": value, "unit": "voxel-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -436,15 +453,14 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64" if args.dtype == "float64" else "f32", "data": "synthetic",
-            "config": {"workload": "C4: 3D TV-L2 primal-dual denoising %dx%dx%d, alpha=%g, L2=%g, ALG2, %d iterations per step"
-                                   % (nz_global, n, n, ALPHA, L2, args.iters),
+            "config": {"workload": WORKLOAD % (nz_global, n, n, ALPHA, L2, args.iters),
                        "input": "64^3 Shepp-Logan fixture repeated to size + Gaussian noise 0.05 (seeded)",
                        "parallelism": "z-slab x%d, 3-plane halo exchange per iteration%s" % (world, " overlapped with the interior chunks" if args.overlap else "") if world > 1 else "single GPU",
                        "l2_policy": "inputs larger than L2 (%.1f GiB of solver state per GPU)" % (main_res["plan_bytes"] / 2.0 ** 30)},
             "gpu_launches": main_res["launches"],
             "clocks": main_res["clocks"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "pd_iter_kernel",
+                         "traffic": measured_traffic("f64" if args.dtype == "float64" else "f32", nvox_loc), "peak_source": peak_src, "kernel": "pd_iter_kernel",
                          "algorithmic_bytes_per_launch": 11 * esz * nvox_loc, "avg_launch_ms": main_res["iter_ms"]},
         }
         if "e2e" in main_res:

@@ -36,6 +36,7 @@ extern "C" int nsol_create(int device, nsol_ctx **out) {
     if (const char *v = getenv("NSOL_PD_VARIANT")) ctx->pd_variant = atoi(v);
     if (const char *v = getenv("NSOL_PD_TY")) ctx->pd_ty = atoi(v);
     if (const char *v = getenv("NSOL_PD_ZC")) ctx->pd_zc = atoi(v);
+    if (const char *v = getenv("NSOL_LSMR_PATH")) ctx->lsmr_path = atoi(v);
     *out = ctx;
     return NSOL_OK;
 }
@@ -53,6 +54,7 @@ extern "C" int nsol_set_tuning(nsol_ctx *ctx, const char *key, int value) {
     else if (!strcmp(key, "pd_ty")) ctx->pd_ty = value;
     else if (!strcmp(key, "pd_variant")) ctx->pd_variant = value;
     else if (!strcmp(key, "lsmr_blocks")) ctx->lsmr_blocks = value;
+    else if (!strcmp(key, "lsmr_path")) ctx->lsmr_path = value;
     else return nsol_fail(ctx, NSOL_EINVAL, "nsol_set_tuning: unknown key '%s'", key);
     return NSOL_OK;
 }

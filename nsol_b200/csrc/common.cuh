@@ -19,6 +19,7 @@ struct nsol_ctx {
     int pd_ty = 0;
     int pd_variant = 0;
     int lsmr_blocks = 0;
+    int lsmr_path = 0;      // 0 auto (cooperative single launch), 1 multi-kernel, 2 cooperative
     std::string err;
 };
 

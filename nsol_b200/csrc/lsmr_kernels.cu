@@ -84,61 +84,51 @@ __device__ __forceinline__ void sym_ortho(double a, double b, double &c, double 
 // ---------------------------------------------------------------------------
 // scalar kernels (one block)
 // ---------------------------------------------------------------------------
+// The scalar steps as device functions on a LsmrScalars block (global memory for the multi-kernel
+// path, shared memory for the cooperative kernel).  `ss` is the freshly reduced sum of squares.
+
 // after the right-hand side has been written into u: beta = ||b||
-__global__ void lsmr_scalar_init_beta(LsmrScalars *S, const double *part, int count, double sqrt_alpha, int maxiter) {
-    const double ss = reduce_partials(part, count);
-    if (threadIdx.x == 0) {
-        const double beta = sqrt(ss);
-        S->normb = beta;
-        S->beta = beta;
-        S->inv_beta = beta > 0.0 ? 1.0 / beta : 0.0;
-        S->sqrt_alpha = sqrt_alpha;
-        S->maxiter = maxiter;
-        S->itn = 0;
-        S->istop = 0;
-        S->done = 0;
-        S->alpha = 0.0;
-        S->inv_alpha = 0.0;
-    }
+__device__ __forceinline__ void scal_init_beta(LsmrScalars *S, double ss, double sqrt_alpha, int maxiter) {
+    const double beta = sqrt(ss);
+    S->normb = beta;
+    S->beta = beta;
+    S->inv_beta = beta > 0.0 ? 1.0 / beta : 0.0;
+    S->sqrt_alpha = sqrt_alpha;
+    S->maxiter = maxiter;
+    S->itn = 0;
+    S->istop = 0;
+    S->done = 0;
+    S->alpha = 0.0;
+    S->inv_alpha = 0.0;
 }
 
 // after v = A^T u: alpha = ||v|| and the initial values of lsmr.py:262-313
-__global__ void lsmr_scalar_init_alpha(LsmrScalars *S, const double *part, int count) {
-    const double ss = reduce_partials(part, count);
-    if (threadIdx.x == 0) {
-        const double alpha = S->beta > 0.0 ? sqrt(ss) : 0.0;
-        S->alpha = alpha;
-        S->inv_alpha = alpha > 0.0 ? 1.0 / alpha : 0.0;
-        S->zetabar = alpha * S->beta;
-        S->alphabar = alpha;
-        S->rho = 1.0; S->rhobar = 1.0; S->cbar = 1.0; S->sbar = 0.0;
-        S->betadd = S->beta; S->betad = 0.0; S->rhodold = 1.0; S->tautildeold = 0.0;
-        S->thetatilde = 0.0; S->zeta = 0.0; S->d = 0.0;
-        S->normA2 = alpha * alpha; S->maxrbar = 0.0; S->minrbar = 1e100;
-        S->normA = sqrt(S->normA2); S->condA = 1.0; S->normx = 0.0;
-        S->normr = S->beta;
-        S->normar = alpha * S->beta;
-        // lsmr.py:307-315: nothing to do if A^T b = 0 or b = 0 (x stays 0)
-        if (S->normar == 0.0 || S->normb == 0.0 || S->maxiter <= 0) S->done = 1;
-    }
+__device__ __forceinline__ void scal_init_alpha(LsmrScalars *S, double ss) {
+    const double alpha = S->beta > 0.0 ? sqrt(ss) : 0.0;
+    S->alpha = alpha;
+    S->inv_alpha = alpha > 0.0 ? 1.0 / alpha : 0.0;
+    S->zetabar = alpha * S->beta;
+    S->alphabar = alpha;
+    S->rho = 1.0; S->rhobar = 1.0; S->cbar = 1.0; S->sbar = 0.0;
+    S->betadd = S->beta; S->betad = 0.0; S->rhodold = 1.0; S->tautildeold = 0.0;
+    S->thetatilde = 0.0; S->zeta = 0.0; S->d = 0.0;
+    S->normA2 = alpha * alpha; S->maxrbar = 0.0; S->minrbar = 1e100;
+    S->normA = sqrt(S->normA2); S->condA = 1.0; S->normx = 0.0;
+    S->normr = S->beta;
+    S->normar = alpha * S->beta;
+    // lsmr.py:307-315: nothing to do if A^T b = 0 or b = 0 (x stays 0)
+    if (S->normar == 0.0 || S->normb == 0.0 || S->maxiter <= 0) S->done = 1;
 }
 
 // beta_{k+1} = ||u||  (lsmr.py:338-340)
-__global__ void lsmr_scalar_beta(LsmrScalars *S, const double *part, int count) {
-    if (S->done) return;
-    const double ss = reduce_partials(part, count);
-    if (threadIdx.x == 0) {
-        const double beta = sqrt(ss);
-        S->beta = beta;
-        S->inv_beta = beta > 0.0 ? 1.0 / beta : 0.0;
-    }
+__device__ __forceinline__ void scal_beta(LsmrScalars *S, double ss) {
+    const double beta = sqrt(ss);
+    S->beta = beta;
+    S->inv_beta = beta > 0.0 ? 1.0 / beta : 0.0;
 }
 
 // alpha_{k+1} = ||v|| and the two plane rotations (lsmr.py:344-377, 379-412)
-__global__ void lsmr_scalar_alpha(LsmrScalars *S, const double *part, int count) {
-    if (S->done) return;
-    const double ss = reduce_partials(part, count);
-    if (threadIdx.x != 0) return;
+__device__ __forceinline__ void scal_alpha(LsmrScalars *S, double ss) {
     double alpha = S->alpha;
     const double beta = S->beta;
     if (beta > 0.0) {
@@ -194,10 +184,7 @@ __global__ void lsmr_scalar_alpha(LsmrScalars *S, const double *part, int count)
 }
 
 // ||x|| and the stopping rules with atol = btol = 0, conlim = 1e8 (lsmr.py:418-459)
-__global__ void lsmr_scalar_tests(LsmrScalars *S, const double *part, int count) {
-    if (S->done) return;
-    const double ss = reduce_partials(part, count);
-    if (threadIdx.x != 0) return;
+__device__ __forceinline__ void scal_tests(LsmrScalars *S, double ss) {
     S->normx = sqrt(ss);
     const double normb = S->normb, normA = S->normA, normr = S->normr;
     const double test1 = normr / normb;
@@ -216,6 +203,30 @@ __global__ void lsmr_scalar_tests(LsmrScalars *S, const double *part, int count)
     if (test1 <= rtol) istop = 1;
     S->istop = istop;
     if (istop > 0) S->done = 1;
+}
+
+__global__ void lsmr_scalar_init_beta(LsmrScalars *S, const double *part, int count, double sqrt_alpha, int maxiter) {
+    const double ss = reduce_partials(part, count);
+    if (threadIdx.x == 0) scal_init_beta(S, ss, sqrt_alpha, maxiter);
+}
+__global__ void lsmr_scalar_init_alpha(LsmrScalars *S, const double *part, int count) {
+    const double ss = reduce_partials(part, count);
+    if (threadIdx.x == 0) scal_init_alpha(S, ss);
+}
+__global__ void lsmr_scalar_beta(LsmrScalars *S, const double *part, int count) {
+    if (S->done) return;
+    const double ss = reduce_partials(part, count);
+    if (threadIdx.x == 0) scal_beta(S, ss);
+}
+__global__ void lsmr_scalar_alpha(LsmrScalars *S, const double *part, int count) {
+    if (S->done) return;
+    const double ss = reduce_partials(part, count);
+    if (threadIdx.x == 0) scal_alpha(S, ss);
+}
+__global__ void lsmr_scalar_tests(LsmrScalars *S, const double *part, int count) {
+    if (S->done) return;
+    const double ss = reduce_partials(part, count);
+    if (threadIdx.x == 0) scal_tests(S, ss);
 }
 
 // ---------------------------------------------------------------------------
@@ -420,13 +431,18 @@ struct nsol_lsmr_plan {
     double *part = nullptr;
     LsmrScalars *S = nullptr;
     size_t bytes = 0;
+    // cooperative single-launch path
+    void *taps_dev = nullptr;      // blur taps of all axes in the plan dtype
+    int tap_off[3] = {0, 0, 0};
+    double *coop_part = nullptr;   // [3][coop_blocks]
+    int coop_blocks = 0;           // 0: not initialised, -1: unavailable
 };
 
 extern "C" void nsol_lsmr_plan_destroy(nsol_lsmr_plan *pl) {
     if (!pl) return;
     if (pl->ctx) nsol_bind_device(pl->ctx);
     void *ptrs[] = {pl->u, pl->v, pl->h, pl->hbar, pl->x, pl->opbuf, pl->optmp, pl->breg, pl->admm_v, pl->admm_w,
-                    pl->bbuf, pl->xbuf, pl->stage, pl->part, pl->S};
+                    pl->bbuf, pl->xbuf, pl->stage, pl->part, pl->S, pl->taps_dev, pl->coop_part};
     for (void *p : ptrs) cudaFree(p);
     if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
     delete pl;
@@ -572,8 +588,102 @@ static int lsmr_solve_t(nsol_lsmr_plan *pl, double alpha, const void *b_dev, con
     return NSOL_OK;
 }
 
+#include "lsmr_coop.cuh"
+
+// one-time setup of the cooperative path: taps on the device, co-resident grid size, partial sums
+template <typename T>
+static int coop_prepare(nsol_lsmr_plan *pl) {
+    nsol_ctx *ctx = pl->ctx;
+    if (pl->coop_blocks != 0) return NSOL_OK;
+    int coop = 0;
+    NSOL_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+    if (!coop) {
+        pl->coop_blocks = -1;
+        return NSOL_OK;
+    }
+    std::vector<T> taps;
+    for (int a = 0; a < pl->gv.dim; ++a) {
+        pl->tap_off[a] = (int)taps.size();
+        for (double t : pl->taps[a]) taps.push_back((T)t);
+    }
+    if (taps.empty()) taps.push_back(T(0));
+    NSOL_CUDA(ctx, cudaMalloc(&pl->taps_dev, taps.size() * sizeof(T)));
+    NSOL_CUDA(ctx, cudaMemcpy(pl->taps_dev, taps.data(), taps.size() * sizeof(T), cudaMemcpyHostToDevice));
+    int per_sm = 0;
+    NSOL_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lsmr_coop_kernel<T>, LSMR_THREADS, 0));
+    if (per_sm < 1) {
+        pl->coop_blocks = -1;
+        return NSOL_OK;
+    }
+    if (per_sm > 4) per_sm = 4;   // grid.sync() cost grows with the number of blocks
+    long long want = (pl->gv.n + LSMR_THREADS - 1) / LSMR_THREADS;
+    long long cap = (long long)per_sm * ctx->sm_count;
+    const int blocks = (int)(want < cap ? (want > 0 ? want : 1) : cap);
+    NSOL_CUDA(ctx, cudaMalloc((void **)&pl->coop_part, sizeof(double) * 3 * (size_t)blocks));
+    pl->coop_blocks = blocks;
+    return NSOL_OK;
+}
+
+// whole solve (admm_iters == 0) or whole ADMM run (admm_iters > 0) in one cooperative launch
+template <typename T>
+static int lsmr_solve_coop(nsol_lsmr_plan *pl, double alpha, const void *b_dev, void *breg_dev, int maxiter, double lo, double hi,
+                           void *x_out, int admm_iters, double ell, cudaStream_t s) {
+    nsol_ctx *ctx = pl->ctx;
+    CoopArgs<T> a;
+    a.g = make_geom<T>(pl);
+    const bool use_b = alpha > 1e-10 && pl->rows_b > 0;
+    if (!use_b) a.g.b_op = NSOL_B_NONE;
+    a.rows_b = use_b ? pl->rows_b : 0;
+    a.a_blur = pl->desc.a_op == NSOL_A_BLUR;
+    long long acc = 1;
+    for (int ax = 2; ax >= 0; --ax) {
+        a.np_stride[ax] = 0;
+        a.np_extent[ax] = 1;
+        a.radius[ax] = 0;
+        a.tap_off[ax] = 0;
+    }
+    for (int ax = pl->gv.dim - 1; ax >= 0; --ax) {
+        a.np_stride[ax] = acc;
+        a.np_extent[ax] = (int)pl->grid.shape[ax];
+        acc *= pl->grid.shape[ax];
+        a.radius[ax] = a.a_blur ? pl->desc.radius[ax] : 0;
+        a.tap_off[ax] = pl->tap_off[ax];
+    }
+    a.taps = (const T *)pl->taps_dev;
+    a.b = (const T *)b_dev;
+    a.breg = use_b ? (T *)breg_dev : nullptr;
+    a.u = (T *)pl->u; a.v = (T *)pl->v; a.h = (T *)pl->h; a.hbar = (T *)pl->hbar; a.x = (T *)pl->x;
+    a.opbuf = (T *)pl->opbuf; a.optmp = (T *)pl->optmp;
+    a.xout = (T *)x_out;
+    a.part = pl->coop_part;
+    a.S = pl->S;
+    a.sqrt_alpha = use_b ? sqrt(alpha) : 0.0;
+    a.lo = lo; a.hi = hi;
+    a.maxiter = maxiter;
+    a.admm_iters = admm_iters;
+    a.ell = (T)ell;
+    a.admm_v = (T *)pl->admm_v; a.admm_w = (T *)pl->admm_w;
+    void *params[] = {(void *)&a};
+    NSOL_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)lsmr_coop_kernel<T>, dim3(pl->coop_blocks), dim3(LSMR_THREADS), params, 0, s));
+    ctx->launches++;
+    return NSOL_OK;
+}
+
+static int lsmr_use_coop(nsol_lsmr_plan *pl) {
+    if (pl->ctx->lsmr_path == 1) return 0;
+    int rc = pl->gv.dtype == NSOL_F32 ? coop_prepare<float>(pl) : coop_prepare<double>(pl);
+    if (rc != NSOL_OK) return rc;
+    return pl->coop_blocks > 0 ? 1 : 0;
+}
+
 static int lsmr_solve_any(nsol_lsmr_plan *pl, double alpha, const void *b_dev, const void *breg_dev, int maxiter, double lo, double hi,
                           void *x_out, cudaStream_t s) {
+    const int coop = lsmr_use_coop(pl);
+    if (coop < 0) return coop;
+    if (coop) {
+        if (pl->gv.dtype == NSOL_F32) return lsmr_solve_coop<float>(pl, alpha, b_dev, (void *)breg_dev, maxiter, lo, hi, x_out, 0, 0.0, s);
+        return lsmr_solve_coop<double>(pl, alpha, b_dev, (void *)breg_dev, maxiter, lo, hi, x_out, 0, 0.0, s);
+    }
     if (pl->gv.dtype == NSOL_F32) return lsmr_solve_t<float>(pl, alpha, b_dev, breg_dev, maxiter, lo, hi, x_out, s);
     return lsmr_solve_t<double>(pl, alpha, b_dev, breg_dev, maxiter, lo, hi, x_out, s);
 }
@@ -670,6 +780,18 @@ static int admm_iterations_t(nsol_lsmr_plan *pl, double alpha, double rho, int i
         NSOL_LAUNCH_CHECK(ctx);
         return NSOL_OK;
     };
+    const int coop = lsmr_use_coop(pl);
+    if (coop < 0) return coop;
+    if (coop && iterations > 0) {
+        // cooperative path: the whole ADMM run is ONE launch (or one per outer iteration when the
+        // observer wants every iterate)
+        if (!iterates_host) return lsmr_solve_coop<T>(pl, rho, b_dev, breg, iter_max, 0.0, INFINITY, x_dev, iterations, alpha / rho, s);
+        for (int it = 0; it < iterations; ++it) {
+            NSOL_CHECK(lsmr_solve_coop<T>(pl, rho, b_dev, breg, iter_max, 0.0, INFINITY, x_dev, 1, alpha / rho, s));
+            NSOL_CHECK(lsq_download(pl, x_dev, x_scale, iterates_host + (size_t)(it + 1) * n, s));
+        }
+        return NSOL_OK;
+    }
     if (iterates_host || iterations < 2) {
         // observer attached (one download per outer iteration), or nothing to replay
         for (int it = 0; it < iterations; ++it) {

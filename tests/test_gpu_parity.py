@@ -519,3 +519,48 @@ def test_standalone_prox_linear_least_squares(golden):
     ref = orc.tikhonov_lsmr(Ao, Ao_adj, ident, ident, obs.flatten() / xs, obs.flatten() / xs, alpha=1 / 0.3, b_reg=x,
                             iter_max=10, x_scale=xs)
     assert rel_max(got, ref) < F64_LSMR_TOL
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_lsmr_multi_kernel_and_cooperative_paths(golden, path):
+    """Both LSMR implementations (1 = one kernel per phase + CUDA graph for ADMM, 2 = a single
+    cooperative launch with grid.sync between phases) against the reference fixtures."""
+    ctx = _lib.context()
+    ctx.set_tuning("lsmr_path", path)
+    try:
+        for name in ("admm_1d", "admm_2d", "admm_2d_c3crop", "admm_3d", "tk_2d_TK0", "tk_3d_TK1", "pdd_2d_TV"):
+            meta = golden.manifest["lsmr"][name]
+            obs = golden("lsmr", "in/" + meta["input"])
+            xs = meta.get("x_scale") or float(obs.max())
+            A, A_adj, D, D_adj = deconv_callables(obs.shape, meta["var"])
+            if meta["kind"] == "admm":
+                s = admm.ADMMLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=D, B_adj=D_adj, x0=obs.flatten(),
+                                          dimension=obs.ndim, alpha=meta["alpha"], rho=meta["rho"],
+                                          iterations=meta["iterations"], iter_max=meta["iter_max"], x_scale=xs)
+            elif meta["kind"] == "tikhonov":
+                ident = lambda x: x.flatten()
+                B, B_adj = (D, D_adj) if meta["reg"] == "TK1" else (ident, ident)
+                s = tk.TikhonovLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=B, B_adj=B_adj, x0=obs.flatten(),
+                                            alpha=meta["alpha"], iter_max=meta["iter_max"], x_scale=xs)
+            else:
+                s = make_pd_deconv(obs, meta["var"], meta["reg"], meta["alpha"], meta["iterations"], meta["iter_max"], xs,
+                                   meta["L2"])
+            s.run()
+            assert rel_max(s.get_x(), golden("lsmr", name)) < F64_LSMR_TOL, (path, name)
+        # observer path: every ADMM iterate
+        from nsol_b200.observer import Observer
+        obs = golden("lsmr", "in/bw2d")
+        A, A_adj, D, D_adj = deconv_callables(obs.shape, [1.5, 1.5])
+        Ao, Ao_adj, Do, Do_adj = orc.deconvolution_operators(obs.shape, np.diag([1.5, 1.5]))
+        s = admm.ADMMLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=D, B_adj=D_adj, x0=obs.flatten(), dimension=2,
+                                  alpha=0.01, rho=0.5, iterations=4, iter_max=6, x_scale=float(obs.max()))
+        o = Observer()
+        s.set_observer(o)
+        s.run()
+        _, its = orc.admm_tv(Ao, Ao_adj, Do, Do_adj, obs.reshape(-1), obs.reshape(-1), 2, alpha=0.01, rho=0.5, iterations=4,
+                             iter_max=6, x_scale=float(obs.max()), keep_iterates=True)
+        assert len(o.get_x_list()) == 5
+        for a, b in zip(o.get_x_list(), its):
+            assert rel_max(a, b) < F64_LSMR_TOL
+    finally:
+        ctx.set_tuning("lsmr_path", 0)
