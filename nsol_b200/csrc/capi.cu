@@ -37,6 +37,7 @@ extern "C" int nsol_create(int device, nsol_ctx **out) {
     if (const char *v = getenv("NSOL_PD_TY")) ctx->pd_ty = atoi(v);
     if (const char *v = getenv("NSOL_PD_ZC")) ctx->pd_zc = atoi(v);
     if (const char *v = getenv("NSOL_LSMR_PATH")) ctx->lsmr_path = atoi(v);
+    if (const char *v = getenv("NSOL_LSMR_BLOCKS")) ctx->lsmr_blocks = atoi(v);
     *out = ctx;
     return NSOL_OK;
 }

@@ -40,18 +40,59 @@ struct CoopArgs {
     T *admm_v, *admm_w;
 };
 
+// Row-wise work distribution for the stencil phases: a work item is a run of up to COOP_RUN
+// contiguous x-elements of one (y, z) row, so the (x, y, z) coordinates cost one 32-bit division
+// per item instead of two 64-bit divisions per element.  f(i, idx) with idx = {ix, iy, iz}.
+template <typename T, typename F>
+__device__ __forceinline__ void coop_for_each(const LsqGeom<T> &g, F f) {
+    const int lane = threadIdx.x & 31;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned long long rows = (unsigned long long)g.ny * g.nz;
+    // run length: as long as possible while every warp still gets about two items
+    int run_len = 256;
+    while (run_len > 32 && rows * (unsigned)((g.nx + run_len - 1) / run_len) < 2ull * nwarps) run_len >>= 1;
+    const unsigned runs = (unsigned)((g.nx + run_len - 1) / run_len);
+    const unsigned long long items = rows * runs;
+    for (unsigned long long item = warp; item < items; item += nwarps) {
+        const unsigned row = (unsigned)(item / runs), run = (unsigned)(item - (unsigned long long)row * runs);
+        int idx[3];
+        idx[2] = (int)(row / (unsigned)g.ny);
+        idx[1] = (int)(row - (unsigned)idx[2] * (unsigned)g.ny);
+        const long long base = (long long)row * g.nx;
+        const int x_end = min(g.nx, (int)(run + 1) * run_len);
+        for (int ix = (int)run * run_len + lane; ix < x_end; ix += 32) {
+            idx[0] = ix;
+            f(base + ix, idx);
+        }
+    }
+}
+
+// kernel axis (0 = x, 1 = y, 2 = z) of numpy axis `ax`
+__device__ __forceinline__ int coop_kaxis(int dim, int ax) { return ax == dim - 1 ? 0 : ((dim == 3 && ax == 1) ? 1 : 2); }
+
+// periodic 1-D convolution along numpy axis `axis` at element i with coordinates idx
 template <typename T>
-__device__ __forceinline__ T coop_blur_at(const CoopArgs<T> &a, const T *in, long long i, int axis) {
+__device__ __forceinline__ T coop_blur_at(const CoopArgs<T> &a, const T *in, long long i, const int idx[3], int axis) {
     const long long st = a.np_stride[axis];
     const int ext = a.np_extent[axis], r = a.radius[axis];
-    const int pos = (int)((i / st) % ext);
-    const long long base = i - (long long)pos * st;
+    const int pos = idx[coop_kaxis(a.g.dim, axis)];
+    const T *line = in + (i - (long long)pos * st);
     const T *tp = a.taps + a.tap_off[axis];
     T acc = T(0);
-    for (int k = 0; k <= 2 * r; ++k) {
-        int q = (pos - (k - r)) % ext;
-        if (q < 0) q += ext;
-        acc += tp[k] * in[base + (long long)q * st];
+    if (r < ext) {      // wrap with one conditional add/subtract
+        for (int k = 0; k <= 2 * r; ++k) {
+            int q = pos - (k - r);
+            q += q < 0 ? ext : 0;
+            q -= q >= ext ? ext : 0;
+            acc += tp[k] * line[(long long)q * st];
+        }
+    } else {            // mask wider than the axis: general modulo
+        for (int k = 0; k <= 2 * r; ++k) {
+            int q = (pos - (k - r)) % ext;
+            if (q < 0) q += ext;
+            acc += tp[k] * line[(long long)q * st];
+        }
     }
     return acc;
 }
@@ -60,12 +101,10 @@ __device__ __forceinline__ T coop_blur_at(const CoopArgs<T> &a, const T *in, lon
 template <typename T>
 __device__ const T *coop_blur_front(const CoopArgs<T> &a, cg::grid_group &grid, const T *in) {
     const int dim = a.g.dim;
-    const long long n = a.g.n;
     const T *src = in;
     for (int ax = 0; ax + 1 < dim; ++ax) {
         T *dst = (src == a.optmp) ? a.opbuf : a.optmp;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-            dst[i] = coop_blur_at(a, src, i, ax);
+        coop_for_each(a.g, [&](long long i, const int idx[3]) { dst[i] = coop_blur_at(a, src, i, idx, ax); });
         grid.sync();
         src = dst;
     }
@@ -110,11 +149,9 @@ __global__ void __launch_bounds__(LSMR_THREADS) lsmr_coop_kernel(const CoopArgs<
             const T *src = a.a_blur ? coop_blur_front(a, grid, a.u) : a.u;
             const T inv_beta = (T)S.inv_beta;
             double acc = 0.0;
-            for (long long i = gtid; i < n; i += gstride) {
-                T r = (a.a_blur ? coop_blur_at(a, src, i, last_ax) : src[i]) * inv_beta;
+            coop_for_each(g, [&](long long i, const int idx[3]) {
+                T r = (a.a_blur ? coop_blur_at(a, src, i, idx, last_ax) : src[i]) * inv_beta;
                 if (g.b_op == NSOL_B_GRAD) {
-                    int idx[3];
-                    lsq_decode(g, i, idx);
                     T div = T(0);
                     for (int k = 0; k < g.dim; ++k) {
                         const T *uk = a.u + (long long)(1 + k) * n;
@@ -128,7 +165,7 @@ __global__ void __launch_bounds__(LSMR_THREADS) lsmr_coop_kernel(const CoopArgs<
                 }
                 a.v[i] = r;
                 acc += (double)r * (double)r;
-            }
+            });
             acc = block_sum(acc);
             if (threadIdx.x == 0) part_v[blockIdx.x] = acc;
         }
@@ -168,14 +205,12 @@ __global__ void __launch_bounds__(LSMR_THREADS) lsmr_coop_kernel(const CoopArgs<
             {   // u <- (u * inv_beta) * (-alpha) + [A v; sqrt_alpha B v]
                 const T inv_alpha = (T)S.inv_alpha, inv_beta = (T)S.inv_beta, malpha = (T)(-S.alpha);
                 double acc = 0.0;
-                for (long long i = gtid; i < n; i += gstride) {
-                    const T av = (a.a_blur ? coop_blur_at(a, src, i, last_ax) : src[i]) * inv_alpha;
+                coop_for_each(g, [&](long long i, const int idx[3]) {
+                    const T av = (a.a_blur ? coop_blur_at(a, src, i, idx, last_ax) : src[i]) * inv_alpha;
                     T un = (a.u[i] * inv_beta) * malpha + av;
                     a.u[i] = un;
                     acc += (double)un * (double)un;
                     if (g.b_op == NSOL_B_GRAD) {
-                        int idx[3];
-                        lsq_decode(g, i, idx);
                         const T vc = a.v[i] * inv_alpha;
                         for (int k = 0; k < g.dim; ++k) {
                             const T hi = (idx[g.axis[k]] + 1 < g.extent[k]) ? a.v[i + g.stride[k]] * inv_alpha : T(0);
@@ -191,7 +226,7 @@ __global__ void __launch_bounds__(LSMR_THREADS) lsmr_coop_kernel(const CoopArgs<
                         uk[i] = un;
                         acc += (double)un * (double)un;
                     }
-                }
+                });
                 acc = block_sum(acc);
                 if (threadIdx.x == 0) part_u[blockIdx.x] = acc;
             }
@@ -206,11 +241,9 @@ __global__ void __launch_bounds__(LSMR_THREADS) lsmr_coop_kernel(const CoopArgs<
             {   // v <- (v * inv_alpha) * (-beta) + (A^T u0 + sqrt_alpha B^T u1..)
                 const T inv_alpha = (T)S.inv_alpha, inv_beta = (T)S.inv_beta, mbeta = (T)(-S.beta);
                 double acc = 0.0;
-                for (long long i = gtid; i < n; i += gstride) {
-                    T r = (a.a_blur ? coop_blur_at(a, src, i, last_ax) : src[i]) * inv_beta;
+                coop_for_each(g, [&](long long i, const int idx[3]) {
+                    T r = (a.a_blur ? coop_blur_at(a, src, i, idx, last_ax) : src[i]) * inv_beta;
                     if (g.b_op == NSOL_B_GRAD) {
-                        int idx[3];
-                        lsq_decode(g, i, idx);
                         T div = T(0);
                         for (int k = 0; k < g.dim; ++k) {
                             const T *uk = a.u + (long long)(1 + k) * n;
@@ -226,7 +259,7 @@ __global__ void __launch_bounds__(LSMR_THREADS) lsmr_coop_kernel(const CoopArgs<
                     // v is also read at neighbouring indices by nobody in this phase: in-place is safe
                     a.v[i] = vn;
                     acc += (double)vn * (double)vn;
-                }
+                });
                 acc = block_sum(acc);
                 if (threadIdx.x == 0) part_v[blockIdx.x] = acc;
             }
@@ -268,9 +301,7 @@ __global__ void __launch_bounds__(LSMR_THREADS) lsmr_coop_kernel(const CoopArgs<
         }
         if (a.admm_iters > 0) {
             grid.sync();
-            for (long long i = gtid; i < n; i += gstride) {
-                int idx[3];
-                lsq_decode(g, i, idx);
+            coop_for_each(g, [&](long long i, const int idx[3]) {
                 const T xc = a.xout[i];
                 T t[3];
                 T ss = T(0);
@@ -290,7 +321,7 @@ __global__ void __launch_bounds__(LSMR_THREADS) lsmr_coop_kernel(const CoopArgs<
                     a.admm_w[(long long)k * n + i] = wk;
                     a.breg[(long long)k * n + i] = vk - wk;
                 }
-            }
+            });
             grid.sync();
         }
     }

@@ -618,6 +618,7 @@ static int coop_prepare(nsol_lsmr_plan *pl) {
     if (per_sm > 4) per_sm = 4;   // grid.sync() cost grows with the number of blocks
     long long want = (pl->gv.n + LSMR_THREADS - 1) / LSMR_THREADS;
     long long cap = (long long)per_sm * ctx->sm_count;
+    if (ctx->lsmr_blocks > 0 && ctx->lsmr_blocks < cap) cap = ctx->lsmr_blocks;
     const int blocks = (int)(want < cap ? (want > 0 ? want : 1) : cap);
     NSOL_CUDA(ctx, cudaMalloc((void **)&pl->coop_part, sizeof(double) * 3 * (size_t)blocks));
     pl->coop_blocks = blocks;
@@ -669,8 +670,13 @@ static int lsmr_solve_coop(nsol_lsmr_plan *pl, double alpha, const void *b_dev, 
     return NSOL_OK;
 }
 
+// Path choice (measured on B200, profiles/r1_lsmr_paths.md): the single cooperative launch wins while
+// the vectors are small enough to be latency / launch bound (<= 2^20 elements: 44 vs 57 us per inner
+// iteration at 512^2); for larger problems one kernel per phase (more threads in flight than a
+// co-resident grid allows) is faster.
 static int lsmr_use_coop(nsol_lsmr_plan *pl) {
     if (pl->ctx->lsmr_path == 1) return 0;
+    if (pl->ctx->lsmr_path == 0 && pl->gv.n > (1ll << 20)) return 0;
     int rc = pl->gv.dtype == NSOL_F32 ? coop_prepare<float>(pl) : coop_prepare<double>(pl);
     if (rc != NSOL_OK) return rc;
     return pl->coop_blocks > 0 ? 1 : 0;
