@@ -35,27 +35,37 @@ struct LsmrScalars {
 // reductions
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double block_sum(double v) {
-    __shared__ double warp_part[LSMR_THREADS / 32];
+    __shared__ double warp_part[32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
     __syncthreads();   // protect warp_part against a previous call
     if (lane == 0) warp_part[wid] = v;
     __syncthreads();
     double r = 0.0;
     if (wid == 0) {
-        r = lane < LSMR_THREADS / 32 ? warp_part[lane] : 0.0;
+        r = lane < nwarps ? warp_part[lane] : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
     }
     return r;   // valid in thread 0
 }
 
-// sum of `count` partials, fixed order; result valid in thread 0 (one block)
+// sum of `count` partials in a fixed order (deterministic); result valid in thread 0 (one block).
+// Four independent accumulators per thread keep several loads in flight.
 __device__ __forceinline__ double reduce_partials(const double *part, int count) {
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < count; i += blockDim.x) acc += part[i];
-    return block_sum(acc);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const int step = blockDim.x;
+    int i = threadIdx.x;
+    for (; i + 3 * step < count; i += 4 * step) {
+        a0 += part[i];
+        a1 += part[i + step];
+        a2 += part[i + 2 * step];
+        a3 += part[i + 3 * step];
+    }
+    for (; i < count; i += step) a0 += part[i];
+    return block_sum((a0 + a1) + (a2 + a3));
 }
 
 // ---------------------------------------------------------------------------
@@ -245,6 +255,14 @@ struct LsqGeom {
 
 template <typename T>
 __device__ __forceinline__ void lsq_decode(const LsqGeom<T> &g, long long r, int idx[3]) {
+    if (g.n <= 0x7fffffffLL) {      // 32-bit division is ~5x cheaper than the 64-bit sequence
+        const unsigned r32 = (unsigned)r, nx = (unsigned)g.nx, ny = (unsigned)g.ny;
+        const unsigned t = r32 / nx;
+        idx[0] = (int)(r32 - t * nx);
+        idx[2] = (int)(t / ny);
+        idx[1] = (int)(t - (unsigned)idx[2] * ny);
+        return;
+    }
     idx[0] = (int)(r % g.nx);
     const long long t = r / g.nx;
     idx[1] = (int)(t % g.ny);
@@ -268,21 +286,70 @@ __global__ void lsmr_rhs_kernel(LsqGeom<T> g, int rows_b, const T *__restrict__ 
     if (threadIdx.x == 0) part[blockIdx.x] = acc;
 }
 
-// u <- (u * inv_beta) * (-alpha) + [Av; sqrt_alpha * B v],  v = vhat * inv_alpha   (lsmr.py:336-337)
-// Av_hat holds A(vhat) (un-normalised; A is linear) or equals vhat when A is the identity.
+// ---------------------------------------------------------------------------
+// row-mapped vector kernels of the multi-kernel path: grid = (ceil(nx / FAST_TH), ny, nz), so a
+// thread knows its (x, y, z) without any integer division, the separable blur wraps with a
+// conditional add/subtract, and the LAST blur pass (along x) is fused into the consumer.
+// ---------------------------------------------------------------------------
+#define FAST_TH 256
+#define FAST_MAX_TAPS 129
+
 template <typename T>
-__global__ void lsmr_fwd_kernel(LsqGeom<T> g, const LsmrScalars *__restrict__ S, const T *__restrict__ Av_hat, const T *__restrict__ vhat,
-                                T *__restrict__ u, double *__restrict__ part) {
+struct TapArgs {
+    T t[FAST_MAX_TAPS];
+    int r;   // radius; -1: no blur (identity)
+};
+
+template <typename T>
+__device__ __forceinline__ T fast_blur_line(const TapArgs<T> &tp, const T *line, int pos, int ext, long long st) {
+    T acc = T(0);
+    const int r = tp.r;
+    if (r < ext) {
+        for (int k = 0; k <= 2 * r; ++k) {
+            int q = pos - (k - r);
+            q += q < 0 ? ext : 0;
+            q -= q >= ext ? ext : 0;
+            acc += tp.t[k] * line[(long long)q * st];
+        }
+    } else {
+        for (int k = 0; k <= 2 * r; ++k) {
+            int q = (pos - (k - r)) % ext;
+            if (q < 0) q += ext;
+            acc += tp.t[k] * line[(long long)q * st];
+        }
+    }
+    return acc;
+}
+
+// one separable pass along kernel axis kaxis (0 = x, 1 = y, 2 = z)
+template <typename T>
+__global__ void __launch_bounds__(FAST_TH) fast_blur_pass_kernel(LsqGeom<T> g, const __grid_constant__ TapArgs<T> tp, int kaxis,
+                                                                 const T *__restrict__ in, T *__restrict__ out) {
+    const int idx[3] = {(int)(blockIdx.x * FAST_TH + threadIdx.x), (int)blockIdx.y, (int)blockIdx.z};
+    if (idx[0] >= g.nx) return;
+    const long long i = ((long long)idx[2] * g.ny + idx[1]) * g.nx + idx[0];
+    const long long st = kaxis == 0 ? 1 : (kaxis == 1 ? g.nx : (long long)g.nx * g.ny);
+    const int ext = kaxis == 0 ? g.nx : (kaxis == 1 ? g.ny : g.nz);
+    out[i] = fast_blur_line(tp, in + (i - (long long)idx[kaxis] * st), idx[kaxis], ext, st);
+}
+
+// u <- (u * inv_beta) * (-alpha) + [A v; sqrt_alpha B v], v = vhat * inv_alpha, partial ||u||^2   (lsmr.py:336-338)
+// src: vhat after the blur passes along z / y; the pass along x is applied here.
+template <typename T>
+__global__ void __launch_bounds__(FAST_TH) fast_fwd_kernel(LsqGeom<T> g, const LsmrScalars *__restrict__ S, const __grid_constant__ TapArgs<T> tx,
+                                                           const T *__restrict__ src, const T *__restrict__ vhat, T *__restrict__ u,
+                                                           double *__restrict__ part) {
     if (S->done) return;
-    const T inv_alpha = (T)S->inv_alpha, inv_beta = (T)S->inv_beta, malpha = (T)(-S->alpha), sa = (T)S->sqrt_alpha;
+    const int idx[3] = {(int)(blockIdx.x * FAST_TH + threadIdx.x), (int)blockIdx.y, (int)blockIdx.z};
     double acc = 0.0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += (long long)gridDim.x * blockDim.x) {
-        T un = (u[i] * inv_beta) * malpha + Av_hat[i] * inv_alpha;
+    if (idx[0] < g.nx) {
+        const T inv_alpha = (T)S->inv_alpha, inv_beta = (T)S->inv_beta, malpha = (T)(-S->alpha), sa = (T)S->sqrt_alpha;
+        const long long i = ((long long)idx[2] * g.ny + idx[1]) * g.nx + idx[0];
+        const T av = (tx.r >= 0 ? fast_blur_line(tx, src + (i - idx[0]), idx[0], g.nx, 1) : src[i]) * inv_alpha;
+        T un = (u[i] * inv_beta) * malpha + av;
         u[i] = un;
         acc += (double)un * (double)un;
         if (g.b_op == NSOL_B_GRAD) {
-            int idx[3];
-            lsq_decode(g, i, idx);
             const T vc = vhat[i] * inv_alpha;
             for (int k = 0; k < g.dim; ++k) {
                 const T hi = (idx[g.axis[k]] + 1 < g.extent[k]) ? vhat[i + g.stride[k]] * inv_alpha : T(0);
@@ -300,23 +367,22 @@ __global__ void lsmr_fwd_kernel(LsqGeom<T> g, const LsmrScalars *__restrict__ S,
         }
     }
     acc = block_sum(acc);
-    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+    if (threadIdx.x == 0) part[((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = acc;
 }
 
-// vhat <- (vhat * inv_alpha) * (-beta) + (A^T u0 + sqrt_alpha * B^T u1..),  u = uhat * inv_beta   (lsmr.py:342-343)
-// Atu_hat holds A^T(uhat_0) (un-normalised) or equals uhat_0 when A is the identity.
-// first = 1: cold start v = A^T u (no previous v).
+// vhat <- (vhat * inv_alpha) * (-beta) + (A^T u0 + sqrt_alpha B^T u1..), u = uhat * inv_beta, partial ||v||^2 (lsmr.py:342-344)
 template <typename T>
-__global__ void lsmr_adj_kernel(LsqGeom<T> g, const LsmrScalars *__restrict__ S, const T *__restrict__ Atu_hat, const T *__restrict__ u,
-                                T *__restrict__ vhat, double *__restrict__ part, int first) {
+__global__ void __launch_bounds__(FAST_TH) fast_adj_kernel(LsqGeom<T> g, const LsmrScalars *__restrict__ S, const __grid_constant__ TapArgs<T> tx,
+                                                           const T *__restrict__ src, const T *__restrict__ u, T *__restrict__ vhat,
+                                                           double *__restrict__ part, int first) {
     if (S->done) return;
-    const T inv_alpha = (T)S->inv_alpha, inv_beta = (T)S->inv_beta, mbeta = (T)(-S->beta), sa = (T)S->sqrt_alpha;
+    const int idx[3] = {(int)(blockIdx.x * FAST_TH + threadIdx.x), (int)blockIdx.y, (int)blockIdx.z};
     double acc = 0.0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += (long long)gridDim.x * blockDim.x) {
-        T r = Atu_hat[i] * inv_beta;
+    if (idx[0] < g.nx) {
+        const T inv_alpha = (T)S->inv_alpha, inv_beta = (T)S->inv_beta, mbeta = (T)(-S->beta), sa = (T)S->sqrt_alpha;
+        const long long i = ((long long)idx[2] * g.ny + idx[1]) * g.nx + idx[0];
+        T r = (tx.r >= 0 ? fast_blur_line(tx, src + (i - idx[0]), idx[0], g.nx, 1) : src[i]) * inv_beta;
         if (g.b_op == NSOL_B_GRAD) {
-            int idx[3];
-            lsq_decode(g, i, idx);
             T div = T(0);
             for (int k = 0; k < g.dim; ++k) {
                 const T *uk = u + (long long)(1 + k) * g.n;
@@ -333,7 +399,7 @@ __global__ void lsmr_adj_kernel(LsqGeom<T> g, const LsmrScalars *__restrict__ S,
         acc += (double)vn * (double)vn;
     }
     acc = block_sum(acc);
-    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+    if (threadIdx.x == 0) part[((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = acc;
 }
 
 // h = v, hbar = 0, x = 0   (lsmr.py:277-278, 253)
@@ -420,7 +486,8 @@ struct nsol_lsmr_plan {
     std::vector<double> taps[3];
     size_t esz = 8;
     int rows_b = 0;           // number of N-blocks of B rows
-    int nblocks = 0;          // blocks of the vector kernels = number of partials
+    int nblocks = 0;          // blocks of the flat vector kernels = number of their partials
+    int row_blocks = 0;       // blocks (= partials) of the row-mapped kernels: ceil(nx/FAST_TH) * ny * nz
     void *u = nullptr, *v = nullptr, *h = nullptr, *hbar = nullptr, *x = nullptr;
     void *opbuf = nullptr, *optmp = nullptr;   // A v / A^T u and separable scratch
     void *breg = nullptr;                      // b_reg staging (rows_b * N)
@@ -478,6 +545,7 @@ extern "C" int nsol_lsmr_plan_create(nsol_ctx *ctx, const nsol_lsq_desc *desc, n
     long long want = (gv.n + LSMR_THREADS - 1) / LSMR_THREADS;
     long long cap = ctx->lsmr_blocks > 0 ? ctx->lsmr_blocks : (long long)ctx->sm_count * 8;
     pl->nblocks = (int)(want < cap ? (want > 0 ? want : 1) : cap);
+    pl->row_blocks = ((gv.nx + FAST_TH - 1) / FAST_TH) * gv.ny * gv.nz;
     const size_t nb = (size_t)gv.n * pl->esz;
     auto alloc = [&](void **ptr, size_t bytes) -> bool {
         cudaError_t e = cudaMalloc(ptr, bytes ? bytes : 8);
@@ -491,7 +559,7 @@ extern "C" int nsol_lsmr_plan_create(nsol_ctx *ctx, const nsol_lsq_desc *desc, n
     bool ok = alloc(&pl->u, nb * (1 + pl->rows_b)) && alloc(&pl->v, nb) && alloc(&pl->h, nb) && alloc(&pl->hbar, nb) && alloc(&pl->x, nb) &&
               alloc(&pl->opbuf, nb) && alloc(&pl->optmp, nb) && alloc(&pl->breg, nb * (pl->rows_b ? pl->rows_b : 1)) &&
               alloc(&pl->admm_v, nb * gv.dim) && alloc(&pl->admm_w, nb * gv.dim) && alloc(&pl->bbuf, nb) && alloc(&pl->xbuf, nb) &&
-              alloc((void **)&pl->part, sizeof(double) * (size_t)pl->nblocks * 2) && alloc((void **)&pl->S, sizeof(LsmrScalars));
+              alloc((void **)&pl->part, sizeof(double) * (size_t)(pl->nblocks > pl->row_blocks ? pl->nblocks : pl->row_blocks) * 2) && alloc((void **)&pl->S, sizeof(LsmrScalars));
     if (!ok) {
         nsol_lsmr_plan_destroy(pl);
         return NSOL_ENOMEM;
@@ -528,15 +596,34 @@ static LsqGeom<T> make_geom(const nsol_lsmr_plan *pl) {
     return g;
 }
 
-// A(in) -> out for the plan's data operator (un-normalised input); returns the array holding the result
-static int lsq_apply_A(nsol_lsmr_plan *pl, const void *in, const void **result, cudaStream_t s) {
-    if (pl->desc.a_op == NSOL_A_IDENTITY) {
-        *result = in;
-        return NSOL_OK;
+// taps of numpy axis `ax` as a kernel argument (r = -1: identity, no blur)
+template <typename T>
+static TapArgs<T> lsq_taps(const nsol_lsmr_plan *pl, int ax) {
+    TapArgs<T> t;
+    t.r = -1;
+    if (pl->desc.a_op == NSOL_A_BLUR && ax >= 0) {
+        t.r = pl->desc.radius[ax];
+        for (int k = 0; k <= 2 * t.r; ++k) t.t[k] = (T)pl->taps[ax][k];
     }
-    const double *taps[3] = {pl->taps[0].data(), pl->taps[1].data(), pl->taps[2].data()};
-    NSOL_CHECK(nsol_blur_sep(pl->ctx, &pl->grid, taps, pl->desc.radius, in, pl->opbuf, pl->optmp, s));
-    *result = pl->opbuf;
+    return t;
+}
+
+// blur passes along every numpy axis except the last (x): in -> optmp (-> opbuf); *result is what the
+// consumer's fused x-pass reads (in itself for 1-D problems or A = identity)
+template <typename T>
+static int lsq_blur_front(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *in, const void **result, cudaStream_t s) {
+    *result = in;
+    if (pl->desc.a_op != NSOL_A_BLUR) return NSOL_OK;
+    const dim3 grid((g.nx + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
+    const void *src = in;
+    for (int ax = 0; ax + 1 < g.dim; ++ax) {
+        void *dst = (src == pl->optmp) ? pl->opbuf : pl->optmp;
+        const int kaxis = (g.dim == 3 && ax == 1) ? 1 : 2;
+        fast_blur_pass_kernel<T><<<grid, FAST_TH, 0, s>>>(g, lsq_taps<T>(pl, ax), kaxis, (const T *)src, (T *)dst);
+        NSOL_LAUNCH_CHECK(pl->ctx);
+        src = dst;
+    }
+    *result = src;
     return NSOL_OK;
 }
 
@@ -559,24 +646,29 @@ static int lsmr_solve_t(nsol_lsmr_plan *pl, double alpha, const void *b_dev, con
     NSOL_LAUNCH_CHECK(ctx);
     lsmr_scalar_init_beta<<<1, th, 0, s>>>(pl->S, part, nb, sa, maxiter);
     NSOL_LAUNCH_CHECK(ctx);
+    if (g.ny > 65535 || g.nz > 65535)
+        return nsol_fail(ctx, NSOL_EINVAL, "lsmr (multi-kernel path): more than 65535 rows along y or z are not supported");
+    const dim3 rgrid((g.nx + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
+    const int rparts = pl->row_blocks;
+    const TapArgs<T> tx = lsq_taps<T>(pl, g.dim - 1);
     const void *op = nullptr;
-    NSOL_CHECK(lsq_apply_A(pl, u, &op, s));       // A^T = A (same mask, periodic)
-    lsmr_adj_kernel<T><<<nb, th, 0, s>>>(ge, pl->S, (const T *)op, u, v, part, 1);
+    NSOL_CHECK(lsq_blur_front<T>(pl, ge, u, &op, s));       // A^T = A (same mask, periodic)
+    fast_adj_kernel<T><<<rgrid, FAST_TH, 0, s>>>(ge, pl->S, tx, (const T *)op, u, v, part, 1);
     NSOL_LAUNCH_CHECK(ctx);
-    lsmr_scalar_init_alpha<<<1, th, 0, s>>>(pl->S, part, nb);
+    lsmr_scalar_init_alpha<<<1, 1024, 0, s>>>(pl->S, part, rparts);
     NSOL_LAUNCH_CHECK(ctx);
     lsmr_init_vectors_kernel<T><<<nb, th, 0, s>>>(g.n, pl->S, v, h, hbar, x);
     NSOL_LAUNCH_CHECK(ctx);
     for (int it = 0; it < maxiter; ++it) {
-        NSOL_CHECK(lsq_apply_A(pl, v, &op, s));
-        lsmr_fwd_kernel<T><<<nb, th, 0, s>>>(ge, pl->S, (const T *)op, v, u, part);
+        NSOL_CHECK(lsq_blur_front<T>(pl, ge, v, &op, s));
+        fast_fwd_kernel<T><<<rgrid, FAST_TH, 0, s>>>(ge, pl->S, tx, (const T *)op, v, u, part);
         NSOL_LAUNCH_CHECK(ctx);
-        lsmr_scalar_beta<<<1, th, 0, s>>>(pl->S, part, nb);
+        lsmr_scalar_beta<<<1, 1024, 0, s>>>(pl->S, part, rparts);
         NSOL_LAUNCH_CHECK(ctx);
-        NSOL_CHECK(lsq_apply_A(pl, u, &op, s));
-        lsmr_adj_kernel<T><<<nb, th, 0, s>>>(ge, pl->S, (const T *)op, u, v, part, 0);
+        NSOL_CHECK(lsq_blur_front<T>(pl, ge, u, &op, s));
+        fast_adj_kernel<T><<<rgrid, FAST_TH, 0, s>>>(ge, pl->S, tx, (const T *)op, u, v, part, 0);
         NSOL_LAUNCH_CHECK(ctx);
-        lsmr_scalar_alpha<<<1, th, 0, s>>>(pl->S, part, nb);
+        lsmr_scalar_alpha<<<1, 1024, 0, s>>>(pl->S, part, rparts);
         NSOL_LAUNCH_CHECK(ctx);
         lsmr_update_kernel<T><<<nb, th, 0, s>>>(g.n, pl->S, v, h, hbar, x, part);
         NSOL_LAUNCH_CHECK(ctx);
@@ -670,13 +762,13 @@ static int lsmr_solve_coop(nsol_lsmr_plan *pl, double alpha, const void *b_dev, 
     return NSOL_OK;
 }
 
-// Path choice (measured on B200, profiles/r1_lsmr_paths.md): the single cooperative launch wins while
-// the vectors are small enough to be latency / launch bound (<= 2^20 elements: 44 vs 57 us per inner
-// iteration at 512^2); for larger problems one kernel per phase (more threads in flight than a
-// co-resident grid allows) is faster.
+// Path choice (measured on B200, profiles/r1_lsmr_paths.md): the single cooperative launch wins only for
+// very small vectors (sync floor ~23 us per inner iteration at 256^2); from 512^2 on, one row-mapped
+// kernel per phase + CUDA-graph replay is faster (40 vs 44 us) because more threads are in flight than a
+// co-resident grid allows.
 static int lsmr_use_coop(nsol_lsmr_plan *pl) {
     if (pl->ctx->lsmr_path == 1) return 0;
-    if (pl->ctx->lsmr_path == 0 && pl->gv.n > (1ll << 20)) return 0;
+    if (pl->ctx->lsmr_path == 0 && pl->gv.n > (1ll << 17)) return 0;
     int rc = pl->gv.dtype == NSOL_F32 ? coop_prepare<float>(pl) : coop_prepare<double>(pl);
     if (rc != NSOL_OK) return rc;
     return pl->coop_blocks > 0 ? 1 : 0;

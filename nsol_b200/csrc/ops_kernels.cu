@@ -175,15 +175,26 @@ template <typename T>
 __global__ void conv_axis_wrap_kernel(const __grid_constant__ ConvAxisArgs<T> a) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long step = (long long)gridDim.x * blockDim.x;
+    const bool small = a.total <= 0x7fffffffLL;          // 32-bit index arithmetic
+    const bool narrow = a.radius < a.extent;              // wrap with one conditional add / subtract
     for (; i < a.total; i += step) {
-        const int pos = (int)((i / a.stride) % a.extent);
-        const long long base = i - (long long)pos * a.stride;
+        const int pos = small ? (int)(((unsigned)i / (unsigned)a.stride) % (unsigned)a.extent) : (int)((i / a.stride) % a.extent);
+        const T *line = a.in + (i - (long long)pos * a.stride);
         T acc = T(0);
-        for (int k = 0; k <= 2 * a.radius; ++k) {
-            int q = pos - (k - a.radius);
-            q %= a.extent;
-            if (q < 0) q += a.extent;
-            acc += a.taps[k] * a.in[base + (long long)q * a.stride];
+        if (narrow) {
+#pragma unroll 7
+            for (int k = 0; k <= 2 * a.radius; ++k) {
+                int q = pos - (k - a.radius);
+                q += q < 0 ? a.extent : 0;
+                q -= q >= a.extent ? a.extent : 0;
+                acc += a.taps[k] * line[(long long)q * a.stride];
+            }
+        } else {
+            for (int k = 0; k <= 2 * a.radius; ++k) {
+                int q = (pos - (k - a.radius)) % a.extent;
+                if (q < 0) q += a.extent;
+                acc += a.taps[k] * line[(long long)q * a.stride];
+            }
         }
         a.out[i] = acc;
     }
