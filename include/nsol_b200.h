@@ -139,6 +139,21 @@ typedef enum { NSOL_PROX_TV_CONJ = 0, NSOL_PROX_HUBER_CONJ = 1, NSOL_PROX_TK1_CO
 int nsol_prox_apply(nsol_ctx *ctx, int kind, int dtype, int64_t n, const void *x_dev, const void *x0_dev,
                     double p0, double p1, void *out_dev, nsol_stream s);
 
+/* ---- on-device measures ----------------------------------
+ * One reduction pass instead of copying an iterate to the host.  y = x * scale (the solver's
+ * x_scale), r = reference image (float64, n elements):
+ *   out[0..7] = sum y, sum y^2, sum r, sum r^2, sum y r, sum (y-r)^2, sum |y-r|, max r
+ * from which SSD / MSE / RMSE / MAE / PSNR / NCC follow (nsol/similarity_measures.py:26-120).
+ * nsol_prior_stats: out[0] = sum_i sqrt(sum_k (D_k y)_i^2)   (total variation, nsol/prior_measures.py:27-37)
+ *                   out[1] = 1/2 sum_i sum_k (D_k y)_i^2     (first-order Tikhonov, :22-24)
+ *                   out[2] = sum_i huber(|grad y|_i^2, gamma) / (2 gamma)   (:40-52)
+ *                   out[3] = 1/2 sum_i y_i^2                 (zeroth-order Tikhonov, :19-20)
+ * Results are written to host memory; the call synchronises the stream. */
+int nsol_similarity_stats(nsol_ctx *ctx, int dtype_x, int64_t n, const void *x_dev, double scale,
+                          const double *xref_dev, double *out_host8, nsol_stream s);
+int nsol_prior_stats(nsol_ctx *ctx, const nsol_grid *g, const void *x_dev, double scale, double huber_gamma,
+                     double *out_host4, nsol_stream s);
+
 /* ---- fused primal-dual (Chambolle-Pock) ----------------------------------
  * Replaces the body of PrimalDualSolver._run (nsol/primal_dual_solver.py:215-263)
  * for B = grad, B_conj = grad_adj, prox_g_conj in {tv, huber, tk1} and

@@ -72,6 +72,9 @@ SIGNATURES = {
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsol_prox_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_double,
                                   C.c_double, C.c_void_p, C.c_void_p]),
+    "nsol_similarity_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
+    "nsol_prior_stats": (C.c_int, [C.c_void_p, C.POINTER(Grid), C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "nsol_pd_plan_create": (C.c_int, [C.c_void_p, C.POINTER(PdDesc), c_void_pp]),
     "nsol_pd_plan_destroy": (None, [C.c_void_p]),
     "nsol_pd_plan_update": (C.c_int, [C.c_void_p, C.POINTER(PdDesc)]),

@@ -375,3 +375,141 @@ extern "C" int nsol_prox_apply(nsol_ctx *ctx, int kind, int dtype, int64_t n, co
     NSOL_LAUNCH_CHECK(ctx);
     return NSOL_OK;
 }
+
+// ---------------------------------------------------------------------------
+// on-device measures: one reduction pass per iterate (no copy of the iterate to the host)
+// ---------------------------------------------------------------------------
+#define STATS_THREADS 256
+#define STATS_MAX_BLOCKS 1024
+
+template <int K>
+__device__ __forceinline__ void stats_block_reduce(double (&v)[K], bool is_max_last, double *out_block) {
+    __shared__ double sm[K][STATS_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double x = v[k];
+        const bool mx = is_max_last && k == K - 1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double y = __shfl_down_sync(0xffffffffu, x, o);
+            x = mx ? fmax(x, y) : x + y;
+        }
+        if (lane == 0) sm[k][wid] = x;
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const bool mx = is_max_last && k == K - 1;
+            double x = lane < STATS_THREADS / 32 ? sm[k][lane] : (mx ? -INFINITY : 0.0);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double y = __shfl_down_sync(0xffffffffu, x, o);
+                x = mx ? fmax(x, y) : x + y;
+            }
+            if (lane == 0) out_block[k] = x;
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(STATS_THREADS) similarity_stats_kernel(long long n, const T *__restrict__ x, double scale,
+                                                                         const double *__restrict__ r, double *__restrict__ part) {
+    double v[8] = {0, 0, 0, 0, 0, 0, 0, -INFINITY};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double y = (double)x[i] * scale, ri = r[i], d = y - ri;
+        v[0] += y; v[1] += y * y; v[2] += ri; v[3] += ri * ri; v[4] += y * ri; v[5] += d * d; v[6] += fabs(d);
+        v[7] = fmax(v[7], ri);
+    }
+    stats_block_reduce<8>(v, true, part + (size_t)blockIdx.x * 8);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(STATS_THREADS) prior_stats_kernel(GradArgs<T> a, double scale, double gamma, double *__restrict__ part) {
+    double v[4] = {0, 0, 0, 0};
+    const double g2 = gamma * gamma;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (long long)gridDim.x * blockDim.x) {
+        int idx[3];
+        decode_axes<T>(i, a.nx, a.ny, idx[0], idx[1], idx[2]);
+        const double c = (double)a.in[i] * scale;
+        double ss = 0.0;
+        for (int k = 0; k < a.dim; ++k) {
+            const int ax = (k == 0) ? 0 : ((a.dim == 3 && k == 1) ? 1 : 2);
+            const double hi = (idx[ax] + 1 < a.extent[k]) ? (double)a.in[i + a.stride[k]] * scale : 0.0;
+            const double d = (double)a.w[k] * hi + (-(double)a.w[k]) * c;
+            ss = (k == 0) ? d * d : ss + d * d;
+        }
+        v[0] += sqrt(ss);
+        v[1] += ss;
+        v[2] += ss < g2 ? ss : 2.0 * gamma * sqrt(ss) - g2;     // loss_functions.huber (f_scale = 1)
+        v[3] += c * c;
+    }
+    stats_block_reduce<4>(v, false, part + (size_t)blockIdx.x * 4);
+}
+
+template <int K>
+__global__ void stats_final_kernel(const double *__restrict__ part, int nblocks, bool is_max_last, double *__restrict__ out) {
+    double v[K];
+    for (int k = 0; k < K; ++k) v[k] = (is_max_last && k == K - 1) ? -INFINITY : 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
+        for (int k = 0; k < K; ++k) {
+            const double x = part[(size_t)b * K + k];
+            v[k] = (is_max_last && k == K - 1) ? fmax(v[k], x) : v[k] + x;
+        }
+    stats_block_reduce<K>(v, is_max_last, out);
+}
+
+static int stats_finish(nsol_ctx *ctx, double *part, int nblocks, int k, double *out_host, cudaStream_t st) {
+    double *res = part + (size_t)STATS_MAX_BLOCKS * 8;
+    if (k == 8) stats_final_kernel<8><<<1, STATS_THREADS, 0, st>>>(part, nblocks, true, res);
+    else stats_final_kernel<4><<<1, STATS_THREADS, 0, st>>>(part, nblocks, false, res);
+    NSOL_LAUNCH_CHECK(ctx);
+    NSOL_CUDA(ctx, cudaMemcpyAsync(out_host, res, k * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NSOL_CUDA(ctx, cudaStreamSynchronize(st));
+    NSOL_CUDA(ctx, cudaFreeAsync(part, st));
+    return NSOL_OK;
+}
+
+extern "C" int nsol_similarity_stats(nsol_ctx *ctx, int dtype_x, int64_t n, const void *x_dev, double scale, const double *xref_dev,
+                                     double *out_host8, nsol_stream s) {
+    if (!ctx) return NSOL_EINVAL;
+    if (n < 1 || !x_dev || !xref_dev || !out_host8) return nsol_fail(ctx, NSOL_EINVAL, "nsol_similarity_stats: bad argument");
+    NSOL_CHECK(nsol_bind_device(ctx));
+    cudaStream_t st = (cudaStream_t)s;
+    long long want = (n + STATS_THREADS - 1) / STATS_THREADS;
+    const int nb = (int)(want < STATS_MAX_BLOCKS ? want : STATS_MAX_BLOCKS);
+    double *part = nullptr;
+    NSOL_CUDA(ctx, cudaMallocAsync((void **)&part, sizeof(double) * (STATS_MAX_BLOCKS + 1) * 8, st));
+    if (dtype_x == NSOL_F32) similarity_stats_kernel<float><<<nb, STATS_THREADS, 0, st>>>(n, (const float *)x_dev, scale, xref_dev, part);
+    else if (dtype_x == NSOL_F64) similarity_stats_kernel<double><<<nb, STATS_THREADS, 0, st>>>(n, (const double *)x_dev, scale, xref_dev, part);
+    else return nsol_fail(ctx, NSOL_EINVAL, "nsol_similarity_stats: bad dtype");
+    NSOL_LAUNCH_CHECK(ctx);
+    return stats_finish(ctx, part, nb, 8, out_host8, st);
+}
+
+extern "C" int nsol_prior_stats(nsol_ctx *ctx, const nsol_grid *g, const void *x_dev, double scale, double huber_gamma, double *out_host4,
+                                nsol_stream s) {
+    if (!ctx) return NSOL_EINVAL;
+    if (!x_dev || !out_host4 || !(huber_gamma > 0.0)) return nsol_fail(ctx, NSOL_EINVAL, "nsol_prior_stats: bad argument");
+    NSOL_CHECK(nsol_bind_device(ctx));
+    GridView gv;
+    NSOL_CHECK(nsol_grid_view(ctx, g, &gv));
+    if (gv.batch != 1) return nsol_fail(ctx, NSOL_EINVAL, "nsol_prior_stats: grid.batch must be 1");
+    cudaStream_t st = (cudaStream_t)s;
+    long long want = (gv.n + STATS_THREADS - 1) / STATS_THREADS;
+    const int nb = (int)(want < STATS_MAX_BLOCKS ? want : STATS_MAX_BLOCKS);
+    double *part = nullptr;
+    NSOL_CUDA(ctx, cudaMallocAsync((void **)&part, sizeof(double) * (STATS_MAX_BLOCKS + 1) * 8, st));
+    if (gv.dtype == NSOL_F32) {
+        GradArgs<float> a;
+        fill_grad_args<float>(gv, x_dev, nullptr, a);
+        prior_stats_kernel<float><<<nb, STATS_THREADS, 0, st>>>(a, scale, huber_gamma, part);
+    } else {
+        GradArgs<double> a;
+        fill_grad_args<double>(gv, x_dev, nullptr, a);
+        prior_stats_kernel<double><<<nb, STATS_THREADS, 0, st>>>(a, scale, huber_gamma, part);
+    }
+    NSOL_LAUNCH_CHECK(ctx);
+    return stats_finish(ctx, part, nb, 4, out_host4, st);
+}

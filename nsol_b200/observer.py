@@ -7,7 +7,12 @@ import numpy as np
 
 class Observer(object):
 
-    def __init__(self, name="Observer"):
+    def __init__(self, name="Observer", store_iterates=True):
+        """``store_iterates=False`` (additive option): a GPU solver evaluates the measures it can map to
+        device reductions (SimilarityMeasures SSD/MAE/MSE/RMSE/PSNR/NCC) per iteration on the device and
+        hands over only the final iterate -- no copy of every iterate to the host."""
+        self._store_iterates = store_iterates
+        self._device_results = None
         self._name = name
         self._x_list = []
         self._measures = []
@@ -26,6 +31,29 @@ class Observer(object):
 
     def clear_x_list(self):
         self._x_list = []
+        self._device_results = None
+
+    def get_store_iterates(self):
+        return self._store_iterates
+
+    def device_measure_requests(self, n):
+        """{name: MeasureRequest} if every measure can be evaluated on the device, else None."""
+        from nsol_b200 import _trace
+        from nsol_b200.similarity_measures import DEVICE_MEASURES, MeasureRequest
+        reqs = {}
+        for name, fn in zip(self._measures_names, self._measures):
+            try:
+                r = fn(_trace.Symbol(("arg",), (int(n),)))
+            except Exception:
+                return None
+            if not isinstance(r, MeasureRequest) or r.kind not in DEVICE_MEASURES:
+                return None
+            reqs[name] = r
+        return reqs
+
+    def set_device_results(self, results):
+        """{name: array of one value per iteration (0..n)} produced by a GPU solver."""
+        self._device_results = results
 
     def get_x_list(self):
         return self._x_list
@@ -47,6 +75,10 @@ class Observer(object):
 
     def compute_measures(self):
         """One value per stored iterate and measure (nsol/observer.py:111-119)."""
+        if self._device_results is not None:
+            for name in self._measures_names:
+                self._dic_measures[name] = np.array(self._device_results[name])
+            return
         n = len(self._x_list)
         for k, name in enumerate(self._measures_names):
             res = np.zeros(n)

@@ -197,8 +197,41 @@ class PrimalDualSolver(Solver):
             ctx.check(lib.nsol_pd_plan_get_x_host(plan, out.ctypes.data, None))
             return out
 
+        reqs = None
+        if self._observer is not None and not getattr(self._observer, "get_store_iterates", lambda: True)():
+            reqs = self._observer.device_measure_requests(n)
         if self._observer is None:
             ctx.check(lib.nsol_pd_plan_iterate(plan, iters, None))
+        elif reqs is not None:
+            # measures as device reductions on the resident iterate
+            from nsol_b200.similarity_measures import device_stats, from_stats
+            refs = {}
+            for name, r in reqs.items():
+                key = id(r.x_ref)
+                if key not in refs:
+                    xr = np.ascontiguousarray(np.asarray(r.x_ref, dtype=np.float64).reshape(-1))
+                    if xr.size != n:
+                        raise ValueError("measure '%s': reference has %d values, x has %d" % (name, xr.size, n))
+                    refs[key] = ctx.device_alloc(xr.nbytes).upload(xr)
+            results = {name: np.zeros(iters + 1) for name in reqs}
+            xptr = C.c_void_p()
+            dcode = int(desc.grid.dtype)
+            try:
+                for i in range(iters + 1):
+                    if i > 0:
+                        ctx.check(lib.nsol_pd_plan_iterate(plan, 1, None))
+                    ctx.check(lib.nsol_pd_plan_x_dev(plan, C.byref(xptr)))
+                    cache = {}
+                    for name, r in reqs.items():
+                        key = id(r.x_ref)
+                        if key not in cache:
+                            cache[key] = device_stats(ctx, dcode, n, xptr, float(self._x_scale), refs[key])
+                        results[name][i] = from_stats(r.kind, cache[key], n)
+            finally:
+                for buf in refs.values():
+                    buf.free()
+            self._observer.set_device_results(results)
+            self._observer.add_x(fetch())
         else:
             # nsol/primal_dual_solver.py:218-219, 260-261: the observer sees x0 and every iterate
             self._observer.add_x(fetch())

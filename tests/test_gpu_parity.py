@@ -564,3 +564,64 @@ def test_lsmr_multi_kernel_and_cooperative_paths(golden, path):
             assert rel_max(a, b) < F64_LSMR_TOL
     finally:
         ctx.set_tuning("lsmr_path", 0)
+
+
+# ------------------------------------------------------------------ measures on the device
+def test_similarity_and_prior_measures_on_device():
+    """SimilarityMeasures / PriorMeasures evaluated by device reductions equal the reference formulas
+    (nsol/similarity_measures.py:26-120, nsol/prior_measures.py:19-52)."""
+    from nsol_b200.similarity_measures import SimilarityMeasures as sim
+    from nsol_b200.prior_measures import PriorMeasures as prior
+    rng = np.random.RandomState(9)
+    x_ref = rng.rand(37 * 29) * 255
+    x = x_ref + rng.randn(x_ref.size) * 5
+    n = float(x.size)
+    ssd = np.sum(np.square(x - x_ref))
+    expect = {"SSD": ssd, "MAE": np.sum(np.abs(x - x_ref)) / n, "MSE": ssd / n, "RMSE": np.sqrt(ssd / n),
+              "PSNR": orc.psnr(x, x_ref), "NCC": orc.ncc(x, x_ref)}
+    for name, val in expect.items():
+        got = sim.similarity_measures[name](x, x_ref)
+        assert abs(got - val) <= 1e-10 * abs(val), (name, got, val)
+    assert abs(sim.sum_of_absolute_differences(x, x_ref) - np.sum(np.abs(x - x_ref))) < 1e-7
+    # identities of tests/similarity_measures_test.py:31-93
+    assert sim.sum_of_squared_differences(x, x) == 0 and np.isinf(sim.peak_signal_to_noise_ratio(x, x))
+    assert abs(sim.normalized_cross_correlation(3 * x + 7, x) - sim.normalized_cross_correlation(x, x)) < 1e-12
+    with pytest.raises(ValueError):
+        sim.mean_squared_error(x, x_ref[:-1])
+    with pytest.raises(NotImplementedError):
+        sim.structural_similarity(x, x_ref)
+    shape = (37, 29)
+    grad, _ = lo.LinearOperators2D(spacing=np.array([0.7, 1.3])).get_gradient_operators()
+    D = lambda v: grad(v.reshape(*shape)).flatten()
+    g = orc.grad(x.reshape(shape), [0.7, 1.3])
+    ss = g[:37] ** 2 + g[37:] ** 2
+    assert abs(prior.total_variation(x, D, 2) - np.sum(np.sqrt(ss))) < 1e-9 * np.sum(np.sqrt(ss))
+    assert abs(prior.first_order_tikhonov(x, D) - 0.5 * np.sum(ss)) < 1e-9 * np.sum(ss)
+    assert abs(prior.zeroth_order_tikhonov(x) - 0.5 * np.sum(x ** 2)) < 1e-9 * np.sum(x ** 2)
+    hub = np.where(ss < 0.05 ** 2, ss, 2 * 0.05 * np.sqrt(ss) - 0.05 ** 2) / (2 * 0.05)
+    assert abs(prior.huber(x, D, 2) - np.sum(hub)) < 1e-9 * np.sum(hub)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_observer_device_measures_match_host_measures(golden, dtype):
+    """Observer(store_iterates=False): measures per iteration as device reductions, no iterate copies;
+    same values as the reference flow (every iterate copied, measures on the host)."""
+    from nsol_b200.observer import Observer
+    from nsol_b200.similarity_measures import SimilarityMeasures as sim
+    obs = golden("pd", "in/bw2d")
+    x_ref = obs.reshape(-1) * 0.97 + 1.0
+    names = ["PSNR", "RMSE", "NCC", "SSD"]
+    out = {}
+    for tag, store in (("host", True), ("device", False)):
+        s = make_pd(obs, reg="TV", data="L2", alpha=0.05, L2=8, iterations=7, dtype=dtype)
+        o = Observer(store_iterates=store)
+        o.set_measures({m: (lambda x, m=m: sim.similarity_measures[m](x, x_ref)) for m in names})
+        s.set_observer(o)
+        s.run()
+        o.compute_measures()
+        out[tag] = (o.get_measures(), o.get_x_list())
+    assert len(out["host"][1]) == 8 and len(out["device"][1]) == 1
+    assert np.array_equal(out["device"][1][-1], out["host"][1][-1])
+    for m in names:
+        a, b = out["device"][0][m], out["host"][0][m]
+        assert a.shape == (8,) and np.allclose(a, b, rtol=1e-9, atol=0), (m, a, b)
