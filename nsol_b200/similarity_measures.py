@@ -41,7 +41,7 @@ def from_stats(kind, st, n):
         return np.sqrt(ssd / n)
     if kind == "PSNR":
         with np.errstate(divide="ignore"):
-            return 10 * np.log10(rmax ** 2 / (ssd / n))
+            return float(10 * np.log10(np.float64(rmax ** 2) / np.float64(ssd / n)))
     if kind == "NCC":
         cov = syr - sy * sr / n
         var_y = (syy - sy * sy / n) / (n - 1.0)
