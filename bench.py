@@ -126,6 +126,27 @@ def measured_traffic(dtype_key, nvox):
         return None
 
 
+def pcie_bandwidth(ctx, stream, nbytes=1 << 28):
+    """Measured pinned host<->device copy bandwidth of this box (explains the e2e number)."""
+    import torch
+    host = ctx.pinned_empty((nbytes,), np.uint8)
+    dev = ctx.device_alloc(nbytes)
+    out = {}
+    for name, fn in (("h2d_gbs", lambda: ctx.lib.nsol_memcpy_h2d(ctx.handle, dev.ptr, host.ctypes.data, nbytes, stream)),
+                     ("d2h_gbs", lambda: ctx.lib.nsol_memcpy_d2h(ctx.handle, host.ctypes.data, dev.ptr, nbytes, stream))):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = 3 * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    dev.free()
+    return out
+
+
 WORKLOAD = "C4: 3D TV-L2 primal-dual denoising %dx%dx%d, alpha=%g, L2=%g, ALG2, %d iterations per step"
 
 
@@ -274,6 +295,9 @@ def main():
     ap.add_argument("--overlap", action="store_true",
                     help="multi-GPU: split every iteration (boundary chunks, exchange || interior chunks); measured no faster "
                          "than the plain exchange on 8 B200 (profiles/r1_scaling.md), so off by default")
+    ap.add_argument("--halo", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="multi-GPU halo exchange: p2p = inside the iteration kernels over peer memory (NVLink), "
+                         "nccl = grouped send/recv before every launch; auto = p2p if CUDA IPC works")
     ap.add_argument("--secondary-dtype", action="store_true", help="also time the other dtype (reported under 'other_dtype')")
     ap.add_argument("--other-configs", action="store_true", help="also time BASELINE configs 1, 2, 3, 5 (reported under 'other_configs')")
     args = ap.parse_args()
@@ -326,6 +350,8 @@ def main():
     del vol
     out_host = ctx.pinned_empty((nvox_loc,), np.float64)
 
+    halo_mode = ["single"]
+
     def measure(dtype_name, want_e2e):
         dcode = _lib.dtype_code(dtype_name)
         esz = 4 if dcode == _lib.F32 else 8
@@ -339,7 +365,8 @@ def main():
         alpha_arr = np.array([ALPHA])
         desc.alpha = alpha_arr.ctypes.data_as(_lib.c_double_p)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        slab = SlabPrimalDual(ctx, desc, n * n, np_dt, rank, world, device)
+        slab = SlabPrimalDual(ctx, desc, n * n, np_dt, rank, world, device, halo=args.halo)
+        halo_mode[0] = slab.mode
         lib, plan = ctx.lib, slab.plan
         # observation resident in HBM in the plan's dtype
         stage = ctx.device_alloc(nvox_loc * 8)
@@ -377,6 +404,7 @@ def main():
             pairs.append((e1, e2))
         ev[3].record()
         barrier()
+        slab.check(stream)      # a timed-out in-kernel halo wait invalidates the run
         total_ms = max_over_ranks(ev[0].elapsed_time(ev[3]))
         kernel_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in pairs))
         launches = ctx.launch_count() - launches0
@@ -411,13 +439,19 @@ def main():
                     solver.run()
                     return solver.get_x()
             else:
-                slab2 = SlabPrimalDual(ctx, desc, n * n, np_dt, rank, world, device)
+                slab2 = SlabPrimalDual(ctx, desc, n * n, np_dt, rank, world, device, halo=args.halo)
                 def e2e_step():
                     slab2.reset_host(obs_host.ctypes.data, None, stream)
                     slab2.iterate(args.iters, stream, overlap=args.overlap)
                     ctx.check(lib.nsol_pd_plan_get_x_host(slab2.plan, out_host.ctypes.data, stream))
                     return out_host
-            e2e_step()
+            # warm-up: two results alive at once, so the page-locked result pool holds a spare buffer
+            # and no timed step pays for a cudaHostAlloc
+            x = e2e_step()
+            x_spare = e2e_step()
+            del x_spare
+            barrier()
+            link = pcie_bandwidth(ctx, stream) if rank == 0 else None
             barrier()
             t0 = time.perf_counter()
             n_e2e = max(1, min(args.steps, 3))
@@ -429,7 +463,8 @@ def main():
                           "h2d_bytes_per_step": 2 * nvox_loc * 8 if world == 1 else nvox_loc * 8,
                           "d2h_bytes_per_step": nvox_loc * 8, "ms_per_step": dt / n_e2e * 1e3, "steps": n_e2e,
                           "api": "PrimalDualSolver.run()+get_x()" if world == 1 else
-                                 "SlabPrimalDual: nsol_pd_plan_reset_host + iterate + nsol_pd_plan_get_x_host"}
+                                 "SlabPrimalDual: nsol_pd_plan_reset_host + iterate + nsol_pd_plan_get_x_host",
+                          "host_link": link}
             res["checksum"] = float(np.sum(x[:: max(1, x.size // 4096)]))
             if world > 1:
                 slab2.close()
@@ -455,7 +490,10 @@ def main():
             "dtype": "f64" if args.dtype == "float64" else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD % (nz_global, n, n, ALPHA, L2, args.iters),
                        "input": "64^3 Shepp-Logan fixture repeated to size + Gaussian noise 0.05 (seeded)",
-                       "parallelism": "z-slab x%d, 3-plane halo exchange per iteration%s" % (world, " overlapped with the interior chunks" if args.overlap else "") if world > 1 else "single GPU",
+                       "parallelism": ("z-slab x%d, 3-plane halo exchange per iteration, %s" % (
+                           world, "inside the iteration kernels over peer memory (NVLink), no host work per iteration"
+                           if halo_mode[0] == "p2p" else
+                           "NCCL send/recv" + (" overlapped with the interior chunks" if args.overlap else ""))) if world > 1 else "single GPU",
                        "l2_policy": "inputs larger than L2 (%.1f GiB of solver state per GPU)" % (main_res["plan_bytes"] / 2.0 ** 30)},
             "gpu_launches": main_res["launches"],
             "clocks": main_res["clocks"],

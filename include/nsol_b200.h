@@ -222,6 +222,28 @@ int nsol_pd_plan_iterate_part(nsol_pd_plan *plan, int part, nsol_stream s);
 int nsol_pd_plan_boundary_planes_next(nsol_pd_plan *plan, const void **xbar_first, const void **xbar_last,
                                       const void **pz_last);
 int nsol_pd_plan_chunks(nsol_pd_plan *plan);
+/* In-kernel halo exchange over peer memory (NVLink / NVSwitch) -- the fused form of the z-slab
+ * exchange: no NCCL call and no host work per iteration.  Every rank owns a "link block" (flags +
+ * double-buffered receive slots for the three halo planes).  The boundary CTAs of an iteration
+ * store the first xbar plane / the last xbar and p_z planes of the state they produce straight
+ * into the neighbours' blocks and raise a flag there (release, system scope); the next iteration
+ * of the neighbour spins on that flag (acquire) before it reads the halo.  With a link connected,
+ * nsol_pd_plan_iterate(plan, n) just queues n launches; all ranks must call reset / iterate in
+ * lockstep (same sequence, same n).  The first iterate after a reset also publishes the boundary
+ * planes of the start state (n = 0 does only that -- needed when one stream drives several linked
+ * plans).  nsol_pd_plan_set_halo is not used in this mode.
+ *   link_create      allocates this plan's block and returns its device pointer / size
+ *   link_ipc_handle  64-byte cudaIpcMemHandle_t of the block, to be sent to the neighbours
+ *   link_open        maps the neighbours' blocks from their IPC handles (NULL = no neighbour:
+ *                    global bottom / top) and switches the plan to link mode
+ *   link_connect     same with raw device pointers valid in this process (one process driving
+ *                    several plans / GPUs; used by the single-GPU emulation tests)
+ *   link_status      synchronises and returns NSOL_ENCCL if a flag wait timed out */
+int nsol_pd_plan_link_create(nsol_pd_plan *plan, void **block_dev, size_t *block_bytes);
+int nsol_pd_plan_link_ipc_handle(nsol_pd_plan *plan, void *handle64);
+int nsol_pd_plan_link_open(nsol_pd_plan *plan, const void *handle_below64, const void *handle_above64);
+int nsol_pd_plan_link_connect(nsol_pd_plan *plan, void *block_below, void *block_above);
+int nsol_pd_plan_link_status(nsol_pd_plan *plan, nsol_stream s);
 
 /* ---- stacked least squares: LSMR on [A; sqrt(alpha) B] ---------------------
  * Replaces TikhonovLinearSolver._run, lsmr/linear branch

@@ -93,6 +93,11 @@ SIGNATURES = {
     "nsol_pd_plan_iterate_part": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "nsol_pd_plan_boundary_planes_next": (C.c_int, [C.c_void_p, c_void_pp, c_void_pp, c_void_pp]),
     "nsol_pd_plan_chunks": (C.c_int, [C.c_void_p]),
+    "nsol_pd_plan_link_create": (C.c_int, [C.c_void_p, c_void_pp, C.POINTER(C.c_size_t)]),
+    "nsol_pd_plan_link_ipc_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nsol_pd_plan_link_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsol_pd_plan_link_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsol_pd_plan_link_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nsol_lsmr_plan_create": (C.c_int, [C.c_void_p, C.POINTER(LsqDesc), c_void_pp]),
     "nsol_lsmr_plan_destroy": (None, [C.c_void_p]),
     "nsol_lsmr_plan_bytes": (C.c_size_t, [C.c_void_p]),
@@ -151,6 +156,8 @@ class Context(object):
             _raise(NSOL_ECUDA if rc != NSOL_EINVAL else rc,
                    (self.lib.nsol_last_error(None) or b"nsol_create failed").decode())
         self.handle = h
+        self._pool = {}          # nbytes -> [pinned pointers ready for reuse]
+        self._pool_bytes = 0
 
     def check(self, rc):
         if rc != NSOL_OK:
@@ -183,12 +190,56 @@ class Context(object):
         arr = _PinnedArray(arr, owner)
         return arr
 
+    # Results of large solves come back into page-locked buffers: a pageable np.empty() of 1 GiB costs
+    # ~1 s of page faults + staged copies per get_x(), a pinned one ~20 ms.  cudaHostAlloc itself is slow,
+    # so buffers whose array has been garbage-collected are kept for the next result of the same size.
+    POOL_MIN_BYTES = 1 << 20
+    POOL_MAX_BYTES = 8 << 30
+
+    def result_empty(self, shape, dtype=np.float64):
+        """Fresh host array for a solver result: page-locked (pooled) when large, plain numpy otherwise."""
+        shape = tuple(int(s) for s in np.atleast_1d(shape))
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        if nbytes < self.POOL_MIN_BYTES:
+            return np.empty(shape, dtype=dtype)
+        with _lock:
+            free = self._pool.get(nbytes)
+            ptr = free.pop() if free else None
+            if ptr is not None:
+                self._pool_bytes -= nbytes
+        if ptr is None:
+            p = C.c_void_p()
+            self.check(self.lib.nsol_host_alloc(self.handle, nbytes, C.byref(p)))
+            ptr = p.value
+        owner = _PooledOwner(self, ptr, nbytes)
+        buf = (C.c_char * nbytes).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        return _PinnedArray(arr, owner)
+
+    def _pool_return(self, ptr, nbytes):
+        with _lock:
+            if self.handle and self._pool_bytes + nbytes <= self.POOL_MAX_BYTES:
+                self._pool.setdefault(nbytes, []).append(ptr)
+                self._pool_bytes += nbytes
+                return
+        self.lib.nsol_host_free(self.handle, C.c_void_p(ptr))
+
+    def pool_trim(self):
+        """Release every cached page-locked buffer."""
+        with _lock:
+            ptrs = [p for lst in self._pool.values() for p in lst]
+            self._pool.clear()
+            self._pool_bytes = 0
+        for p in ptrs:
+            self.lib.nsol_host_free(self.handle, C.c_void_p(p))
+
     def sync(self, stream=None):
         self.check(self.lib.nsol_stream_sync(self.handle, stream))
 
     def __del__(self):
         try:
             if getattr(self, "handle", None):
+                self.pool_trim()
                 self.lib.nsol_destroy(self.handle)
                 self.handle = None
         except Exception:
@@ -202,6 +253,19 @@ class _PinnedOwner(object):
     def __del__(self):
         try:
             self.ctx.lib.nsol_host_free(self.ctx.handle, self.ptr)
+        except Exception:
+            pass
+
+
+class _PooledOwner(object):
+    """Hands its page-locked buffer back to the context's pool when the last array view dies."""
+
+    def __init__(self, ctx, ptr, nbytes):
+        self.ctx, self.ptr, self.nbytes = ctx, ptr, nbytes
+
+    def __del__(self):
+        try:
+            self.ctx._pool_return(self.ptr, self.nbytes)
         except Exception:
             pass
 
@@ -230,7 +294,7 @@ class DeviceBuffer(object):
         return self
 
     def download(self, shape, dtype, stream=None):
-        out = np.empty(shape, dtype=dtype)
+        out = self.ctx.result_empty(shape, dtype)
         assert out.nbytes <= self.nbytes
         self.ctx.check(self.ctx.lib.nsol_memcpy_d2h(self.ctx.handle, out.ctypes.data, self.ptr, out.nbytes, stream))
         self.ctx.sync(stream)

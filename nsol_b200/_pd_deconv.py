@@ -31,7 +31,7 @@ def run_pd_deconvolution(solver, cfg):
     desc = solver._make_desc(cfg_pd, [float(solver._alpha)])
     x0s = np.ascontiguousarray(solver._x0, dtype=np.float64)
     iters = int(solver._iterations)
-    x_out = np.empty(n, dtype=np.float64)
+    x_out = _lib.context().result_empty(n, np.float64)
     its = np.empty((iters + 1, n), dtype=np.float64) if solver._observer is not None else None
     plan = LsmrPlan(info, solver._dtype)
     try:

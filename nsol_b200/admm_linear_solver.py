@@ -66,7 +66,7 @@ class ADMMLinearSolver(LinearSolver):
             ctx = plan.ctx
             b = np.ascontiguousarray(self._b, dtype=np.float64)
             x0 = np.ascontiguousarray(self._x0, dtype=np.float64)   # v = B(x0) (:171); lsmr itself is cold-started
-            x_out = np.empty(n, dtype=np.float64)
+            x_out = ctx.result_empty(n, np.float64)
             its = np.empty((iters + 1, n), dtype=np.float64) if self._observer is not None else None
             ctx.check(ctx.lib.nsol_admm_run_host(
                 plan.handle, float(self._alpha), float(self._rho), iters, int(self._iter_max), 1.0,

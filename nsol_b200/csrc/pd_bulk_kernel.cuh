@@ -20,6 +20,20 @@
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of the (converged) warp; the compiler then issues the uniform-datapath TMA instructions
+// under a plain predicate instead of an elect loop per instruction
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -58,7 +72,7 @@ struct PdBulkLayout {
     }
 };
 
-template <typename T, int VEC, int REG, int DATA>
+template <typename T, int VEC, int REG, int DATA, bool LINK, bool UNIT>
 __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kernel(const PdArgs<T> a) {
     using V = Vec<T, VEC>;
     using L = PdBulkLayout<T, VEC>;
@@ -68,11 +82,12 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kern
 
     const int lane = threadIdx.x;
     const int TY = (int)blockDim.y;
-    const int ty = (int)threadIdx.y;
+    const int ty = __shfl_sync(0xffffffffu, (int)threadIdx.y, 0);   // broadcast: the compiler then knows it is warp-uniform
     const int x0t = (int)blockIdx.x * W;                        // first voxel of the tile row
     const int x0 = x0t + lane * VEC;
     const int y = (int)blockIdx.y * TY + ty;
-    const int chunk = a.chunk_first + (int)(blockIdx.z % (unsigned)a.nsel) * a.chunk_stride;
+    int chunk = a.chunk_first + (int)(blockIdx.z % (unsigned)a.nsel) * a.chunk_stride;
+    if (LINK && a.front_chunks) chunk = chunk == 0 ? 0 : (chunk == 1 ? a.nchunks - 1 : chunk - 1);
     const int bz = (int)(blockIdx.z / (unsigned)a.nsel);
     const int z0 = chunk * a.zc;
     const int z1 = min(a.nz, z0 + a.zc);
@@ -122,7 +137,8 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kern
         T *sh = s_halo + slot * L::HALO_STAGE;
         const unsigned row_b = (unsigned)(w_in * sizeof(T));
         const bool xbn_plane = zq + 1 < a.nz;                   // xbar plane zq+1 exists locally
-        const bool xbn_halo = !xbn_plane && !top_zero;           // ... or comes from the rank above
+        const bool xbn_halo = !LINK && !xbn_plane && !top_zero;  // ... or comes from the rank above (NCCL-filled
+                                                                // buffer; in link mode it is read directly, below)
         const bool nx_plane = zq + 1 < z1;                      // CTA processes plane zq+1: needs its halos
         unsigned total = 5 * row_b + (unsigned)(ext_l * sizeof(T));          // px(+left ext), py, pz, x, b
         if (xbn_plane) total += row_b + (unsigned)((ext_l + ext_r) * sizeof(T));
@@ -144,7 +160,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kern
     };
 
     // ---- prologue ------------------------------------------------------------------------
-    if (row_in && lane == 0) {
+    if (row_in && elect_one()) {
         for (int k = 0; k < S - 1; ++k)
             if (z0 + k < z1) issue(z0 + k, k, offt + (long long)k * sz, bofft + (long long)k * sz);
     }
@@ -154,11 +170,12 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kern
     T xr_c = need_r ? a.xbar_in[off0 + VEC] : T(0);
     T xl_c = need_l ? a.xbar_in[off0 - 1] : T(0);
     V pz_prev = vec_zero<T, VEC>();
+    if (LINK) pd_link_begin(a, z0, z1);
     if (active && (z0 > 0 || a.halo_pz_below)) {
-        V xb_m = z0 > 0 ? vec_load<T, VEC>(a.xbar_in + off0 - sz) : vec_load<T, VEC>(a.halo_xbar_below + hrow_t + lcol);
-        V pz_m = z0 > 0 ? vec_load<T, VEC>(a.pz_in + off0 - sz) : vec_load<T, VEC>(a.halo_pz_below + hrow_t + lcol);
+        V xb_m = z0 > 0 ? vec_load<T, VEC>(a.xbar_in + off0 - sz) : vec_load_cg<T, VEC>(a.halo_xbar_below + hrow_t + lcol);
+        V pz_m = z0 > 0 ? vec_load<T, VEC>(a.pz_in + off0 - sz) : vec_load_cg<T, VEC>(a.halo_pz_below + hrow_t + lcol);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) pz_prev.v[v] = dual_update<T, REG>(pz_m.v[v], xb_c.v[v], xb_m.v[v], wz, sigma, div_g);
+        for (int v = 0; v < VEC; ++v) pz_prev.v[v] = dual_update<T, REG, UNIT>(pz_m.v[v], xb_c.v[v], xb_m.v[v], wz, sigma, div_g);
     }
     {
         T *buf = s_xb + (z0 & 1) * (TY + 2) * W;
@@ -180,7 +197,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kern
     for (int z = z0; z < z1; ++z) {
         const bool more = (z + 1 < z1);
         // refill the slot consumed one plane ago (all its readers passed the last __syncthreads)
-        if (row_in && lane == 0 && (z + S - 1 < z1)) {
+        if (row_in && (z + S - 1 < z1) && elect_one()) {
             int ps = slot + S - 1;
             if (ps >= S) ps -= S;
             issue(z + S - 1, ps, offt + (long long)(S - 1) * sz, bofft + (long long)(S - 1) * sz);
@@ -192,7 +209,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kern
         if (row_in) {
             mbar_wait(&bars[ty * S + slot], parity);
             if (active) {
-                if (z + 1 < a.nz || !top_zero) xbn = vec_load<T, VEC>(st + VEC + lcol);
+                if (z + 1 < a.nz || (!LINK && !top_zero)) xbn = vec_load<T, VEC>(st + VEC + lcol);
                 pxv = vec_load<T, VEC>(st + L::WX + VEC + lcol);
                 pyv = vec_load<T, VEC>(st + 2 * L::WX + lcol);
                 pzv = vec_load<T, VEC>(st + 2 * L::WX + W + lcol);
@@ -207,6 +224,11 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kern
                 }
                 if (need_dn) pydn = vec_load<T, VEC>(sh + 2 * W + lcol);
             }
+        }
+
+        if (LINK && z + 1 == a.nz && !top_zero) {
+            // xbar plane of the rank above: stored by that rank's kernel into this rank's link block
+            if (active) xbn = vec_load_cg<T, VEC>(a.halo_xbar_above + hrow_t + lcol);
         }
 
         // neighbours of the current plane
@@ -224,9 +246,9 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kern
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             T hi = (v + 1 < VEC) ? xb_c.v[(v + 1) % VEC] : x_right;
-            pnx.v[v] = dual_update<T, REG>(pxv.v[v], hi, xb_c.v[v], wx, sigma, div_g);
-            pny.v[v] = dual_update<T, REG>(pyv.v[v], xup.v[v], xb_c.v[v], wy, sigma, div_g);
-            pnz.v[v] = dual_update<T, REG>(pzv.v[v], xbn.v[v], xb_c.v[v], wz, sigma, div_g);
+            pnx.v[v] = dual_update<T, REG, UNIT>(pxv.v[v], hi, xb_c.v[v], wx, sigma, div_g);
+            pny.v[v] = dual_update<T, REG, UNIT>(pyv.v[v], xup.v[v], xb_c.v[v], wy, sigma, div_g);
+            pnz.v[v] = dual_update<T, REG, UNIT>(pzv.v[v], xbn.v[v], xb_c.v[v], wz, sigma, div_g);
         }
         const long long off = offt + lcol;
         if (active) {
@@ -235,7 +257,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kern
             vec_store<T, VEC>(a.pz_out + off, pnz);
         }
         T pnx_left = shfl_up_t(pnx.v[VEC - 1], 1);
-        if (lane == 0) pnx_left = need_l ? dual_update<T, REG>(pxl, xb_c.v[0], xl_c, wx, sigma, div_g) : T(0);
+        if (lane == 0) pnx_left = need_l ? dual_update<T, REG, UNIT>(pxl, xb_c.v[0], xl_c, wx, sigma, div_g) : T(0);
 
         // publish p'_y of this row (and of the halo row below the tile) and the next xbar plane
         vec_store<T, VEC>(pbuf + (ty + 1) * W + lcol, pny);
@@ -243,7 +265,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kern
             V h = vec_zero<T, VEC>();
             if (need_dn && active) {
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) h.v[v] = dual_update<T, REG>(pydn.v[v], xb_c.v[v], xdn.v[v], wy, sigma, div_g);
+                for (int v = 0; v < VEC; ++v) h.v[v] = dual_update<T, REG, UNIT>(pydn.v[v], xb_c.v[v], xdn.v[v], wy, sigma, div_g);
             }
             vec_store<T, VEC>(pbuf + lcol, h);
         }
@@ -260,9 +282,9 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kern
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             T lo = (v == 0) ? pnx_left : pnx.v[(v + VEC - 1) % VEC];
-            T div = madd(wx, lo, (-wx) * pnx.v[v]);
-            div = div + madd(wy, pny_dn.v[v], (-wy) * pny.v[v]);
-            div = div + madd(wz, pz_prev.v[v], (-wz) * pnz.v[v]);
+            T div = wdiff<T, UNIT>(wx, lo, pnx.v[v]);
+            div = div + wdiff<T, UNIT>(wy, pny_dn.v[v], pny.v[v]);
+            div = div + wdiff<T, UNIT>(wz, pz_prev.v[v], pnz.v[v]);
             primal_update<T, DATA>(xv.v[v], bv.v[v], div, tau, tl, theta, div_f, xnew.v[v], xbnew.v[v]);
         }
         if (active) {
@@ -281,4 +303,5 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kern
             parity ^= 1u;
         }
     }
+    if (LINK) pd_link_finish<T, VEC>(a, z0, z1, hrow_t + lcol, active);
 }

@@ -35,6 +35,16 @@ struct PdArgs {
     T *px_out, *py_out, *pz_out;
     const double *sched;              // [it][batch][8]
     const T *halo_xbar_above, *halo_xbar_below, *halo_pz_below;  // z-slab neighbours (or NULL)
+    // in-kernel halo exchange over peer memory ("link", see nsol_pd_plan_link_*): all NULL when the
+    // halos are refreshed by the caller (NCCL send/recv) or there is no neighbour on that side
+    const unsigned *flag_below, *flag_above;   // local: generations the lower / upper neighbour has published
+    unsigned *peer_flag_below, *peer_flag_above;   // the corresponding flags in the neighbours' memory
+    unsigned *count_below, *count_above;       // local arrival counters of the boundary CTAs
+    T *push_below_xbar;                        // lower neighbour's xbar_above halo plane (peer memory)
+    T *push_above_xbar, *push_above_pz;        // upper neighbour's xbar_below / pz_below halo planes
+    int *link_error;                           // set when a wait timed out
+    unsigned want, publish;                    // flag value this iteration needs / stores when its boundary is done
+    int front_chunks;                          // 1: schedule the two boundary chunks first (link mode)
     long long n;                      // voxels per problem
     long long b_stride;               // 0 (shared observation) or n
     int nx, ny, nz, zc, nchunks;
@@ -43,6 +53,72 @@ struct PdArgs {
     T wx, wy, wz;
     int it, batch;
 };
+
+// ---- in-kernel z-slab halo exchange (peer memory over NVLink) --------------------------------
+// Protocol (one flag per direction, living in the CONSUMER's memory):  the boundary CTAs of the
+// iteration that produces state g store their boundary planes into the neighbour's halo buffer
+// [g & 1], fence (system scope) and count themselves; the last one stores flag = g + 1 with
+// release semantics.  The iteration that consumes state g spins on flag >= g + 1 (acquire) before it
+// reads the halo.  Writing state g into buffer [g & 1] is safe once the neighbour has published
+// state g - 1 (its readers of state g - 2 are then finished) -- which every writer CTA has
+// observed, because it waits for exactly that flag value before it reads its own halo.
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#ifndef NSOL_LINK_INLINE
+#define NSOL_LINK_INLINE __noinline__
+#endif
+#ifndef NSOL_LINK_TIMEOUT_NS
+#define NSOL_LINK_TIMEOUT_NS 5000000000ull
+#endif
+// every calling thread polls the flag itself (same address: one broadcast load per warp)
+__device__ NSOL_LINK_INLINE void pd_link_wait(const unsigned *flag, unsigned want, int *error) {
+    if ((int)(ld_acquire_sys(flag) - want) >= 0) return;
+    if (*(volatile int *)error) return;           // a neighbour already failed: do not wait again
+    const unsigned long long t0 = global_timer_ns();
+    while ((int)(ld_acquire_sys(flag) - want) < 0) {
+        __nanosleep(64);
+        if (global_timer_ns() - t0 > NSOL_LINK_TIMEOUT_NS) {
+            *(volatile int *)error = 1;
+            return;
+        }
+    }
+}
+// called by one thread of a boundary CTA after the CTA's peer stores are fenced
+__device__ NSOL_LINK_INLINE void pd_link_signal(unsigned *count, unsigned *peer_flag, unsigned ctas, unsigned publish) {
+    const unsigned done = atomicAdd(count, 1u);
+    if (done + 1u == ctas) {
+        atomicExch(count, 0u);
+        __threadfence_system();
+        st_release_sys(peer_flag, publish);
+    }
+}
+// halo planes are written by another GPU while this kernel may already run: bypass L1
+template <typename T, int VEC>
+__device__ __forceinline__ Vec<T, VEC> vec_load_cg(const T *p) {
+    Vec<T, VEC> r;
+    if constexpr (sizeof(T) * VEC == 16) {
+        const float4 q = __ldcg(reinterpret_cast<const float4 *>(p));
+        memcpy(&r, &q, 16);
+    } else if constexpr (sizeof(T) * VEC == 8) {
+        const float2 q = __ldcg(reinterpret_cast<const float2 *>(p));
+        memcpy(&r, &q, 8);
+    } else {
+        const float q = __ldcg(reinterpret_cast<const float *>(p));
+        memcpy(&r, &q, 4);
+    }
+    return r;
+}
 
 // a*b + c with the reference's two roundings in float64 (no contraction: the float64 path is
 // bit-identical to numpy); a fused multiply-add in float32 (tolerance 1e-4)
@@ -76,13 +152,29 @@ struct ConstDiv<float> {
 
 // projection onto [-1, 1]: q / max(1, |q|) is q itself for |q| <= 1 and q/|q| = +-1 exactly
 // otherwise, so the reference's division (proximal_operators.py:140,159) is a clamp, bit for bit
-__device__ __forceinline__ double clamp_unit(double q) { return fmin(fmax(q, -1.0), 1.0); }
+// float64: decided on the exponent word with integer instructions (|q| >= 1  <=>  the high word without
+// its sign is >= 0x3ff00000): 5 integer instructions instead of the ~12 of fmin(fmax()) with its NaN
+// handling.  Same bits as the division for every finite q, including +-1 and -0.
+__device__ __forceinline__ double clamp_unit(double q) {
+    const int hi = __double2hiint(q);
+    const bool sat = (unsigned)(hi & 0x7fffffff) >= 0x3ff00000u;
+    const int rhi = sat ? ((hi & (int)0x80000000) | 0x3ff00000) : hi;
+    const int rlo = sat ? 0 : __double2loint(q);
+    return __hiloint2double(rhi, rlo);
+}
 __device__ __forceinline__ float clamp_unit(float q) { return fminf(fmaxf(q, -1.0f), 1.0f); }
 
-template <typename T, int REG>
+// UNIT: spacing 1 (w == 1, every configuration of BASELINE.json): 1*a and (-1)*a are exact, so
+// fl(fl(w*hi) + fl((-w)*lo)) == fl(hi - lo) bit for bit and the two multiplications are dropped
+template <typename T, bool UNIT>
+__device__ __forceinline__ T wdiff(T w, T hi, T lo) {
+    return UNIT ? hi - lo : madd(w, hi, (-w) * lo);
+}
+
+template <typename T, int REG, bool UNIT = false>
 __device__ __forceinline__ T dual_update(T p, T hi, T lo, T w, T sigma, const ConstDiv<T> &div_g) {
     // grad: fl(fl(w*x[i+1]) + fl((-w)*x[i]))   (scipy.ndimage.convolve order)
-    T g = madd(w, hi, (-w) * lo);
+    T g = wdiff<T, UNIT>(w, hi, lo);
     T q = madd(sigma, g, p);                                 // primal_dual_solver.py:242-243
     if (REG != NSOL_REG_TV) q = div_g(q);                    // proximal_operators.py:158 / TK1
     if (REG != NSOL_REG_TK1) q = clamp_unit(q);              // proximal_operators.py:140,159
@@ -103,6 +195,42 @@ __device__ __forceinline__ void primal_update(T xv, T bv, T div, T tau, T tl, T 
     xbn = madd(theta, xn - xv, xn);                          // primal_dual_solver.py:253
 }
 
+// Link mode, start of a CTA: the bottom chunk reads the lower neighbour's planes, the top chunk
+// the upper neighbour's plane; wait until they have been published.  (The boundary chunks are
+// scheduled first and the flags were raised early in the neighbours' previous iteration, so this
+// normally falls straight through.)  Every thread polls for itself.
+template <typename T>
+__device__ __forceinline__ void pd_link_begin(const PdArgs<T> &a, int z0, int z1) {
+    if (z0 == 0 && a.flag_below) pd_link_wait(a.flag_below, a.want, a.link_error);
+    if (z1 == a.nz && a.flag_above) pd_link_wait(a.flag_above, a.want, a.link_error);
+}
+
+// Link mode, end of a CTA: boundary CTAs copy the boundary planes of the NEW state (their own
+// stores of this launch) into the neighbours' receive slots, fence (system scope) and count
+// themselves; the last CTA of a side raises the neighbour's flag.  hoff = this thread's element
+// offset inside a plane.  Block-uniform control flow.
+template <typename T, int VEC>
+__device__ __forceinline__ void pd_link_finish(const PdArgs<T> &a, int z0, int z1, long long hoff, bool active) {
+    const bool bot = a.push_below_xbar && z0 == 0;
+    const bool top = a.push_above_xbar && z1 == a.nz;
+    if (!bot && !top) return;
+    if (active) {
+        if (bot) vec_store<T, VEC>(a.push_below_xbar + hoff, vec_load<T, VEC>(a.xbar_out + hoff));
+        if (top) {
+            const long long o = (long long)(a.nz - 1) * a.nx * a.ny + hoff;
+            vec_store<T, VEC>(a.push_above_xbar + hoff, vec_load<T, VEC>(a.xbar_out + o));
+            vec_store<T, VEC>(a.push_above_pz + hoff, vec_load<T, VEC>(a.pz_out + o));
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const unsigned ctas = gridDim.x * gridDim.y;
+        if (bot) pd_link_signal(a.count_below, a.peer_flag_below, ctas, a.publish);
+        if (top) pd_link_signal(a.count_above, a.peer_flag_above, ctas, a.publish);
+    }
+}
+
 // everything one thread loads for plane z: p, x, b at z; xbar at z+1 (own voxels and, if the CTA
 // also processes plane z+1, its x/y halos); the low-side halos of p needed to recompute p'
 template <typename T, int VEC>
@@ -119,7 +247,7 @@ struct PdStep {
 #ifndef NSOL_PD_MINB_F32
 #define NSOL_PD_MINB_F32 2
 #endif
-template <typename T, int VEC, bool HAS_Y, int REG, int DATA>
+template <typename T, int VEC, bool HAS_Y, int REG, int DATA, bool LINK>
 __global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : NSOL_PD_MINB_F64) pd_iter_kernel(const PdArgs<T> a) {
     using V = Vec<T, VEC>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -131,7 +259,8 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : NSOL_
     const int x0 = (int)blockIdx.x * tile_w + (int)threadIdx.x * VEC;
     const int y0 = HAS_Y ? (int)blockIdx.y * TY : 0;
     const int y = y0 + ty;
-    const int chunk = a.chunk_first + (int)(blockIdx.z % (unsigned)a.nsel) * a.chunk_stride;
+    int chunk = a.chunk_first + (int)(blockIdx.z % (unsigned)a.nsel) * a.chunk_stride;
+    if (LINK && a.front_chunks) chunk = chunk == 0 ? 0 : (chunk == 1 ? a.nchunks - 1 : chunk - 1);
     const int bz = (int)(blockIdx.z / (unsigned)a.nsel);
     const int z0 = chunk * a.zc;
     const int z1 = min(a.nz, z0 + a.zc);
@@ -167,10 +296,11 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : NSOL_
     // own voxels of xbar plane zq located at element offset o; planes -1 / nz come from the z-slab
     // halos of the neighbouring rank (or are the zero boundary)
     auto load_xbar_own = [&](int zq, long long o) -> V {
-        const T *ptr = a.xbar_in + o;
-        if (zq < 0) ptr = a.halo_xbar_below ? a.halo_xbar_below + hrow : nullptr;
-        if (zq >= a.nz) ptr = a.halo_xbar_above ? a.halo_xbar_above + hrow : nullptr;
-        return (active && ptr) ? vec_load<T, VEC>(ptr) : vec_zero<T, VEC>();
+        if (zq < 0 || zq >= a.nz) {
+            const T *ptr = zq < 0 ? a.halo_xbar_below : a.halo_xbar_above;
+            return (active && ptr) ? vec_load_cg<T, VEC>(ptr + hrow) : vec_zero<T, VEC>();
+        }
+        return active ? vec_load<T, VEC>(a.xbar_in + o) : vec_zero<T, VEC>();
     };
     // loads of plane zq whose offsets are o (x, xbar, p) and bo (b).  Only xbn must be zero in
     // inactive threads (it supplies the Dirichlet zero to the neighbours); the other fields of an
@@ -194,6 +324,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : NSOL_
     };
 
     // ---- prologue: plane z0 --------------------------------------------------
+    if (LINK) pd_link_begin(a, z0, z1);
     PdStep<T, VEC> cur;
     load_step(z0, off, boff, cur);
     V xb_c = load_xbar_own(z0, off);
@@ -202,7 +333,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : NSOL_
     V pz_prev = vec_zero<T, VEC>();
     if (has_z && active && (z0 > 0 || a.halo_pz_below)) {
         V xb_m = load_xbar_own(z0 - 1, off - sz);
-        V pz_m = z0 > 0 ? vec_load<T, VEC>(a.pz_in + off - sz) : vec_load<T, VEC>(a.halo_pz_below + hrow);
+        V pz_m = z0 > 0 ? vec_load<T, VEC>(a.pz_in + off - sz) : vec_load_cg<T, VEC>(a.halo_pz_below + hrow);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) pz_prev.v[v] = dual_update<T, REG>(pz_m.v[v], xb_c.v[v], xb_m.v[v], wz, sigma, div_g);
     }
@@ -306,6 +437,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : NSOL_
         plane_step(z, cur, alt);
         if (z + 1 < z1) plane_step(z + 1, alt, cur);
     }
+    if (LINK) pd_link_finish<T, VEC>(a, z0, z1, hrow, active);
 }
 
 #include "pd_bulk_kernel.cuh"
@@ -339,7 +471,23 @@ struct nsol_pd_plan {
     bool ready = false;
     size_t bytes = 0;
     const void *halo_above = nullptr, *halo_below = nullptr, *halo_pz_below = nullptr;
+    // in-kernel halo exchange over peer memory (nsol_pd_plan_link_*)
+    char *link_block = nullptr;       // this rank's block: flags, counters, receive buffers
+    size_t link_plane = 0;            // bytes of one halo plane slot
+    char *peer_below = nullptr, *peer_above = nullptr;   // the neighbours' blocks mapped into this process
+    bool peer_below_ipc = false, peer_above_ipc = false;
+    bool link_on = false;
+    bool link_fresh = false;          // the neighbours hold the halos of the current state
+    unsigned link_pub = 0;            // generations published so far (= index of the next one)
 };
+
+// layout of a link block (all offsets 256-byte aligned)
+enum { LINK_FLAG_BELOW = 0, LINK_FLAG_ABOVE = 64, LINK_COUNT_BELOW = 128, LINK_COUNT_ABOVE = 192, LINK_ERROR = 224,
+       LINK_HEADER = 256 };
+// receive slots after the header: [parity][0 = xbar_above, 1 = xbar_below, 2 = pz_below]
+static inline size_t link_slot(const nsol_pd_plan *pl, int parity, int which) {
+    return LINK_HEADER + (size_t)(parity * 3 + which) * pl->link_plane;
+}
 
 // step sizes: reference nsol/primal_dual_solver.py:278-283, :302-306 (ALG2), :321-337, :356-358
 // (ALG3), :374-379, :398-403 (AHMOD); float64 host arithmetic in the reference's order.
@@ -425,6 +573,9 @@ extern "C" void nsol_pd_plan_destroy(nsol_pd_plan *pl) {
     }
     cudaFree(pl->stage);
     cudaFree(pl->sched);
+    if (pl->peer_below && pl->peer_below_ipc) cudaIpcCloseMemHandle(pl->peer_below);
+    if (pl->peer_above && pl->peer_above_ipc) cudaIpcCloseMemHandle(pl->peer_above);
+    cudaFree(pl->link_block);
     delete pl;
 }
 
@@ -544,6 +695,7 @@ static int pd_reset_common(nsol_pd_plan *pl, int src_dtype, const void *b_src, c
     pl->cur = 0;
     pl->it = 0;
     pl->ready = true;
+    pl->link_fresh = false;
     return NSOL_OK;
 }
 
@@ -606,12 +758,173 @@ static int pd_boundary_planes(nsol_pd_plan *pl, int which, const void **xbar_fir
     return NSOL_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// in-kernel halo exchange over peer memory
+// ---------------------------------------------------------------------------
+// Publishes the boundary planes of the CURRENT state (after a reset) as a new generation: waits
+// until both neighbours have published the previous generation (so nobody still reads the slots
+// about to be overwritten), copies the planes into the neighbours' receive slots and raises their
+// flags -- the same protocol the iteration kernels follow for the states they produce.
+struct LinkPublishArgs {
+    const char *xbar_first, *xbar_last, *pz_last;        // boundary planes of the current state
+    char *dst_below_xbar, *dst_above_xbar, *dst_above_pz;  // peer slots (NULL without that neighbour)
+    const unsigned *flag_below, *flag_above;
+    unsigned *peer_flag_below, *peer_flag_above;
+    unsigned *count;                                     // local arrival counter (the "below" one is reused)
+    int *error;
+    unsigned long long plane_vec;                        // 16-byte words per plane
+    unsigned want, publish;
+};
+
+__global__ void __launch_bounds__(256) pd_link_publish_kernel(const LinkPublishArgs a) {
+    if (a.flag_below) pd_link_wait(a.flag_below, a.want, a.error);
+    if (a.flag_above) pd_link_wait(a.flag_above, a.want, a.error);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.plane_vec; i += stride) {
+        if (a.dst_below_xbar) reinterpret_cast<float4 *>(a.dst_below_xbar)[i] = reinterpret_cast<const float4 *>(a.xbar_first)[i];
+        if (a.dst_above_xbar) {
+            reinterpret_cast<float4 *>(a.dst_above_xbar)[i] = reinterpret_cast<const float4 *>(a.xbar_last)[i];
+            reinterpret_cast<float4 *>(a.dst_above_pz)[i] = reinterpret_cast<const float4 *>(a.pz_last)[i];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(a.count, 1u);
+        if (done + 1u == gridDim.x) {
+            atomicExch(a.count, 0u);
+            __threadfence_system();
+            if (a.peer_flag_below) st_release_sys(a.peer_flag_below, a.publish);
+            if (a.peer_flag_above) st_release_sys(a.peer_flag_above, a.publish);
+        }
+    }
+}
+
+static int pd_link_publish(nsol_pd_plan *pl, cudaStream_t s) {
+    nsol_ctx *ctx = pl->ctx;
+    const GridView &gv = pl->gv;
+    const size_t plane = (size_t)gv.nx * gv.ny * pl->esz;
+    const unsigned g = pl->link_pub;
+    const int wr = (int)(g & 1u);
+    const char *xb = (const char *)pl->xbar[pl->cur];
+    LinkPublishArgs a;
+    a.xbar_first = xb;
+    a.xbar_last = xb + (size_t)(gv.nz - 1) * plane;
+    a.pz_last = (const char *)pl->p[pl->cur][gv.comp_z] + (size_t)(gv.nz - 1) * plane;
+    a.dst_below_xbar = pl->peer_below ? pl->peer_below + link_slot(pl, wr, 0) : nullptr;
+    a.dst_above_xbar = pl->peer_above ? pl->peer_above + link_slot(pl, wr, 1) : nullptr;
+    a.dst_above_pz = pl->peer_above ? pl->peer_above + link_slot(pl, wr, 2) : nullptr;
+    a.flag_below = pl->peer_below ? (const unsigned *)(pl->link_block + LINK_FLAG_BELOW) : nullptr;
+    a.flag_above = pl->peer_above ? (const unsigned *)(pl->link_block + LINK_FLAG_ABOVE) : nullptr;
+    a.peer_flag_below = pl->peer_below ? (unsigned *)(pl->peer_below + LINK_FLAG_ABOVE) : nullptr;
+    a.peer_flag_above = pl->peer_above ? (unsigned *)(pl->peer_above + LINK_FLAG_BELOW) : nullptr;
+    a.count = (unsigned *)(pl->link_block + LINK_COUNT_BELOW);
+    a.error = (int *)(pl->link_block + LINK_ERROR);
+    a.plane_vec = plane / 16;
+    a.want = g;               // neighbours have published generation g - 1 (trivially true for g = 0)
+    a.publish = g + 1u;
+    pd_link_publish_kernel<<<32, 256, 0, s>>>(a);
+    NSOL_LAUNCH_CHECK(ctx);
+    pl->link_pub = g + 1u;
+    pl->link_fresh = true;
+    return NSOL_OK;
+}
+
+extern "C" int nsol_pd_plan_link_create(nsol_pd_plan *pl, void **block_dev, size_t *block_bytes) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    const GridView &gv = pl->gv;
+    if (gv.dim < 2) return nsol_fail(ctx, NSOL_EINVAL, "pd link: slab decomposition needs dim >= 2");
+    if (gv.batch != 1) return nsol_fail(ctx, NSOL_EINVAL, "pd link: batch must be 1");
+    const size_t plane = (size_t)gv.nx * gv.ny * pl->esz;
+    if (plane % 16) return nsol_fail(ctx, NSOL_EINVAL, "pd link: a plane must be a multiple of 16 bytes (nx*ny = %lld)", (long long)gv.nx * gv.ny);
+    NSOL_CHECK(nsol_bind_device(ctx));
+    if (!pl->link_block) {
+        pl->link_plane = (plane + 255) / 256 * 256;
+        const size_t bytes = LINK_HEADER + 6 * pl->link_plane;
+        NSOL_CUDA(ctx, cudaMalloc((void **)&pl->link_block, bytes));
+        NSOL_CUDA(ctx, cudaMemset(pl->link_block, 0, bytes));
+        pl->bytes += bytes;
+    }
+    if (block_dev) *block_dev = pl->link_block;
+    if (block_bytes) *block_bytes = LINK_HEADER + 6 * pl->link_plane;
+    return NSOL_OK;
+}
+
+extern "C" int nsol_pd_plan_link_ipc_handle(nsol_pd_plan *pl, void *handle64) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    if (!handle64) return nsol_fail(ctx, NSOL_EINVAL, "pd link: handle buffer is NULL");
+    NSOL_CHECK(nsol_pd_plan_link_create(pl, nullptr, nullptr));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    NSOL_CUDA(ctx, cudaIpcGetMemHandle(&h, pl->link_block));
+    memcpy(handle64, &h, 64);
+    return NSOL_OK;
+}
+
+static int pd_link_set_peers(nsol_pd_plan *pl, char *below, bool below_ipc, char *above, bool above_ipc) {
+    nsol_ctx *ctx = pl->ctx;
+    if (!pl->link_block) return nsol_fail(ctx, NSOL_ESTATE, "pd link: call nsol_pd_plan_link_create first");
+    if (pl->link_on) return nsol_fail(ctx, NSOL_ESTATE, "pd link: already connected");
+    pl->peer_below = below;
+    pl->peer_below_ipc = below_ipc;
+    pl->peer_above = above;
+    pl->peer_above_ipc = above_ipc;
+    pl->link_on = (below != nullptr) || (above != nullptr);
+    pl->link_fresh = false;
+    pl->link_pub = 0;
+    return NSOL_OK;
+}
+
+extern "C" int nsol_pd_plan_link_connect(nsol_pd_plan *pl, void *block_below, void *block_above) {
+    if (!pl) return NSOL_EINVAL;
+    return pd_link_set_peers(pl, (char *)block_below, false, (char *)block_above, false);
+}
+
+extern "C" int nsol_pd_plan_link_open(nsol_pd_plan *pl, const void *handle_below64, const void *handle_above64) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    NSOL_CHECK(nsol_bind_device(ctx));
+    void *below = nullptr, *above = nullptr;
+    cudaIpcMemHandle_t h;
+    if (handle_below64) {
+        memcpy(&h, handle_below64, 64);
+        NSOL_CUDA(ctx, cudaIpcOpenMemHandle(&below, h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    if (handle_above64) {
+        memcpy(&h, handle_above64, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&above, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            if (below) cudaIpcCloseMemHandle(below);
+            return nsol_fail(ctx, NSOL_ECUDA, "pd link: cudaIpcOpenMemHandle -> %s", cudaGetErrorString(e));
+        }
+    }
+    return pd_link_set_peers(pl, (char *)below, below != nullptr, (char *)above, above != nullptr);
+}
+
+// synchronises the stream and reports a timed-out wait of any launch so far
+extern "C" int nsol_pd_plan_link_status(nsol_pd_plan *pl, nsol_stream s) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    if (!pl->link_block) return NSOL_OK;
+    NSOL_CHECK(nsol_bind_device(ctx));
+    int err = 0;
+    NSOL_CUDA(ctx, cudaMemcpyAsync(&err, pl->link_block + LINK_ERROR, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)s));
+    NSOL_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)s));
+    if (err) return nsol_fail(ctx, NSOL_ENCCL, "pd link: a wait for a neighbour's halo timed out (neighbour not iterating in lockstep?)");
+    return NSOL_OK;
+}
+
 template <typename T, int VEC, bool HAS_Y>
 static void pd_launch_rd(const nsol_pd_plan *pl, const PdArgs<T> &a, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
     const int reg = pl->desc.reg, data = pl->desc.data;
+    const bool link = pl->link_on;
 #define NSOL_PD_CASE(R, D)                                                                 \
     if (reg == R && data == D) {                                                           \
-        pd_iter_kernel<T, VEC, HAS_Y, R, D><<<grid, block, smem, s>>>(a);                  \
+        if (link) pd_iter_kernel<T, VEC, HAS_Y, R, D, true><<<grid, block, smem, s>>>(a);  \
+        else pd_iter_kernel<T, VEC, HAS_Y, R, D, false><<<grid, block, smem, s>>>(a);      \
         return;                                                                            \
     }
     NSOL_PD_CASE(NSOL_REG_TV, NSOL_DATA_L2)
@@ -624,20 +937,29 @@ static void pd_launch_rd(const nsol_pd_plan *pl, const PdArgs<T> &a, dim3 grid, 
 }
 
 // bulk-async (TMA) staged variant: 3-D, vector path only
+template <typename T, int VEC, int R, int D, bool LINK, bool UNIT>
+static int pd_launch_bulk_one(const nsol_pd_plan *pl, const PdArgs<T> &a, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(pd_iter_bulk_kernel<T, VEC, R, D, LINK, UNIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return nsol_fail(pl->ctx, NSOL_ECUDA, "pd bulk: smem opt-in %zu -> %s", smem, cudaGetErrorString(e));
+        configured = smem;
+    }
+    pd_iter_bulk_kernel<T, VEC, R, D, LINK, UNIT><<<grid, block, smem, s>>>(a);
+    return NSOL_OK;
+}
+
 template <typename T, int VEC>
 static int pd_launch_bulk(const nsol_pd_plan *pl, const PdArgs<T> &a, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
     const int reg = pl->desc.reg, data = pl->desc.data;
+    const bool link = pl->link_on;
+    const bool unit = a.wx == T(1) && a.wy == T(1) && a.wz == T(1);
 #define NSOL_PD_CASE(R, D)                                                                              \
     if (reg == R && data == D) {                                                                        \
-        static size_t configured = 0;                                                                   \
-        if (smem > configured) {                                                                        \
-            cudaError_t e = cudaFuncSetAttribute(pd_iter_bulk_kernel<T, VEC, R, D>,                     \
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e != cudaSuccess) return nsol_fail(pl->ctx, NSOL_ECUDA, "pd bulk: smem opt-in %zu -> %s", smem, cudaGetErrorString(e)); \
-            configured = smem;                                                                          \
-        }                                                                                               \
-        pd_iter_bulk_kernel<T, VEC, R, D><<<grid, block, smem, s>>>(a);                                 \
-        return NSOL_OK;                                                                                 \
+        if (link) return unit ? pd_launch_bulk_one<T, VEC, R, D, true, true>(pl, a, grid, block, smem, s)    \
+                              : pd_launch_bulk_one<T, VEC, R, D, true, false>(pl, a, grid, block, smem, s);  \
+        return unit ? pd_launch_bulk_one<T, VEC, R, D, false, true>(pl, a, grid, block, smem, s)         \
+                    : pd_launch_bulk_one<T, VEC, R, D, false, false>(pl, a, grid, block, smem, s);       \
     }
     NSOL_PD_CASE(NSOL_REG_TV, NSOL_DATA_L2)
     NSOL_PD_CASE(NSOL_REG_TV, NSOL_DATA_L1)
@@ -695,6 +1017,38 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0) {
     a.halo_xbar_above = (const T *)pl->halo_above;
     a.halo_xbar_below = (const T *)pl->halo_below;
     a.halo_pz_below = (const T *)pl->halo_pz_below;
+    a.flag_below = a.flag_above = nullptr;
+    a.peer_flag_below = a.peer_flag_above = nullptr;
+    a.count_below = a.count_above = nullptr;
+    a.push_below_xbar = a.push_above_xbar = a.push_above_pz = nullptr;
+    a.link_error = nullptr;
+    a.want = a.publish = 0;
+    a.front_chunks = 0;
+    if (pl->link_on) {
+        if (part != 0) return nsol_fail(ctx, NSOL_ESTATE, "pd: the split iteration is not available with the in-kernel halo exchange");
+        // this iteration consumes generation g = link_pub - 1 and publishes generation link_pub
+        const unsigned g = pl->link_pub - 1;
+        const int rd = (int)(g & 1u), wr = (int)(pl->link_pub & 1u);
+        a.link_error = (int *)(pl->link_block + LINK_ERROR);
+        a.want = g + 1u;
+        a.publish = pl->link_pub + 1u;
+        if (pl->peer_below) {
+            a.halo_xbar_below = (const T *)(pl->link_block + link_slot(pl, rd, 1));
+            a.halo_pz_below = (const T *)(pl->link_block + link_slot(pl, rd, 2));
+            a.flag_below = (const unsigned *)(pl->link_block + LINK_FLAG_BELOW);
+            a.count_below = (unsigned *)(pl->link_block + LINK_COUNT_BELOW);
+            a.push_below_xbar = (T *)(pl->peer_below + link_slot(pl, wr, 0));      // their xbar_above
+            a.peer_flag_below = (unsigned *)(pl->peer_below + LINK_FLAG_ABOVE);    // I am their upper neighbour
+        }
+        if (pl->peer_above) {
+            a.halo_xbar_above = (const T *)(pl->link_block + link_slot(pl, rd, 0));
+            a.flag_above = (const unsigned *)(pl->link_block + LINK_FLAG_ABOVE);
+            a.count_above = (unsigned *)(pl->link_block + LINK_COUNT_ABOVE);
+            a.push_above_xbar = (T *)(pl->peer_above + link_slot(pl, wr, 1));      // their xbar_below
+            a.push_above_pz = (T *)(pl->peer_above + link_slot(pl, wr, 2));        // their pz_below
+            a.peer_flag_above = (unsigned *)(pl->peer_above + LINK_FLAG_BELOW);    // I am their lower neighbour
+        }
+    }
     a.n = gv.n;
     a.b_stride = pl->desc.b_batched ? gv.n : 0;
     a.nx = gv.nx;
@@ -736,6 +1090,7 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0) {
             a.chunk_first = 1;
         }
     }
+    a.front_chunks = (pl->link_on && a.nchunks >= 3) ? 1 : 0;
     const long long gz = (long long)a.nsel * gv.batch;
     if (gz > 65535) return nsol_fail(ctx, NSOL_EINVAL, "pd: nchunks*batch = %lld exceeds the grid limit; raise pd_zc", gz);
     grid.z = (unsigned)gz;
@@ -755,6 +1110,7 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0) {
     if (part != 1) {
         pl->cur = nxt;
         pl->it += 1;
+        if (pl->link_on) pl->link_pub += 1;
     }
     return NSOL_OK;
 }
@@ -770,6 +1126,7 @@ extern "C" int nsol_pd_plan_iterate(nsol_pd_plan *pl, int n, nsol_stream s) {
     cudaStream_t st = (cudaStream_t)s;
     const int vecw = gv.dtype == NSOL_F32 ? 4 : 2;
     const bool vec_ok = (gv.nx % vecw) == 0;
+    if (pl->link_on && !pl->link_fresh) NSOL_CHECK(pd_link_publish(pl, st));   // also for n == 0 (publish only)
     for (int i = 0; i < n; ++i) {
         int rc;
         if (gv.dtype == NSOL_F32) rc = vec_ok ? pd_launch_iteration<float, 4>(pl, st) : pd_launch_iteration<float, 1>(pl, st);
@@ -833,6 +1190,7 @@ extern "C" int nsol_pd_plan_get_x_host(nsol_pd_plan *pl, double *x_host, nsol_st
     NSOL_CHECK(nsol_scale_convert(ctx, (int64_t)nv, pl->gv.dtype, pl->x, NSOL_F64, pl->stage, pl->desc.x_scale, 0, s));
     NSOL_CUDA(ctx, cudaMemcpyAsync(x_host, pl->stage, nv * sizeof(double), cudaMemcpyDeviceToHost, st));
     NSOL_CUDA(ctx, cudaStreamSynchronize(st));
+    if (pl->link_on) NSOL_CHECK(nsol_pd_plan_link_status(pl, s));
     return NSOL_OK;
 }
 

@@ -88,26 +88,83 @@ def tensor_from_ptr(ptr, numel, np_dtype, device):
 class SlabPrimalDual(object):
     """z-slab sharded fused primal-dual iteration on one GPU per rank.
 
-    Wraps an ``nsol_pd_plan`` built for the local slab, wires its halo pointers to the
-    exchanger's receive buffers and alternates  exchange -> one fused iteration."""
+    Wraps an ``nsol_pd_plan`` built for the local slab.  Two ways to move the three halo planes:
 
-    def __init__(self, ctx, desc, plane_numel, np_dtype, rank, world, device):
+    * ``halo="p2p"`` (default where CUDA IPC between the ranks' GPUs works): the in-kernel exchange over
+      peer memory (``nsol_pd_plan_link_*``).  The boundary CTAs of every iteration store their new
+      boundary planes straight into the neighbours' receive slots over NVLink and raise a flag; the
+      neighbours' next launch waits on it.  ``iterate(n)`` queues n launches, nothing else.
+    * ``halo="nccl"``: grouped NCCL send/recv between neighbours before every launch
+      (``HaloExchanger``), optionally overlapped with the interior chunks (``overlap=True``).
+    ``halo="auto"`` tries p2p and falls back to nccl (all ranks together, with a warning)."""
+
+    def __init__(self, ctx, desc, plane_numel, np_dtype, rank, world, device, halo="auto"):
         import ctypes as C
         self.C = C
         self.ctx = ctx
         self.np_dtype = np_dtype
         self.plane_numel = plane_numel
         self.device = device
+        self.rank, self.world = rank, world
         h = C.c_void_p()
         ctx.check(ctx.lib.nsol_pd_plan_create(ctx.handle, C.byref(desc), C.byref(h)))
         self.plan = h
-        import torch
-        tdtype = torch.float32 if np.dtype(np_dtype) == np.float32 else torch.float64
-        self.halo = HaloExchanger(rank, world, plane_numel, tdtype, device)
-        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
-        ctx.check(ctx.lib.nsol_pd_plan_set_halo(self.plan, ptr(self.halo.xbar_above), ptr(self.halo.xbar_below),
-                                               ptr(self.halo.pz_below)))
         self._views = {}
+        self.halo = None
+        self.mode = "single" if world == 1 else halo
+        if world == 1:
+            return
+        if self.mode not in ("auto", "p2p", "nccl"):
+            raise ValueError("halo must be 'auto', 'p2p' or 'nccl'")
+        if self.mode in ("auto", "p2p"):
+            err = self._connect_link()
+            if err is None:
+                self.mode = "p2p"
+            elif self.mode == "p2p":
+                raise RuntimeError("in-kernel halo exchange unavailable: %s" % err)
+            else:
+                if rank == 0:
+                    import sys
+                    sys.stderr.write("nsol_b200: peer-memory halo exchange unavailable (%s); using NCCL send/recv\n" % err)
+                self.mode = "nccl"
+        if self.mode == "nccl":
+            import torch
+            tdtype = torch.float32 if np.dtype(np_dtype) == np.float32 else torch.float64
+            self.halo = HaloExchanger(rank, world, plane_numel, tdtype, device)
+            ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+            ctx.check(ctx.lib.nsol_pd_plan_set_halo(self.plan, ptr(self.halo.xbar_above), ptr(self.halo.xbar_below),
+                                                   ptr(self.halo.pz_below)))
+
+    def _connect_link(self):
+        """Exchange the CUDA IPC handles of the link blocks with the neighbours and map theirs.
+        Returns None on success (on every rank) or a message (on every rank)."""
+        import torch.distributed as dist
+        C, lib, ctx = self.C, self.ctx.lib, self.ctx
+        handle = (C.c_char * 64)()
+        err = None
+        try:
+            ctx.check(lib.nsol_pd_plan_link_ipc_handle(self.plan, handle))
+        except Exception as e:      # e.g. plane not a multiple of 16 bytes
+            err = "rank %d: %s" % (self.rank, e)
+        mine = bytes(handle.raw) if err is None else None
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine)
+        if any(hd is None for hd in handles):
+            err = err or "a rank could not export its link block"
+        else:
+            below = handles[self.rank - 1] if self.rank > 0 else None
+            above = handles[self.rank + 1] if self.rank < self.world - 1 else None
+            try:
+                ctx.check(lib.nsol_pd_plan_link_open(self.plan, below, above))
+            except Exception as e:
+                err = "rank %d: %s" % (self.rank, e)
+        errs = [None] * self.world
+        dist.all_gather_object(errs, err)
+        errs = [e for e in errs if e]
+        if errs and err is None:
+            # somebody failed: this rank must not stay in link mode on its own
+            raise RuntimeError("in-kernel halo exchange: inconsistent setup (%s)" % errs[0])
+        return errs[0] if errs else None
 
     def _boundary_tensors(self, upcoming=False):
         """Boundary planes of the current state, or (upcoming=True) of the state the running
@@ -121,13 +178,14 @@ class SlabPrimalDual(object):
             self._views[key] = tuple(tensor_from_ptr(p, self.plane_numel, self.np_dtype, self.device) for p in key)
         return self._views[key]
 
-    def iterate(self, n, stream, overlap=True):
-        """n iterations.  With overlap (default, needs >= 3 z-chunks) every iteration is split:
-        the two boundary chunks run first, their new boundary planes are exchanged while the
-        interior chunks compute, and the next iteration starts when both have finished.
-        Without overlap: exchange, then one full-iteration launch."""
+    def iterate(self, n, stream, overlap=False):
+        """n iterations (every rank must call this with the same n).
+        p2p: n back-to-back launches, the halo exchange happens inside the kernels.
+        nccl: exchange, then one full-iteration launch; with overlap (needs >= 3 z-chunks) every
+        iteration is split: the two boundary chunks run first, their new boundary planes are
+        exchanged while the interior chunks compute."""
         lib, ctx, plan = self.ctx.lib, self.ctx, self.plan
-        if self.halo.world == 1:
+        if self.mode in ("single", "p2p"):
             ctx.check(lib.nsol_pd_plan_iterate(plan, n, stream))
             return
         if not overlap or lib.nsol_pd_plan_chunks(plan) < 3:
@@ -145,6 +203,10 @@ class SlabPrimalDual(object):
             self.halo.finish_exchange(reqs)
         self._halo_fresh = True     # the halos now belong to the current state
 
+    def check(self, stream):
+        """Synchronise and raise if an in-kernel halo wait timed out."""
+        self.ctx.check(self.ctx.lib.nsol_pd_plan_link_status(self.plan, stream))
+
     def reset_host(self, b_host_ptr, x0_host_ptr, stream):
         self._halo_fresh = False
         self.ctx.check(self.ctx.lib.nsol_pd_plan_reset_host(self.plan, b_host_ptr, x0_host_ptr, stream))
@@ -155,5 +217,11 @@ class SlabPrimalDual(object):
 
     def close(self):
         if self.plan is not None:
+            if self.mode == "p2p":
+                # the neighbours' kernels write into this rank's link block: everybody finishes first
+                import torch
+                import torch.distributed as dist
+                torch.cuda.synchronize()
+                dist.barrier()
             self.ctx.lib.nsol_pd_plan_destroy(self.plan)
             self.plan = None

@@ -193,7 +193,7 @@ class PrimalDualSolver(Solver):
         ctx.check(lib.nsol_pd_plan_reset_host(plan, b.ctypes.data, x0.ctypes.data, None))
 
         def fetch():
-            out = np.empty(n, dtype=np.float64)
+            out = ctx.result_empty(n, np.float64)
             ctx.check(lib.nsol_pd_plan_get_x_host(plan, out.ctypes.data, None))
             return out
 
@@ -257,7 +257,7 @@ class PrimalDualSolver(Solver):
         desc = self._make_desc(cfg, alphas)
         x0 = np.ascontiguousarray(self._x0, dtype=np.float64)
         b = np.ascontiguousarray(cfg["b"], dtype=np.float64)
-        x_out = np.empty((len(alphas), n), dtype=np.float64)
+        x_out = ctx.result_empty((len(alphas), n), np.float64)
         ctx.check(ctx.lib.nsol_pd_run_host(ctx.handle, C.byref(desc), int(self._iterations), b.ctypes.data,
                                            x0.ctypes.data, x_out.ctypes.data, None, None))
         return x_out

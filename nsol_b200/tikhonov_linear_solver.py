@@ -60,7 +60,7 @@ class TikhonovLinearSolver(LinearSolver):
             b_reg = None
             if np.ndim(self._b_reg) != 0 or float(self._b_reg) != 0.0:
                 b_reg = np.ascontiguousarray(np.broadcast_to(np.asarray(self._b_reg, dtype=np.float64), (rows,)))
-            x_out = np.empty(n, dtype=np.float64)
+            x_out = ctx.result_empty(n, np.float64)
             ctx.check(ctx.lib.nsol_tikhonov_run_host(
                 plan.handle, float(self._alpha), 1.0, float(self._x_scale), b.ctypes.data,
                 b_reg.ctypes.data if b_reg is not None else None, int(self._iter_max), lo, hi,

@@ -468,6 +468,113 @@ def test_zslab_emulation_matches_unsharded(dtype, nslabs, split):
         assert rel_max(np.concatenate(parts), ref) < 1e-5
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("nslabs,zc", [(2, 0), (3, 2)])
+def test_zslab_link_emulation_matches_unsharded(dtype, nslabs, zc, variant):
+    """The in-kernel halo exchange (nsol_pd_plan_link_*): S slabs on ONE GPU whose link blocks are
+    connected by raw pointers (on S GPUs: CUDA IPC handles), driven alternately on one stream --
+    the kernels push their boundary planes into the neighbour's receive slots and raise / wait on
+    the generation flags themselves.  Two solves back to back exercise the generation counters
+    across a reset.  Bit-exact against the unsharded run."""
+    import ctypes as C
+    from nsol_b200.distributed import slab_bounds
+    rng = np.random.RandomState(5)
+    shape = (23, 10, 68)
+    obs = rng.rand(*shape) * 255
+    xs = float(obs.max())
+    ctx = _lib.context()
+    lib = ctx.lib
+    dcode = _lib.dtype_code(dtype)
+    plane = shape[1] * shape[2]
+    alpha = np.array([0.05])
+    ctx.set_tuning("pd_variant", variant)
+    ctx.set_tuning("pd_zc", zc)          # zc = 2: >= 3 chunks per slab, boundary chunks scheduled first
+    plans, spans, blocks = [], [], []
+    try:
+        for r in range(nslabs):
+            z_lo, z_hi = slab_bounds(shape[0], r, nslabs)
+            spans.append((z_lo, z_hi))
+            desc = _lib.PdDesc()
+            desc.grid = _lib.make_grid((z_hi - z_lo,) + shape[1:], None, dcode, 1)
+            desc.reg, desc.data, desc.alg = _lib.REG["TV"], _lib.DATA["L2"], _lib.ALG["ALG2"]
+            desc.huber_gamma, desc.L2 = 0.05, 8.0
+            desc.x_scale = desc.x0_scale = desc.b_scale = xs
+            desc.alpha = alpha.ctypes.data_as(_lib.c_double_p)
+            h = C.c_void_p()
+            ctx.check(lib.nsol_pd_plan_create(ctx.handle, C.byref(desc), C.byref(h)))
+            plans.append(h)
+            blk, nbytes = C.c_void_p(), C.c_size_t()
+            ctx.check(lib.nsol_pd_plan_link_create(h, C.byref(blk), C.byref(nbytes)))
+            assert nbytes.value >= 6 * plane * (4 if dcode == _lib.F32 else 8)
+            blocks.append(blk)
+        for r, h in enumerate(plans):
+            ctx.check(lib.nsol_pd_plan_link_connect(h, blocks[r - 1] if r > 0 else None,
+                                                    blocks[r + 1] if r < nslabs - 1 else None))
+        for iters in (7, 4):            # second solve: generations continue across the reset
+            ref = run_pd(obs, reg="TV", data="L2", alpha=0.05, L2=8, iterations=iters, x_scale=xs, dtype=dtype)
+            ctx.set_tuning("pd_variant", variant)
+            ctx.set_tuning("pd_zc", zc)
+            for (z_lo, z_hi), h in zip(spans, plans):
+                slab = np.ascontiguousarray(obs[z_lo:z_hi]).reshape(-1)
+                ctx.check(lib.nsol_pd_plan_reset_host(h, slab.ctypes.data, None, None))
+            for h in plans:
+                ctx.check(lib.nsol_pd_plan_iterate(h, 0, None))      # publish the start state
+            for _ in range(iters):
+                for h in plans:
+                    ctx.check(lib.nsol_pd_plan_iterate(h, 1, None))
+            parts = []
+            for (z_lo, z_hi), h in zip(spans, plans):
+                out = np.empty((z_hi - z_lo) * plane)
+                ctx.check(lib.nsol_pd_plan_get_x_host(h, out.ctypes.data, None))   # also checks the link status
+                parts.append(out)
+            if dtype == "float64":
+                assert np.array_equal(np.concatenate(parts), ref)
+            else:
+                assert rel_max(np.concatenate(parts), ref) < 1e-5
+    finally:
+        ctx.set_tuning("pd_zc", 0)
+        ctx.set_tuning("pd_variant", 0)
+        for h in plans:
+            lib.nsol_pd_plan_destroy(h)
+
+
+def test_zslab_link_timeout_is_reported():
+    """A linked plan whose neighbour never publishes must not hang: the wait gives up after
+    NSOL_LINK_TIMEOUT_NS and get_x / link_status report it."""
+    import ctypes as C
+    ctx = _lib.context()
+    lib = ctx.lib
+    shape = (6, 4, 8)
+    obs = np.random.RandomState(0).rand(*shape)
+    alpha = np.array([0.05])
+    plans, blocks = [], []
+    try:
+        for r in range(2):
+            desc = _lib.PdDesc()
+            desc.grid = _lib.make_grid(shape, None, _lib.F64, 1)
+            desc.reg, desc.data, desc.alg = _lib.REG["TV"], _lib.DATA["L2"], _lib.ALG["ALG2"]
+            desc.huber_gamma, desc.L2 = 0.05, 8.0
+            desc.x_scale = desc.x0_scale = desc.b_scale = 1.0
+            desc.alpha = alpha.ctypes.data_as(_lib.c_double_p)
+            h = C.c_void_p()
+            ctx.check(lib.nsol_pd_plan_create(ctx.handle, C.byref(desc), C.byref(h)))
+            plans.append(h)
+            blk = C.c_void_p()
+            ctx.check(lib.nsol_pd_plan_link_create(h, C.byref(blk), None))
+            blocks.append(blk)
+        ctx.check(lib.nsol_pd_plan_link_connect(plans[0], None, blocks[1]))
+        ctx.check(lib.nsol_pd_plan_link_connect(plans[1], blocks[0], None))
+        flat = np.ascontiguousarray(obs.reshape(-1))
+        ctx.check(lib.nsol_pd_plan_reset_host(plans[0], flat.ctypes.data, None, None))
+        ctx.check(lib.nsol_pd_plan_iterate(plans[0], 1, None))       # plan 1 never publishes
+        with pytest.raises(RuntimeError, match="timed out"):
+            ctx.check(lib.nsol_pd_plan_link_status(plans[0], None))
+    finally:
+        for h in plans:
+            lib.nsol_pd_plan_destroy(h)
+
+
 # ------------------------------------------------------------------ primal-dual deconvolution (prox_linear_least_squares)
 def make_pd_deconv(obs, var, reg, alpha, iterations, iter_max, x_scale, L2=8, dtype=None):
     """nsol/deconvolution_solver_parameter_study_interface.py:255-280 (TV) / :303-325 (Huber)."""

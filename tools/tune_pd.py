@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--data", default="L2")
     ap.add_argument("--dim", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--warm", type=int, default=3, help="untimed iterations before the timed ones (use ~300 for the power-capped sustained regime)")
     args = ap.parse_args()
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -61,7 +62,7 @@ def main():
                 ctx.set_tuning("pd_zc", zc)
                 ctx.set_tuning("pd_variant", variant)
                 ctx.check(ctx.lib.nsol_pd_plan_reset_dev(plan, C.c_void_p(obs.data_ptr()), None, stream))
-                ctx.check(ctx.lib.nsol_pd_plan_iterate(plan, 3, stream))
+                ctx.check(ctx.lib.nsol_pd_plan_iterate(plan, args.warm, stream))
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
