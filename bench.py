@@ -60,7 +60,7 @@ def synth_volume(shape, seed=1):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks/throttle reasons sampled every 50 ms during the timed region."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -75,7 +75,7 @@ class ClockSampler(object):
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -124,6 +124,27 @@ def measured_traffic(dtype_key, nvox):
         return t["bytes_per_launch"] * (nvox / float(t["voxels"]))
     except Exception:
         return None
+
+
+def device_copy_bandwidth(nbytes=1 << 31):
+    """Device-to-device copy bandwidth (read + write bytes) of THIS GPU in this run, measured the way
+    MEASURED_PEAKS.json was (torch b.copy_(a), best of 10): separates GPU-to-GPU variation of the HBM
+    peak from the kernel's own efficiency."""
+    import torch
+    a = torch.empty(nbytes // 2, dtype=torch.bfloat16, device="cuda")
+    b = torch.empty_like(a)
+    a.zero_()
+    best = None
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        b.copy_(a)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    del a, b
+    return 2.0 * nbytes / (best * 1e-3) / 1e9
 
 
 def pcie_bandwidth(ctx, stream, nbytes=1 << 28):
@@ -480,6 +501,7 @@ def main():
         other = measure(od, False)
 
     peak, peak_src = measured_peak()
+    copy_gbs = device_copy_bandwidth() if rank == 0 else None
     if rank == 0:
         esz = 4 if args.dtype == "float32" else 8
         achieved = 11 * esz * nvox_loc / (main_res["iter_ms"] * 1e-3) / 1e9
@@ -499,7 +521,8 @@ def main():
             "clocks": main_res["clocks"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic("f64" if args.dtype == "float64" else "f32", nvox_loc), "peak_source": peak_src, "kernel": "pd_iter_kernel",
-                         "algorithmic_bytes_per_launch": 11 * esz * nvox_loc, "avg_launch_ms": main_res["iter_ms"]},
+                         "algorithmic_bytes_per_launch": 11 * esz * nvox_loc, "avg_launch_ms": main_res["iter_ms"],
+                         "copy_gbs_this_gpu": copy_gbs, "frac_of_copy_this_gpu": achieved / copy_gbs},
         }
         if "e2e" in main_res:
             line["e2e"] = main_res["e2e"]

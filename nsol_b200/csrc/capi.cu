@@ -56,6 +56,7 @@ extern "C" int nsol_set_tuning(nsol_ctx *ctx, const char *key, int value) {
     else if (!strcmp(key, "pd_variant")) ctx->pd_variant = value;
     else if (!strcmp(key, "lsmr_blocks")) ctx->lsmr_blocks = value;
     else if (!strcmp(key, "lsmr_path")) ctx->lsmr_path = value;
+    else if (!strcmp(key, "link_timeout_ms")) ctx->link_timeout_ms = value;
     else return nsol_fail(ctx, NSOL_EINVAL, "nsol_set_tuning: unknown key '%s'", key);
     return NSOL_OK;
 }

@@ -43,6 +43,7 @@ struct PdArgs {
     T *push_below_xbar;                        // lower neighbour's xbar_above halo plane (peer memory)
     T *push_above_xbar, *push_above_pz;        // upper neighbour's xbar_below / pz_below halo planes
     int *link_error;                           // set when a wait timed out
+    unsigned long long link_timeout_ns;
     unsigned want, publish;                    // flag value this iteration needs / stores when its boundary is done
     int front_chunks;                          // 1: schedule the two boundary chunks first (link mode)
     long long n;                      // voxels per problem
@@ -78,17 +79,17 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 #ifndef NSOL_LINK_INLINE
 #define NSOL_LINK_INLINE __noinline__
 #endif
-#ifndef NSOL_LINK_TIMEOUT_NS
-#define NSOL_LINK_TIMEOUT_NS 5000000000ull
+#ifndef NSOL_LINK_TIMEOUT_MS
+#define NSOL_LINK_TIMEOUT_MS 5000   // default; nsol_set_tuning("link_timeout_ms")
 #endif
 // every calling thread polls the flag itself (same address: one broadcast load per warp)
-__device__ NSOL_LINK_INLINE void pd_link_wait(const unsigned *flag, unsigned want, int *error) {
+__device__ NSOL_LINK_INLINE void pd_link_wait(const unsigned *flag, unsigned want, int *error, unsigned long long timeout_ns) {
     if ((int)(ld_acquire_sys(flag) - want) >= 0) return;
     if (*(volatile int *)error) return;           // a neighbour already failed: do not wait again
     const unsigned long long t0 = global_timer_ns();
     while ((int)(ld_acquire_sys(flag) - want) < 0) {
         __nanosleep(64);
-        if (global_timer_ns() - t0 > NSOL_LINK_TIMEOUT_NS) {
+        if (global_timer_ns() - t0 > timeout_ns) {
             *(volatile int *)error = 1;
             return;
         }
@@ -201,8 +202,8 @@ __device__ __forceinline__ void primal_update(T xv, T bv, T div, T tau, T tl, T 
 // normally falls straight through.)  Every thread polls for itself.
 template <typename T>
 __device__ __forceinline__ void pd_link_begin(const PdArgs<T> &a, int z0, int z1) {
-    if (z0 == 0 && a.flag_below) pd_link_wait(a.flag_below, a.want, a.link_error);
-    if (z1 == a.nz && a.flag_above) pd_link_wait(a.flag_above, a.want, a.link_error);
+    if (z0 == 0 && a.flag_below) pd_link_wait(a.flag_below, a.want, a.link_error, a.link_timeout_ns);
+    if (z1 == a.nz && a.flag_above) pd_link_wait(a.flag_above, a.want, a.link_error, a.link_timeout_ns);
 }
 
 // Link mode, end of a CTA: boundary CTAs copy the boundary planes of the NEW state (their own
@@ -774,12 +775,13 @@ struct LinkPublishArgs {
     unsigned *count;                                     // local arrival counter (the "below" one is reused)
     int *error;
     unsigned long long plane_vec;                        // 16-byte words per plane
+    unsigned long long timeout_ns;
     unsigned want, publish;
 };
 
 __global__ void __launch_bounds__(256) pd_link_publish_kernel(const LinkPublishArgs a) {
-    if (a.flag_below) pd_link_wait(a.flag_below, a.want, a.error);
-    if (a.flag_above) pd_link_wait(a.flag_above, a.want, a.error);
+    if (a.flag_below) pd_link_wait(a.flag_below, a.want, a.error, a.timeout_ns);
+    if (a.flag_above) pd_link_wait(a.flag_above, a.want, a.error, a.timeout_ns);
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.plane_vec; i += stride) {
         if (a.dst_below_xbar) reinterpret_cast<float4 *>(a.dst_below_xbar)[i] = reinterpret_cast<const float4 *>(a.xbar_first)[i];
@@ -822,6 +824,7 @@ static int pd_link_publish(nsol_pd_plan *pl, cudaStream_t s) {
     a.count = (unsigned *)(pl->link_block + LINK_COUNT_BELOW);
     a.error = (int *)(pl->link_block + LINK_ERROR);
     a.plane_vec = plane / 16;
+    a.timeout_ns = (unsigned long long)(ctx->link_timeout_ms > 0 ? ctx->link_timeout_ms : NSOL_LINK_TIMEOUT_MS) * 1000000ull;
     a.want = g;               // neighbours have published generation g - 1 (trivially true for g = 0)
     a.publish = g + 1u;
     pd_link_publish_kernel<<<32, 256, 0, s>>>(a);
@@ -972,7 +975,7 @@ static int pd_launch_bulk(const nsol_pd_plan *pl, const PdArgs<T> &a, dim3 grid,
 }
 
 // rows per CTA (3-D only) and planes per z-chunk
-static void pd_tiling(const nsol_ctx *ctx, const GridView &gv, int vecw, int *ty_out, int *zc_out) {
+static void pd_tiling(const nsol_ctx *ctx, const GridView &gv, int vecw, int *ty_out, int *zc_out, bool link = false) {
     const bool has_y = gv.comp_y >= 0;
     int ty = 1;
     if (has_y) {
@@ -988,6 +991,9 @@ static void pd_tiling(const nsol_ctx *ctx, const GridView &gv, int vecw, int *ty
         zc = 16;
         const long long tiles = (long long)((gv.nx + tile_w - 1) / tile_w) * (has_y ? (gv.ny + ty - 1) / ty : 1) * gv.batch;
         while (zc > 4 && tiles * ((gv.nz + zc - 1) / zc) < (long long)ctx->sm_count * 4) zc /= 2;
+        // thin z-slabs with the in-kernel halo exchange: keep the two boundary chunks (whose CTAs end
+        // with a system-scope fence) a small share of the slab; measured on a 64-plane slab: 8 planes
+        if (link && zc > 8 && gv.nz < 8 * zc) zc = 8;
     }
     if (zc > gv.nz) zc = gv.nz;
     if (zc < 1) zc = 1;
@@ -1024,6 +1030,7 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0) {
     a.link_error = nullptr;
     a.want = a.publish = 0;
     a.front_chunks = 0;
+    a.link_timeout_ns = (unsigned long long)(ctx->link_timeout_ms > 0 ? ctx->link_timeout_ms : NSOL_LINK_TIMEOUT_MS) * 1000000ull;
     if (pl->link_on) {
         if (part != 0) return nsol_fail(ctx, NSOL_ESTATE, "pd: the split iteration is not available with the in-kernel halo exchange");
         // this iteration consumes generation g = link_pub - 1 and publishes generation link_pub
@@ -1065,7 +1072,7 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0) {
     dim3 block, grid;
     size_t smem = 0;
     int ty = 1, zc = 1;
-    pd_tiling(ctx, gv, VECW, &ty, &zc);
+    pd_tiling(ctx, gv, VECW, &ty, &zc, pl->link_on);
     if (has_y) {
         block = dim3(32, ty, 1);
         smem = (size_t)(2 * (ty + 2) + 2 * (ty + 1)) * 32 * VECW * sizeof(T);
@@ -1160,7 +1167,7 @@ extern "C" int nsol_pd_plan_chunks(nsol_pd_plan *pl) {
     const GridView &gv = pl->gv;
     const int vecw = gv.dtype == NSOL_F32 ? 4 : 2;
     int ty, zc;
-    pd_tiling(pl->ctx, gv, (gv.nx % vecw) == 0 ? vecw : 1, &ty, &zc);
+    pd_tiling(pl->ctx, gv, (gv.nx % vecw) == 0 ? vecw : 1, &ty, &zc, pl->link_on);
     return (gv.nz + zc - 1) / zc;
 }
 

@@ -541,10 +541,11 @@ def test_zslab_link_emulation_matches_unsharded(dtype, nslabs, zc, variant):
 
 def test_zslab_link_timeout_is_reported():
     """A linked plan whose neighbour never publishes must not hang: the wait gives up after
-    NSOL_LINK_TIMEOUT_NS and get_x / link_status report it."""
+    link_timeout_ms (50 ms here, 5 s by default) and get_x / link_status report it."""
     import ctypes as C
     ctx = _lib.context()
     lib = ctx.lib
+    ctx.set_tuning("link_timeout_ms", 50)
     shape = (6, 4, 8)
     obs = np.random.RandomState(0).rand(*shape)
     alpha = np.array([0.05])
@@ -571,6 +572,7 @@ def test_zslab_link_timeout_is_reported():
         with pytest.raises(RuntimeError, match="timed out"):
             ctx.check(lib.nsol_pd_plan_link_status(plans[0], None))
     finally:
+        ctx.set_tuning("link_timeout_ms", 0)
         for h in plans:
             lib.nsol_pd_plan_destroy(h)
 
