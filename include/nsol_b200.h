@@ -293,6 +293,45 @@ int nsol_pd_deconv_run_host(nsol_lsmr_plan *plan, const nsol_pd_desc *pd, int it
                             double prox_scale, const double *b_host /* raw observation of the prox */,
                             const double *x0_host, double *x_host, double *iterates_host, nsol_stream s);
 
+/* ---- z-slab decomposition of the LSMR / ADMM path (one rank per GPU) -------------
+ * The plan's volume is the local slab [z_lo, z_hi) of a taller volume (numpy axis 0).  The library does
+ * no communication itself: the caller exchanges halo planes with the neighbouring ranks (NCCL send/recv)
+ * and all-reduces one double per reduction; this API exposes the buffers and cuts a solve into phases at
+ * every such point.  Blur halos are periodic (ring: the lower neighbour of rank 0 is the last rank,
+ * nsol/linear_operators.py:60-68 mode="wrap"); the gradient keeps its zero boundary at the global ends
+ * (has_below / has_above = 0 there, :98-106).
+ *   nsol_lsmr_plan_slab     switch a plan to slab mode and allocate its halo buffers
+ *   nsol_lsmr_slab_buffers  which = V | U0 | UZ | X: the local planes to send (first / last `planes`
+ *                           planes of the array; NULL if that direction is not needed) and the receive
+ *                           buffers (recv_lo <- lower neighbour's last planes, recv_hi <- upper
+ *                           neighbour's first planes)
+ *   nsol_lsmr_slab_arrays   b (N, solver units, written by the caller), x (N: start value in, result
+ *                           out) and the one-double reduction buffer to all-reduce (sum) after every
+ *                           phase that produces a sum of squares
+ *   nsol_lsmr_slab_phase    one phase (asynchronous).  Sequence of a solve with weight alpha
+ *                           (tikhonov_linear_solver.py:226-274 + scipy lsmr.py:239-479):
+ *       RHS(p0 = sqrt(alpha), i0 = 1: use the plan's b_reg, 0: b_reg = 0) . allreduce .
+ *       SCAL_INIT_BETA(p0 = sqrt(alpha), i0 = maxiter)
+ *       [exchange U0, UZ] ADJ_FIRST . allreduce . SCAL_INIT_ALPHA
+ *       maxiter x { [exchange V] FWD . allreduce . SCAL_BETA . [exchange U0, UZ] ADJ . allreduce .
+ *                   SCAL_ALPHA . UPDATE . allreduce . SCAL_TESTS }
+ *       CLIP(p0 = lo, p1 = hi)
+ *     ADMM (admm_linear_solver.py:165-253): [exchange X] ADMM_INIT, then per outer iteration a solve
+ *     with alpha = rho (b_reg = v - w is kept by the plan) followed by [exchange X] ADMM_SHRINK(p0 = alpha/rho).
+ *   nsol_lsmr_plan_status   iteration count / istop of the last solve (synchronises) */
+typedef enum { NSOL_SLAB_V = 0, NSOL_SLAB_U0 = 1, NSOL_SLAB_UZ = 2, NSOL_SLAB_X = 3 } nsol_slab_buffer;
+typedef enum {
+    NSOL_PH_RHS = 0, NSOL_PH_SCAL_INIT_BETA = 1, NSOL_PH_ADJ_FIRST = 2, NSOL_PH_SCAL_INIT_ALPHA = 3,
+    NSOL_PH_FWD = 4, NSOL_PH_SCAL_BETA = 5, NSOL_PH_ADJ = 6, NSOL_PH_SCAL_ALPHA = 7, NSOL_PH_UPDATE = 8,
+    NSOL_PH_SCAL_TESTS = 9, NSOL_PH_CLIP = 10, NSOL_PH_ADMM_INIT = 11, NSOL_PH_ADMM_SHRINK = 12
+} nsol_slab_phase;
+int nsol_lsmr_plan_slab(nsol_lsmr_plan *plan, int has_below, int has_above);
+int nsol_lsmr_slab_buffers(nsol_lsmr_plan *plan, int which, const void **send_first, const void **send_last,
+                           void **recv_lo, void **recv_hi, int *planes);
+int nsol_lsmr_slab_arrays(nsol_lsmr_plan *plan, void **b_dev, void **x_dev, double **ss_dev);
+int nsol_lsmr_slab_phase(nsol_lsmr_plan *plan, int phase, double p0, double p1, int i0, nsol_stream s);
+int nsol_lsmr_plan_status(nsol_lsmr_plan *plan, int *itn_out, int *istop_out, nsol_stream s);
+
 /* device-resident ADMM used by bench.py: arrays in solver units, plan dtype */
 int nsol_admm_run_dev(nsol_lsmr_plan *plan, double alpha, double rho, int iterations, int iter_max,
                       const void *b_dev, const void *x0_dev, void *x_dev, nsol_stream s);

@@ -21,6 +21,9 @@ ALG = {"ALG2": 0, "ALG2_AHMOD": 1, "ALG3": 2}
 B_GRAD, B_IDENTITY, B_NONE = 0, 1, 2
 PROX = {"TV_CONJ": 0, "HUBER_CONJ": 1, "TK1_CONJ": 2, "ELL1": 3, "ELL2": 4}
 A_BLUR, A_IDENTITY = 0, 1
+SLAB_V, SLAB_U0, SLAB_UZ, SLAB_X = 0, 1, 2, 3
+(PH_RHS, PH_SCAL_INIT_BETA, PH_ADJ_FIRST, PH_SCAL_INIT_ALPHA, PH_FWD, PH_SCAL_BETA, PH_ADJ, PH_SCAL_ALPHA, PH_UPDATE,
+ PH_SCAL_TESTS, PH_CLIP, PH_ADMM_INIT, PH_ADMM_SHRINK) = range(13)
 
 c_void_pp = C.POINTER(C.c_void_p)
 c_double_p = C.POINTER(C.c_double)
@@ -111,6 +114,11 @@ SIGNATURES = {
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsol_admm_run_dev": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsol_lsmr_plan_slab": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "nsol_lsmr_slab_buffers": (C.c_int, [C.c_void_p, C.c_int, c_void_pp, c_void_pp, c_void_pp, c_void_pp, C.POINTER(C.c_int)]),
+    "nsol_lsmr_slab_arrays": (C.c_int, [C.c_void_p, c_void_pp, c_void_pp, c_void_pp]),
+    "nsol_lsmr_slab_phase": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p]),
+    "nsol_lsmr_plan_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
     "nsol_admm_shrink": (C.c_int, [C.c_void_p, C.POINTER(Grid), C.c_void_p, C.c_void_p, C.c_double,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
 }

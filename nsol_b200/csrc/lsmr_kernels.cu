@@ -251,7 +251,18 @@ struct LsqGeom {
     int axis[3];           // 0 = x, 1 = y, 2 = z (kernel axis of component k)
     T w[3];
     int b_op;              // nsol_bop
+    // z-slab decomposition (one rank per GPU, nsol_lsmr_plan_slab): the volume is the local slab; planes
+    // below plane 0 / above plane nz-1 live in halo buffers filled by the caller's neighbour exchange
+    int slab;              // 0: whole volume (periodic wrap of the blur / zero boundary of the gradient in-kernel)
+    int grad_lo, grad_hi;  // a neighbour exists below / above for the (non-periodic) gradient stencils
+    int ghost;             // planes per halo buffer (>= blur radius along z, >= 1)
 };
+
+// plane offset of this thread's voxel inside its z-plane
+template <typename T>
+__device__ __forceinline__ long long lsq_plane_off(const LsqGeom<T> &g, const int idx[3]) {
+    return (long long)idx[1] * g.nx + idx[0];
+}
 
 template <typename T>
 __device__ __forceinline__ void lsq_decode(const LsqGeom<T> &g, long long r, int idx[3]) {
@@ -324,12 +335,25 @@ __device__ __forceinline__ T fast_blur_line(const TapArgs<T> &tp, const T *line,
 // one separable pass along kernel axis kaxis (0 = x, 1 = y, 2 = z)
 template <typename T>
 __global__ void __launch_bounds__(FAST_TH) fast_blur_pass_kernel(LsqGeom<T> g, const __grid_constant__ TapArgs<T> tp, int kaxis,
-                                                                 const T *__restrict__ in, T *__restrict__ out) {
+                                                                 const T *__restrict__ in, T *__restrict__ out,
+                                                                 const T *__restrict__ halo_lo, const T *__restrict__ halo_hi) {
     const int idx[3] = {(int)(blockIdx.x * FAST_TH + threadIdx.x), (int)blockIdx.y, (int)blockIdx.z};
     if (idx[0] >= g.nx) return;
     const long long i = ((long long)idx[2] * g.ny + idx[1]) * g.nx + idx[0];
     const long long st = kaxis == 0 ? 1 : (kaxis == 1 ? g.nx : (long long)g.nx * g.ny);
     const int ext = kaxis == 0 ? g.nx : (kaxis == 1 ? g.ny : g.nz);
+    if (kaxis == 2 && g.slab) {
+        // z-slab: the periodic neighbours are the halo planes (same tap order as fast_blur_line)
+        const long long po = lsq_plane_off(g, idx);
+        T acc = T(0);
+        for (int k = 0; k <= 2 * tp.r; ++k) {
+            const int q = idx[2] - (k - tp.r);
+            const T *src = q < 0 ? halo_lo + (long long)(q + g.ghost) * st : (q >= g.nz ? halo_hi + (long long)(q - g.nz) * st : in + (long long)q * st);
+            acc += tp.t[k] * src[po];
+        }
+        out[i] = acc;
+        return;
+    }
     out[i] = fast_blur_line(tp, in + (i - (long long)idx[kaxis] * st), idx[kaxis], ext, st);
 }
 
@@ -338,7 +362,7 @@ __global__ void __launch_bounds__(FAST_TH) fast_blur_pass_kernel(LsqGeom<T> g, c
 template <typename T>
 __global__ void __launch_bounds__(FAST_TH) fast_fwd_kernel(LsqGeom<T> g, const LsmrScalars *__restrict__ S, const __grid_constant__ TapArgs<T> tx,
                                                            const T *__restrict__ src, const T *__restrict__ vhat, T *__restrict__ u,
-                                                           double *__restrict__ part) {
+                                                           double *__restrict__ part, const T *__restrict__ v_hi) {
     if (S->done) return;
     const int idx[3] = {(int)(blockIdx.x * FAST_TH + threadIdx.x), (int)blockIdx.y, (int)blockIdx.z};
     double acc = 0.0;
@@ -352,7 +376,8 @@ __global__ void __launch_bounds__(FAST_TH) fast_fwd_kernel(LsqGeom<T> g, const L
         if (g.b_op == NSOL_B_GRAD) {
             const T vc = vhat[i] * inv_alpha;
             for (int k = 0; k < g.dim; ++k) {
-                const T hi = (idx[g.axis[k]] + 1 < g.extent[k]) ? vhat[i + g.stride[k]] * inv_alpha : T(0);
+                T hi = (idx[g.axis[k]] + 1 < g.extent[k]) ? vhat[i + g.stride[k]] * inv_alpha : T(0);
+                if (g.slab && g.grad_hi && g.axis[k] == 2 && idx[2] + 1 == g.nz) hi = v_hi[lsq_plane_off(g, idx)] * inv_alpha;
                 const T dk = g.w[k] * hi + (-g.w[k]) * vc;
                 T *uk = u + (long long)(1 + k) * g.n;
                 un = (uk[i] * inv_beta) * malpha + sa * dk;
@@ -374,7 +399,7 @@ __global__ void __launch_bounds__(FAST_TH) fast_fwd_kernel(LsqGeom<T> g, const L
 template <typename T>
 __global__ void __launch_bounds__(FAST_TH) fast_adj_kernel(LsqGeom<T> g, const LsmrScalars *__restrict__ S, const __grid_constant__ TapArgs<T> tx,
                                                            const T *__restrict__ src, const T *__restrict__ u, T *__restrict__ vhat,
-                                                           double *__restrict__ part, int first) {
+                                                           double *__restrict__ part, int first, const T *__restrict__ uz_lo) {
     if (S->done) return;
     const int idx[3] = {(int)(blockIdx.x * FAST_TH + threadIdx.x), (int)blockIdx.y, (int)blockIdx.z};
     double acc = 0.0;
@@ -386,7 +411,8 @@ __global__ void __launch_bounds__(FAST_TH) fast_adj_kernel(LsqGeom<T> g, const L
             T div = T(0);
             for (int k = 0; k < g.dim; ++k) {
                 const T *uk = u + (long long)(1 + k) * g.n;
-                const T lo = (idx[g.axis[k]] > 0) ? uk[i - g.stride[k]] * inv_beta : T(0);
+                T lo = (idx[g.axis[k]] > 0) ? uk[i - g.stride[k]] * inv_beta : T(0);
+                if (g.slab && g.grad_lo && g.axis[k] == 2 && idx[2] == 0) lo = uz_lo[lsq_plane_off(g, idx)] * inv_beta;
                 const T dk = g.w[k] * lo + (-g.w[k]) * (uk[i] * inv_beta);
                 div = (k == 0) ? dk : div + dk;
             }
@@ -447,7 +473,7 @@ __global__ void clip_kernel(long long n, const T *__restrict__ in, T *__restrict
 // optionally also breg_out = v - w  (the b_reg of the next Tikhonov solve, :222)
 template <typename T>
 __global__ void admm_shrink_kernel(LsqGeom<T> g, const T *__restrict__ x, const T *__restrict__ w_in, T ell, T *__restrict__ v_out,
-                                   T *__restrict__ w_out, T *__restrict__ breg_out) {
+                                   T *__restrict__ w_out, T *__restrict__ breg_out, const T *__restrict__ x_hi = nullptr, int plain = 0) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += (long long)gridDim.x * blockDim.x) {
         int idx[3];
         lsq_decode(g, i, idx);
@@ -455,11 +481,20 @@ __global__ void admm_shrink_kernel(LsqGeom<T> g, const T *__restrict__ x, const 
         T t[3];
         T ss = T(0);
         for (int k = 0; k < g.dim; ++k) {
-            const T hi = (idx[g.axis[k]] + 1 < g.extent[k]) ? x[i + g.stride[k]] : T(0);
+            T hi = (idx[g.axis[k]] + 1 < g.extent[k]) ? x[i + g.stride[k]] : T(0);
+            if (g.slab && g.grad_hi && g.axis[k] == 2 && idx[2] + 1 == g.nz) hi = x_hi[lsq_plane_off(g, idx)];
             T tk = g.w[k] * hi + (-g.w[k]) * xc;
             if (w_in) tk = tk + w_in[(long long)k * g.n + i];
             t[k] = tk;
             ss = (k == 0) ? tk * tk : ss + tk * tk;
+        }
+        if (plain) {      // v = B x, w = 0, b_reg = v  (start of the ADMM run, admm_linear_solver.py:171-172)
+            for (int k = 0; k < g.dim; ++k) {
+                v_out[(long long)k * g.n + i] = t[k];
+                w_out[(long long)k * g.n + i] = T(0);
+                breg_out[(long long)k * g.n + i] = t[k];
+            }
+            continue;
         }
         const T nrm = sqrt_t(ss);
         const bool on = nrm > ell;
@@ -498,6 +533,14 @@ struct nsol_lsmr_plan {
     double *part = nullptr;
     LsmrScalars *S = nullptr;
     size_t bytes = 0;
+    // z-slab mode (nsol_lsmr_plan_slab): halo planes filled by the caller's neighbour exchange
+    bool slab = false;
+    int grad_lo = 0, grad_hi = 0, ghost = 0;
+    void *halo_v_lo = nullptr, *halo_v_hi = nullptr;   // ghost planes of vhat (blur; the first hi plane also feeds grad)
+    void *halo_u_lo = nullptr, *halo_u_hi = nullptr;   // ghost planes of u block 0 (A^T = blur)
+    void *halo_uz_lo = nullptr;                        // last plane of the lower neighbour's u_z block (D_z^T)
+    void *halo_x_hi = nullptr;                         // first plane of the upper neighbour's x (ADMM: grad x)
+    double *ssbuf = nullptr;                           // [1] local / all-reduced sum of squares
     // cooperative single-launch path
     void *taps_dev = nullptr;      // blur taps of all axes in the plan dtype
     int tap_off[3] = {0, 0, 0};
@@ -509,7 +552,8 @@ extern "C" void nsol_lsmr_plan_destroy(nsol_lsmr_plan *pl) {
     if (!pl) return;
     if (pl->ctx) nsol_bind_device(pl->ctx);
     void *ptrs[] = {pl->u, pl->v, pl->h, pl->hbar, pl->x, pl->opbuf, pl->optmp, pl->breg, pl->admm_v, pl->admm_w,
-                    pl->bbuf, pl->xbuf, pl->stage, pl->part, pl->S, pl->taps_dev, pl->coop_part};
+                    pl->bbuf, pl->xbuf, pl->stage, pl->part, pl->S, pl->taps_dev, pl->coop_part,
+                    pl->halo_v_lo, pl->halo_v_hi, pl->halo_u_lo, pl->halo_u_hi, pl->halo_uz_lo, pl->halo_x_hi, pl->ssbuf};
     for (void *p : ptrs) cudaFree(p);
     if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
     delete pl;
@@ -580,6 +624,10 @@ static LsqGeom<T> make_geom(const nsol_lsmr_plan *pl) {
     g.nz = gv.nz;
     g.dim = gv.dim;
     g.b_op = pl->desc.b_op;
+    g.slab = pl->slab ? 1 : 0;
+    g.grad_lo = pl->grad_lo;
+    g.grad_hi = pl->grad_hi;
+    g.ghost = pl->ghost;
     for (int k = 0; k < 3; ++k) {
         g.stride[k] = 0;
         g.extent[k] = 1;
@@ -611,7 +659,8 @@ static TapArgs<T> lsq_taps(const nsol_lsmr_plan *pl, int ax) {
 // blur passes along every numpy axis except the last (x): in -> optmp (-> opbuf); *result is what the
 // consumer's fused x-pass reads (in itself for 1-D problems or A = identity)
 template <typename T>
-static int lsq_blur_front(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *in, const void **result, cudaStream_t s) {
+static int lsq_blur_front(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *in, const void **result, cudaStream_t s,
+                          const void *halo_lo = nullptr, const void *halo_hi = nullptr) {
     *result = in;
     if (pl->desc.a_op != NSOL_A_BLUR) return NSOL_OK;
     const dim3 grid((g.nx + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
@@ -619,7 +668,8 @@ static int lsq_blur_front(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *i
     for (int ax = 0; ax + 1 < g.dim; ++ax) {
         void *dst = (src == pl->optmp) ? pl->opbuf : pl->optmp;
         const int kaxis = (g.dim == 3 && ax == 1) ? 1 : 2;
-        fast_blur_pass_kernel<T><<<grid, FAST_TH, 0, s>>>(g, lsq_taps<T>(pl, ax), kaxis, (const T *)src, (T *)dst);
+        fast_blur_pass_kernel<T><<<grid, FAST_TH, 0, s>>>(g, lsq_taps<T>(pl, ax), kaxis, (const T *)src, (T *)dst, (const T *)halo_lo,
+                                                          (const T *)halo_hi);
         NSOL_LAUNCH_CHECK(pl->ctx);
         src = dst;
     }
@@ -653,7 +703,7 @@ static int lsmr_solve_t(nsol_lsmr_plan *pl, double alpha, const void *b_dev, con
     const TapArgs<T> tx = lsq_taps<T>(pl, g.dim - 1);
     const void *op = nullptr;
     NSOL_CHECK(lsq_blur_front<T>(pl, ge, u, &op, s));       // A^T = A (same mask, periodic)
-    fast_adj_kernel<T><<<rgrid, FAST_TH, 0, s>>>(ge, pl->S, tx, (const T *)op, u, v, part, 1);
+    fast_adj_kernel<T><<<rgrid, FAST_TH, 0, s>>>(ge, pl->S, tx, (const T *)op, u, v, part, 1, (const T *)nullptr);
     NSOL_LAUNCH_CHECK(ctx);
     lsmr_scalar_init_alpha<<<1, 1024, 0, s>>>(pl->S, part, rparts);
     NSOL_LAUNCH_CHECK(ctx);
@@ -661,12 +711,12 @@ static int lsmr_solve_t(nsol_lsmr_plan *pl, double alpha, const void *b_dev, con
     NSOL_LAUNCH_CHECK(ctx);
     for (int it = 0; it < maxiter; ++it) {
         NSOL_CHECK(lsq_blur_front<T>(pl, ge, v, &op, s));
-        fast_fwd_kernel<T><<<rgrid, FAST_TH, 0, s>>>(ge, pl->S, tx, (const T *)op, v, u, part);
+        fast_fwd_kernel<T><<<rgrid, FAST_TH, 0, s>>>(ge, pl->S, tx, (const T *)op, v, u, part, (const T *)nullptr);
         NSOL_LAUNCH_CHECK(ctx);
         lsmr_scalar_beta<<<1, 1024, 0, s>>>(pl->S, part, rparts);
         NSOL_LAUNCH_CHECK(ctx);
         NSOL_CHECK(lsq_blur_front<T>(pl, ge, u, &op, s));
-        fast_adj_kernel<T><<<rgrid, FAST_TH, 0, s>>>(ge, pl->S, tx, (const T *)op, u, v, part, 0);
+        fast_adj_kernel<T><<<rgrid, FAST_TH, 0, s>>>(ge, pl->S, tx, (const T *)op, u, v, part, 0, (const T *)nullptr);
         NSOL_LAUNCH_CHECK(ctx);
         lsmr_scalar_alpha<<<1, 1024, 0, s>>>(pl->S, part, rparts);
         NSOL_LAUNCH_CHECK(ctx);
@@ -767,6 +817,7 @@ static int lsmr_solve_coop(nsol_lsmr_plan *pl, double alpha, const void *b_dev, 
 // kernel per phase + CUDA-graph replay is faster (40 vs 44 us) because more threads are in flight than a
 // co-resident grid allows.
 static int lsmr_use_coop(nsol_lsmr_plan *pl) {
+    if (pl->slab) return nsol_fail(pl->ctx, NSOL_ESTATE, "lsmr: a z-slab plan is driven phase by phase (nsol_lsmr_slab_phase)");
     if (pl->ctx->lsmr_path == 1) return 0;
     if (pl->ctx->lsmr_path == 0 && pl->gv.n > (1ll << 17)) return 0;
     int rc = pl->gv.dtype == NSOL_F32 ? coop_prepare<float>(pl) : coop_prepare<double>(pl);
@@ -1007,6 +1058,197 @@ extern "C" int nsol_admm_shrink(nsol_ctx *ctx, const nsol_grid *grid, const void
         admm_shrink_kernel<double><<<nb, LSMR_THREADS, 0, (cudaStream_t)s>>>(make_geom<double>(&tmp), (const double *)x_dev, (const double *)w_in_dev,
                                                                             ell, (double *)v_dev, (double *)w_dev, (double *)nullptr);
     NSOL_LAUNCH_CHECK(ctx);
+    return NSOL_OK;
+}
+
+// ---------------------------------------------------------------------------
+// z-slab decomposition of the LSMR / ADMM path (one rank per GPU)
+// ---------------------------------------------------------------------------
+// The plan's volume is the local slab [z_lo, z_hi) of a taller volume.  Communication is the caller's
+// (nsol_b200/distributed.py: NCCL send/recv between neighbours + all-reduce of one double); this side
+// exposes the planes to send, the halo buffers to receive into, and the solve cut into phases at every
+// point where a neighbour exchange or a global sum is needed.  Blur halos are periodic (ring: rank 0's
+// lower neighbour is the last rank); gradient stencils keep the zero boundary at the global ends.
+__global__ void lsmr_reduce_ss_kernel(const LsmrScalars *__restrict__ S, const double *__restrict__ part, int count, double *__restrict__ ss,
+                                      int always) {
+    if (!always && S->done) return;
+    const double v = reduce_partials(part, count);
+    if (threadIdx.x == 0) ss[0] = v;
+}
+
+extern "C" int nsol_lsmr_plan_slab(nsol_lsmr_plan *pl, int has_below, int has_above) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    const GridView &gv = pl->gv;
+    if (gv.dim < 2) return nsol_fail(ctx, NSOL_EINVAL, "lsmr slab: needs dim >= 2");
+    NSOL_CHECK(nsol_bind_device(ctx));
+    int ghost = 1;
+    if (pl->desc.a_op == NSOL_A_BLUR && pl->desc.radius[0] > ghost) ghost = pl->desc.radius[0];   // numpy axis 0 = slab axis
+    if (gv.nz < ghost) return nsol_fail(ctx, NSOL_EINVAL, "lsmr slab: %d local planes but the blur needs %d halo planes", gv.nz, ghost);
+    if (!pl->slab) {
+        const size_t plane = (size_t)gv.nx * gv.ny * pl->esz;
+        void **bufs[] = {&pl->halo_v_lo, &pl->halo_v_hi, &pl->halo_u_lo, &pl->halo_u_hi, &pl->halo_uz_lo, &pl->halo_x_hi};
+        const size_t sizes[] = {plane * ghost, plane * ghost, plane * ghost, plane * ghost, plane, plane};
+        for (int i = 0; i < 6; ++i) {
+            NSOL_CUDA(ctx, cudaMalloc(bufs[i], sizes[i]));
+            NSOL_CUDA(ctx, cudaMemset(*bufs[i], 0, sizes[i]));
+            pl->bytes += sizes[i];
+        }
+        NSOL_CUDA(ctx, cudaMalloc((void **)&pl->ssbuf, sizeof(double)));
+    }
+    pl->slab = true;
+    pl->ghost = ghost;
+    pl->grad_lo = has_below ? 1 : 0;
+    pl->grad_hi = has_above ? 1 : 0;
+    return NSOL_OK;
+}
+
+extern "C" int nsol_lsmr_slab_buffers(nsol_lsmr_plan *pl, int which, const void **send_first, const void **send_last, void **recv_lo,
+                                      void **recv_hi, int *planes) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    if (!pl->slab) return nsol_fail(ctx, NSOL_ESTATE, "lsmr slab: call nsol_lsmr_plan_slab first");
+    const GridView &gv = pl->gv;
+    const size_t plane = (size_t)gv.nx * gv.ny * pl->esz;
+    const void *sf = nullptr, *sl = nullptr;
+    void *rl = nullptr, *rh = nullptr;
+    int np = 0;
+    auto first_last = [&](const char *base, int count) {
+        sf = base;
+        sl = base + (size_t)(gv.nz - count) * plane;
+        np = count;
+    };
+    switch (which) {
+    case NSOL_SLAB_V:       // vhat: ghost planes both ways (periodic blur); hi plane 0 also feeds grad
+        first_last((const char *)pl->v, pl->ghost);
+        rl = pl->halo_v_lo;
+        rh = pl->halo_v_hi;
+        break;
+    case NSOL_SLAB_U0:      // u block 0: ghost planes both ways (A^T)
+        first_last((const char *)pl->u, pl->ghost);
+        rl = pl->halo_u_lo;
+        rh = pl->halo_u_hi;
+        break;
+    case NSOL_SLAB_UZ:      // u block of D_z (the last B block): my last plane -> upper neighbour's lo buffer
+        first_last((const char *)pl->u + (size_t)gv.dim * gv.n * pl->esz, 1);
+        sf = nullptr;
+        rl = pl->halo_uz_lo;
+        break;
+    case NSOL_SLAB_X:       // x: my first plane -> lower neighbour's hi buffer
+        first_last((const char *)pl->xbuf, 1);
+        sl = nullptr;
+        rh = pl->halo_x_hi;
+        break;
+    default:
+        return nsol_fail(ctx, NSOL_EINVAL, "lsmr slab: unknown buffer kind %d", which);
+    }
+    if (send_first) *send_first = sf;
+    if (send_last) *send_last = sl;
+    if (recv_lo) *recv_lo = rl;
+    if (recv_hi) *recv_hi = rh;
+    if (planes) *planes = np;
+    return NSOL_OK;
+}
+
+extern "C" int nsol_lsmr_slab_arrays(nsol_lsmr_plan *pl, void **b_dev, void **x_dev, double **ss_dev) {
+    if (!pl) return NSOL_EINVAL;
+    if (!pl->slab) return nsol_fail(pl->ctx, NSOL_ESTATE, "lsmr slab: call nsol_lsmr_plan_slab first");
+    if (b_dev) *b_dev = pl->bbuf;
+    if (x_dev) *x_dev = pl->xbuf;
+    if (ss_dev) *ss_dev = pl->ssbuf;
+    return NSOL_OK;
+}
+
+template <typename T>
+static int lsmr_slab_phase_t(nsol_lsmr_plan *pl, int phase, double p0, double p1, int i0, cudaStream_t s) {
+    nsol_ctx *ctx = pl->ctx;
+    const LsqGeom<T> g = make_geom<T>(pl);
+    const int nb = pl->nblocks, th = LSMR_THREADS;
+    T *u = (T *)pl->u, *v = (T *)pl->v, *h = (T *)pl->h, *hbar = (T *)pl->hbar, *x = (T *)pl->x;
+    double *part = pl->part;
+    if (g.ny > 65535 || g.nz > 65535) return nsol_fail(ctx, NSOL_EINVAL, "lsmr slab: more than 65535 rows along y or z are not supported");
+    const dim3 rgrid((g.nx + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
+    const int rparts = pl->row_blocks;
+    const TapArgs<T> tx = lsq_taps<T>(pl, g.dim - 1);
+    const void *op = nullptr;
+    switch (phase) {
+    case NSOL_PH_RHS:            // u = [b; sqrt_alpha b_reg]; p0 = sqrt_alpha, i0 = 0: b_reg = 0  -> ss
+        lsmr_rhs_kernel<T><<<nb, th, 0, s>>>(g, pl->rows_b, (const T *)pl->bbuf, i0 ? (const T *)pl->breg : (const T *)nullptr, p0, u, part);
+        NSOL_LAUNCH_CHECK(ctx);
+        lsmr_reduce_ss_kernel<<<1, 1024, 0, s>>>(pl->S, part, nb, pl->ssbuf, 1);
+        break;
+    case NSOL_PH_SCAL_INIT_BETA:  // p0 = sqrt_alpha, i0 = maxiter
+        lsmr_scalar_init_beta<<<1, 32, 0, s>>>(pl->S, pl->ssbuf, 1, p0, i0);
+        break;
+    case NSOL_PH_ADJ_FIRST:
+    case NSOL_PH_ADJ:            // needs the U0 and UZ halos -> ss
+        NSOL_CHECK(lsq_blur_front<T>(pl, g, u, &op, s, pl->halo_u_lo, pl->halo_u_hi));
+        fast_adj_kernel<T><<<rgrid, FAST_TH, 0, s>>>(g, pl->S, tx, (const T *)op, u, v, part, phase == NSOL_PH_ADJ_FIRST ? 1 : 0,
+                                                      (const T *)pl->halo_uz_lo);
+        NSOL_LAUNCH_CHECK(ctx);
+        lsmr_reduce_ss_kernel<<<1, 1024, 0, s>>>(pl->S, part, rparts, pl->ssbuf, phase == NSOL_PH_ADJ_FIRST ? 1 : 0);
+        break;
+    case NSOL_PH_SCAL_INIT_ALPHA:
+        lsmr_scalar_init_alpha<<<1, 32, 0, s>>>(pl->S, pl->ssbuf, 1);
+        NSOL_LAUNCH_CHECK(ctx);
+        lsmr_init_vectors_kernel<T><<<nb, th, 0, s>>>(g.n, pl->S, v, h, hbar, x);
+        break;
+    case NSOL_PH_FWD:            // needs the V halos -> ss
+        NSOL_CHECK(lsq_blur_front<T>(pl, g, v, &op, s, pl->halo_v_lo, pl->halo_v_hi));
+        fast_fwd_kernel<T><<<rgrid, FAST_TH, 0, s>>>(g, pl->S, tx, (const T *)op, v, u, part, (const T *)pl->halo_v_hi);
+        NSOL_LAUNCH_CHECK(ctx);
+        lsmr_reduce_ss_kernel<<<1, 1024, 0, s>>>(pl->S, part, rparts, pl->ssbuf, 0);
+        break;
+    case NSOL_PH_SCAL_BETA:
+        lsmr_scalar_beta<<<1, 32, 0, s>>>(pl->S, pl->ssbuf, 1);
+        break;
+    case NSOL_PH_SCAL_ALPHA:
+        lsmr_scalar_alpha<<<1, 32, 0, s>>>(pl->S, pl->ssbuf, 1);
+        break;
+    case NSOL_PH_UPDATE:         // -> ss
+        lsmr_update_kernel<T><<<nb, th, 0, s>>>(g.n, pl->S, v, h, hbar, x, part);
+        NSOL_LAUNCH_CHECK(ctx);
+        lsmr_reduce_ss_kernel<<<1, 1024, 0, s>>>(pl->S, part, nb, pl->ssbuf, 0);
+        break;
+    case NSOL_PH_SCAL_TESTS:
+        lsmr_scalar_tests<<<1, 32, 0, s>>>(pl->S, pl->ssbuf, 1);
+        break;
+    case NSOL_PH_CLIP:           // xbuf = clip(x, p0, p1)
+        clip_kernel<T><<<nb, th, 0, s>>>(g.n, x, (T *)pl->xbuf, p0, p1);
+        break;
+    case NSOL_PH_ADMM_INIT:      // needs the X halo: v = grad(xbuf), w = 0, b_reg = v
+        admm_shrink_kernel<T><<<nb, th, 0, s>>>(g, (const T *)pl->xbuf, (const T *)nullptr, T(0), (T *)pl->admm_v, (T *)pl->admm_w,
+                                                (T *)pl->breg, (const T *)pl->halo_x_hi, 1);
+        break;
+    case NSOL_PH_ADMM_SHRINK:    // needs the X halo: p0 = ell = alpha / rho
+        admm_shrink_kernel<T><<<nb, th, 0, s>>>(g, (const T *)pl->xbuf, (const T *)pl->admm_w, (T)p0, (T *)pl->admm_v, (T *)pl->admm_w,
+                                                (T *)pl->breg, (const T *)pl->halo_x_hi, 0);
+        break;
+    default:
+        return nsol_fail(ctx, NSOL_EINVAL, "lsmr slab: unknown phase %d", phase);
+    }
+    NSOL_LAUNCH_CHECK(ctx);
+    return NSOL_OK;
+}
+
+extern "C" int nsol_lsmr_slab_phase(nsol_lsmr_plan *pl, int phase, double p0, double p1, int i0, nsol_stream s) {
+    if (!pl) return NSOL_EINVAL;
+    if (!pl->slab) return nsol_fail(pl->ctx, NSOL_ESTATE, "lsmr slab: call nsol_lsmr_plan_slab first");
+    NSOL_CHECK(nsol_bind_device(pl->ctx));
+    if (pl->gv.dtype == NSOL_F32) return lsmr_slab_phase_t<float>(pl, phase, p0, p1, i0, (cudaStream_t)s);
+    return lsmr_slab_phase_t<double>(pl, phase, p0, p1, i0, (cudaStream_t)s);
+}
+
+// current LSMR state of a plan (synchronises): iteration count and stop flag
+extern "C" int nsol_lsmr_plan_status(nsol_lsmr_plan *pl, int *itn_out, int *istop_out, nsol_stream s) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    NSOL_CHECK(nsol_bind_device(ctx));
+    LsmrScalars hS;
+    NSOL_CUDA(ctx, cudaMemcpyAsync(&hS, pl->S, sizeof(hS), cudaMemcpyDeviceToHost, (cudaStream_t)s));
+    NSOL_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)s));
+    if (itn_out) *itn_out = hS.itn;
+    if (istop_out) *istop_out = hS.istop;
     return NSOL_OK;
 }
 

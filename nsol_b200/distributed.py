@@ -225,3 +225,199 @@ class SlabPrimalDual(object):
                 dist.barrier()
             self.ctx.lib.nsol_pd_plan_destroy(self.plan)
             self.plan = None
+
+
+# ---------------------------------------------------------------------------------------------
+# z-slab decomposition of the ADMM / LSMR path
+# ---------------------------------------------------------------------------------------------
+def slab_admm_program(iterations, iter_max, alpha, rho, lo=0.0, hi=float("inf")):
+    """The ADMM TV-L2 run (nsol/admm_linear_solver.py:165-253; inner solve nsol/tikhonov_linear_solver.py:
+    226-274 + scipy lsmr.py:239-479) as a flat list of steps for one slab:
+        ("exchange", [buffer kinds])      neighbour exchange of halo planes (before the next phase)
+        ("phase", id, p0, p1, i0)         nsol_lsmr_slab_phase
+        ("allreduce",)                    sum of the one-double reduction buffer over all slabs
+    Every rank executes the same list in lockstep; the device-side ``done`` flag of LSMR turns the
+    remaining phases of a solve into no-ops, so the list never depends on data."""
+    from nsol_b200 import _lib as L
+    sa = float(np.sqrt(rho))
+    steps = [("exchange", [L.SLAB_X]), ("phase", L.PH_ADMM_INIT, 0.0, 0.0, 0)]
+    for _ in range(int(iterations)):
+        steps += [("phase", L.PH_RHS, sa, 0.0, 1), ("allreduce",), ("phase", L.PH_SCAL_INIT_BETA, sa, 0.0, int(iter_max)),
+                  ("exchange", [L.SLAB_U0, L.SLAB_UZ]), ("phase", L.PH_ADJ_FIRST, 0.0, 0.0, 0), ("allreduce",),
+                  ("phase", L.PH_SCAL_INIT_ALPHA, 0.0, 0.0, 0)]
+        for _ in range(int(iter_max)):
+            steps += [("exchange", [L.SLAB_V]), ("phase", L.PH_FWD, 0.0, 0.0, 0), ("allreduce",), ("phase", L.PH_SCAL_BETA, 0.0, 0.0, 0),
+                      ("exchange", [L.SLAB_U0, L.SLAB_UZ]), ("phase", L.PH_ADJ, 0.0, 0.0, 0), ("allreduce",),
+                      ("phase", L.PH_SCAL_ALPHA, 0.0, 0.0, 0),
+                      ("phase", L.PH_UPDATE, 0.0, 0.0, 0), ("allreduce",), ("phase", L.PH_SCAL_TESTS, 0.0, 0.0, 0)]
+        steps += [("phase", L.PH_CLIP, float(lo), float(hi), 0),
+                  ("exchange", [L.SLAB_X]), ("phase", L.PH_ADMM_SHRINK, float(alpha) / float(rho), 0.0, 0)]
+    return steps
+
+
+class SlabLsq(object):
+    """One rank's slab of the stacked least-squares problem: an ``nsol_lsmr_plan`` in slab mode plus
+    views of its exchange buffers."""
+
+    def __init__(self, ctx, info, dtype, rank, world):
+        """info: {"shape": local slab shape, "spacing", "a_kind": "conv" | "identity", "a_op" (taps), "b_kind": "grad"}"""
+        import ctypes as C
+        from nsol_b200 import _lib as L
+        from nsol_b200.linear_solver import LsmrPlan
+        self.C, self.L, self.ctx = C, L, ctx
+        self.rank, self.world = rank, world
+        self.plan = LsmrPlan(info, dtype)
+        self.handle = self.plan.handle
+        self.dcode = L.dtype_code(dtype)
+        self.np_dtype = L.np_dtype(self.dcode)
+        self.shape = tuple(int(s) for s in info["shape"])
+        self.n = int(np.prod(self.shape))
+        self.plane = self.n // self.shape[0]
+        ctx.check(ctx.lib.nsol_lsmr_plan_slab(self.handle, 1 if rank > 0 else 0, 1 if rank < world - 1 else 0))
+        b, x, ss = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        ctx.check(ctx.lib.nsol_lsmr_slab_arrays(self.handle, C.byref(b), C.byref(x), C.byref(ss)))
+        self.b_ptr, self.x_ptr, self.ss_ptr = b, x, ss
+        self.buffers = {}
+        for kind in (L.SLAB_V, L.SLAB_U0, L.SLAB_UZ, L.SLAB_X):
+            sf, sl, rl, rh, npl = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int()
+            ctx.check(ctx.lib.nsol_lsmr_slab_buffers(self.handle, kind, C.byref(sf), C.byref(sl), C.byref(rl), C.byref(rh), C.byref(npl)))
+            self.buffers[kind] = {"send_first": sf.value, "send_last": sl.value, "recv_lo": rl.value, "recv_hi": rh.value,
+                                  "numel": npl.value * self.plane}
+
+    def upload(self, b_scaled, x0_scaled, stream=None):
+        """b and the start value, float64 host arrays already in solver units (divided by x_scale)."""
+        ctx, L = self.ctx, self.L
+        for ptr, arr in ((self.b_ptr, b_scaled), (self.x_ptr, x0_scaled)):
+            arr = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
+            if arr.size != self.n:
+                raise ValueError("slab array has %d values, the slab %d" % (arr.size, self.n))
+            stage = ctx.device_alloc(arr.nbytes).upload(arr, stream)
+            ctx.check(ctx.lib.nsol_scale_convert(ctx.handle, self.n, L.F64, stage.ptr, self.dcode, ptr, 1.0, 0, stream))
+            ctx.sync(stream)
+            stage.free()
+
+    def download(self, x_scale=1.0, stream=None):
+        ctx, L = self.ctx, self.L
+        stage = ctx.device_alloc(self.n * 8)
+        ctx.check(ctx.lib.nsol_scale_convert(ctx.handle, self.n, self.dcode, self.x_ptr, L.F64, stage.ptr, float(x_scale), 0, stream))
+        out = stage.download((self.n,), np.float64, stream)
+        stage.free()
+        return out
+
+    def phase(self, pid, p0, p1, i0, stream=None):
+        self.ctx.check(self.ctx.lib.nsol_lsmr_slab_phase(self.handle, pid, p0, p1, i0, stream))
+
+    def close(self):
+        self.plan.close()
+
+
+def run_slab_admm_emulated(slabs, steps, stream=None):
+    """Execute a step program for ALL slabs inside one process on one GPU (tests): the exchange is a
+    set of device copies, the all-reduce a host-side sum in rank order."""
+    import ctypes as C
+    ctx = slabs[0].ctx
+    L = slabs[0].L
+    world = len(slabs)
+    esz = 4 if slabs[0].dcode == L.F32 else 8
+    for st in steps:
+        if st[0] == "phase":
+            for sl in slabs:
+                sl.phase(st[1], st[2], st[3], st[4], stream)
+        elif st[0] == "exchange":
+            for kind in st[1]:
+                periodic = kind in (L.SLAB_V, L.SLAB_U0)
+                for r, sl in enumerate(slabs):
+                    buf = sl.buffers[kind]
+                    nbytes = buf["numel"] * esz
+                    up, dn = r + 1, r - 1
+                    if periodic:
+                        up, dn = up % world, dn % world
+                    if buf["send_last"] and 0 <= up < world and slabs[up].buffers[kind]["recv_lo"]:
+                        ctx.check(ctx.lib.nsol_memcpy_d2d(ctx.handle, slabs[up].buffers[kind]["recv_lo"], buf["send_last"], nbytes, stream))
+                    if buf["send_first"] and 0 <= dn < world and slabs[dn].buffers[kind]["recv_hi"]:
+                        ctx.check(ctx.lib.nsol_memcpy_d2d(ctx.handle, slabs[dn].buffers[kind]["recv_hi"], buf["send_first"], nbytes, stream))
+        else:
+            vals = np.zeros(world)
+            for r, sl in enumerate(slabs):
+                one = np.zeros(1)
+                ctx.check(ctx.lib.nsol_memcpy_d2h(ctx.handle, one.ctypes.data, sl.ss_ptr, 8, stream))
+                ctx.sync(stream)
+                vals[r] = one[0]
+            total = np.array([np.sum(vals)])      # rank order, like a tree-less all-reduce
+            for sl in slabs:
+                ctx.check(ctx.lib.nsol_memcpy_h2d(ctx.handle, sl.ss_ptr, total.ctypes.data, 8, stream))
+                ctx.sync(stream)
+
+
+def exchange_slab_halos(dist, group, rank, world, items):
+    """One grouped neighbour exchange.  items: [(views, periodic)], views = dict of 1-D tensors
+    (or None) "send_first", "send_last" (this rank's first / last planes), "recv_lo" (<- the lower
+    neighbour's last planes), "recv_hi" (<- the upper neighbour's first planes).  periodic: the slabs
+    form a ring (blur, mode="wrap"); otherwise the global ends have no neighbour (gradient)."""
+    ops = []
+    for v, periodic in items:
+        up, dn = rank + 1, rank - 1
+        if periodic:
+            up, dn = up % world, dn % world
+        has_up, has_dn = 0 <= up < world, 0 <= dn < world
+        if world == 1:
+            if periodic:       # the slab is its own ring neighbour
+                v["recv_lo"].copy_(v["send_last"])
+                v["recv_hi"].copy_(v["send_first"])
+            continue
+        # order matters when both neighbours are the same rank (world == 2, ring): the k-th send to a
+        # peer pairs with the peer's k-th receive from this rank
+        if v["send_first"] is not None and has_dn:
+            ops.append(dist.P2POp(dist.isend, v["send_first"], dn, group))
+        if v["send_last"] is not None and has_up:
+            ops.append(dist.P2POp(dist.isend, v["send_last"], up, group))
+        if v["recv_hi"] is not None and has_up and v["send_first"] is not None:
+            ops.append(dist.P2POp(dist.irecv, v["recv_hi"], up, group))
+        if v["recv_lo"] is not None and has_dn and v["send_last"] is not None:
+            ops.append(dist.P2POp(dist.irecv, v["recv_lo"], dn, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+class SlabADMM(object):
+    """ADMM TV-L2 deconvolution of one tall volume, z-slab sharded over the ranks of a
+    ``torch.distributed`` group (NCCL): kernel-radius halo planes of the blur travel on a ring
+    (periodic boundary), one-plane halos of the gradient between neighbours, and three scalar
+    all-reduces per LSMR iteration (||u||^2, ||v||^2, ||x||^2) -- SURVEY.md 8e.  All ranks call ``run``
+    together."""
+
+    def __init__(self, ctx, info, dtype, rank, world, device, group=None):
+        import torch
+        self.torch = torch
+        self.group = group
+        self.device = device
+        self.slab = SlabLsq(ctx, info, dtype, rank, world)
+        sl = self.slab
+        self.ss = tensor_from_ptr(sl.ss_ptr.value, 1, np.float64, device)
+        self.views = {}
+        for kind, buf in sl.buffers.items():
+            self.views[kind] = {k: (tensor_from_ptr(buf[k], buf["numel"], sl.np_dtype, device) if buf[k] else None)
+                                for k in ("send_first", "send_last", "recv_lo", "recv_hi")}
+
+    def _exchange(self, kinds):
+        L = self.slab.L
+        exchange_slab_halos(self.torch.distributed, self.group, self.slab.rank, self.slab.world,
+                            [(self.views[k], k in (L.SLAB_V, L.SLAB_U0)) for k in kinds])
+
+    def run(self, b_scaled, x0_scaled, alpha, rho, iterations, iter_max, stream=None):
+        """b, x0: this rank's slab in solver units (float64 host arrays).  Returns the slab of the result
+        (solver units, float64)."""
+        dist = self.torch.distributed
+        self.slab.upload(b_scaled, x0_scaled, stream)
+        for st in slab_admm_program(iterations, iter_max, alpha, rho):
+            if st[0] == "phase":
+                self.slab.phase(st[1], st[2], st[3], st[4], stream)
+            elif st[0] == "exchange":
+                self._exchange(st[1])
+            elif self.slab.world > 1:
+                dist.all_reduce(self.ss, group=self.group)
+        return self.slab.download(1.0, stream)
+
+    def close(self):
+        self.slab.close()

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import nsol_oracle as orc
-from nsol_b200.distributed import HaloExchanger, partition_round_robin, slab_bounds
+from nsol_b200.distributed import HaloExchanger, exchange_slab_halos, partition_round_robin, slab_bounds
 
 
 def test_slab_bounds_and_partition():
@@ -138,3 +138,73 @@ def test_parameter_study_fans_out_over_ranks(tmp_path):
     assert sorted(ra.files) == sorted(rb.files)
     for k in ra.files:
         assert np.array_equal(ra[k], rb[k])
+
+
+def _halo_worker(rank, world, port, ghost, plane):
+    """ADMM / LSMR slab exchange (SlabADMM._exchange): every rank fills tensors whose values encode
+    (owner rank, plane, element) and checks what arrives in its receive buffers."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nz = ghost + 2
+
+    def planes(owner, kind, lo, hi):
+        z = np.arange(lo, hi)[:, None]
+        e = np.arange(plane)[None, :]
+        return (1000.0 * kind + 100.0 * owner + z + e / 1000.0).reshape(-1)
+
+    def views(kind, count, first, last, lo, hi):
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+        return {"send_first": t(planes(rank, kind, 0, count)) if first else None,
+                "send_last": t(planes(rank, kind, nz - count, nz)) if last else None,
+                "recv_lo": torch.full((count * plane,), -1.0, dtype=torch.float64) if lo else None,
+                "recv_hi": torch.full((count * plane,), -1.0, dtype=torch.float64) if hi else None}
+
+    v = views(0, ghost, True, True, True, True)      # vhat: both ways, ring
+    u0 = views(1, ghost, True, True, True, True)     # u block 0: both ways, ring
+    uz = views(2, 1, False, True, True, False)       # u_z: last plane -> upper neighbour
+    x = views(3, 1, True, False, False, True)        # x: first plane -> lower neighbour
+    exchange_slab_halos(dist, None, rank, world, [(v, True)])
+    exchange_slab_halos(dist, None, rank, world, [(u0, True), (uz, False)])
+    exchange_slab_halos(dist, None, rank, world, [(x, False)])
+    up, dn = (rank + 1) % world, (rank - 1) % world
+    for kind, vw in ((0, v), (1, u0)):
+        assert np.array_equal(vw["recv_lo"].numpy(), planes(dn, kind, nz - ghost, nz)), (rank, kind, "lo")
+        assert np.array_equal(vw["recv_hi"].numpy(), planes(up, kind, 0, ghost)), (rank, kind, "hi")
+    if rank > 0:
+        assert np.array_equal(uz["recv_lo"].numpy(), planes(rank - 1, 2, nz - 1, nz))
+    else:
+        assert np.all(uz["recv_lo"].numpy() == -1.0)          # global bottom: untouched (zero boundary in the kernel)
+    if rank < world - 1:
+        assert np.array_equal(x["recv_hi"].numpy(), planes(rank + 1, 3, 0, 1))
+    else:
+        assert np.all(x["recv_hi"].numpy() == -1.0)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_admm_slab_halo_exchange_protocol(world):
+    """Ring (periodic blur) and neighbour (gradient) exchanges of the z-slab ADMM driver deliver the
+    right planes, including world == 2 where both ring neighbours are the same rank."""
+    import torch.multiprocessing as mp
+    mp.spawn(_halo_worker, args=(world, _free_port(), 3, 5), nprocs=world, join=True)
+
+
+def test_slab_admm_program_shape():
+    from nsol_b200 import _lib as L
+    from nsol_b200.distributed import slab_admm_program
+    steps = slab_admm_program(iterations=2, iter_max=3, alpha=0.01, rho=0.1)
+    assert steps[0] == ("exchange", [L.SLAB_X]) and steps[1][1] == L.PH_ADMM_INIT
+    assert sum(1 for s in steps if s[0] == "allreduce") == 2 * (2 + 3 * 3)
+    phases = [s[1] for s in steps if s[0] == "phase"]
+    assert phases.count(L.PH_FWD) == 6 and phases.count(L.PH_ADMM_SHRINK) == 2 and phases.count(L.PH_CLIP) == 2
+    # every FWD is preceded by an exchange of vhat, every ADJ by an exchange of both u halos
+    for i, s in enumerate(steps):
+        if s[0] == "phase" and s[1] == L.PH_FWD:
+            assert steps[i - 1] == ("exchange", [L.SLAB_V])
+        if s[0] == "phase" and s[1] in (L.PH_ADJ, L.PH_ADJ_FIRST):
+            assert steps[i - 1] == ("exchange", [L.SLAB_U0, L.SLAB_UZ])
+        if s[0] == "phase" and s[1] == L.PH_ADMM_SHRINK:
+            assert abs(s[2] - 0.1) < 1e-15

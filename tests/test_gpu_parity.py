@@ -324,6 +324,45 @@ def test_admm_config3_lena512(golden):
     assert rel_max(s.get_x(), golden("lsmr", "admm_c3_lena512")) < 1e-4
 
 
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("shape,nslabs", [((40, 36), 1), ((40, 36), 2), ((41, 36), 3), ((18, 10, 20), 2), ((22, 6, 20), 3)])
+def test_admm_zslab_emulation_matches_unsharded(shape, nslabs, dtype):
+    """the ADMM / LSMR path z-slab sharded.  S slabs are driven phase by phase in one process
+    (nsol_lsmr_slab_phase); the halo exchange (ring for the periodic blur, neighbours for the gradient) is
+    done with device copies and the scalar all-reduce on the host -- the same step program
+    (distributed.slab_admm_program) the NCCL driver SlabADMM executes on S GPUs.  Must agree with the
+    unsharded solver (only the order of the norm reductions differs)."""
+    from nsol_b200.distributed import SlabLsq, slab_admm_program, run_slab_admm_emulated, slab_bounds
+    from nsol_b200.linear_solver import probe_least_squares
+    rng = np.random.RandomState(17)
+    obs = rng.rand(*shape) * 200 + 20
+    var = [1.0] * len(shape)
+    alpha, rho, iterations, iter_max = 0.02, 0.2, 4, 6
+    xs = float(obs.max())
+    A, A_adj, D, D_adj = deconv_callables(shape, var)
+    ref_solver = admm.ADMMLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=D, B_adj=D_adj, x0=obs.flatten(), dimension=len(shape),
+                                       alpha=alpha, rho=rho, iterations=iterations, iter_max=iter_max, x_scale=xs, dtype=dtype)
+    ref_solver.run()
+    ref = ref_solver.get_x()
+    info = probe_least_squares(A, A_adj, D, D_adj, obs.size)
+    ctx = _lib.context()
+    slabs = []
+    try:
+        for r in range(nslabs):
+            z_lo, z_hi = slab_bounds(shape[0], r, nslabs)
+            sl = SlabLsq(ctx, dict(info, shape=(z_hi - z_lo,) + tuple(shape[1:])), dtype, r, nslabs)
+            part = np.ascontiguousarray(obs[z_lo:z_hi]).reshape(-1) / xs
+            sl.upload(part, part)
+            slabs.append(sl)
+        run_slab_admm_emulated(slabs, slab_admm_program(iterations, iter_max, alpha, rho))
+        out = np.concatenate([sl.download(xs) for sl in slabs])
+    finally:
+        for sl in slabs:
+            sl.close()
+    tol = 1e-9 if dtype == "float64" else 2e-3
+    assert rel_max(out, ref) < tol, rel_max(out, ref)
+
+
 @pytest.mark.parametrize("name", ["tk_1d_TK0", "tk_1d_TK1", "tk_2d_TK0", "tk_2d_TK1", "tk_3d_TK0", "tk_3d_TK1"])
 def test_tikhonov_vs_reference(golden, name):
     meta = golden.manifest["lsmr"][name]
