@@ -19,8 +19,8 @@ from abc import ABCMeta, abstractmethod
 
 import numpy as np
 
-from nsol_b200.parameter_study import (ParameterStudy, get_time_stamp, is_float, write_array_to_file,
-                                       write_to_file)
+from nsol_b200.parameter_study import (ParameterStudy, get_time_stamp, is_float, npz_members, write_array_to_file,
+                                       write_npz_members, write_to_file)
 from nsol_b200.reader_parameter_study import ReaderParameterStudy
 
 MAX_SWEEP_BATCH = 32
@@ -91,6 +91,12 @@ class SolverParameterStudy(ParameterStudy):
         rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
         mine = list(range(rank, len(points), world))
         results = self._run_points(keys, points, mine)       # {index: (params, measures, time, x_last)}
+        # the float16 reconstruction of every run is deflated on the rank that computed it (thread pool)
+        import os
+        threads = max(1, (os.cpu_count() or 1) // world)
+        packed = npz_members({str(i + offset): np.array(results[i][3], dtype=np.float16) for i in sorted(results)}, threads)
+        for i, member in zip(sorted(results), packed):
+            results[i] = results[i][:3] + (member,)
         if dist:
             gathered = [None] * world if rank == 0 else None
             dist.gather_object(results, gathered, dst=0)
@@ -100,14 +106,15 @@ class SolverParameterStudy(ParameterStudy):
             results = {}
             for part in gathered:
                 results.update(part)
+        members = npz_members(dic_x)          # reconstruction_info / the runs of the study being appended to
         for i in range(len(points)):
-            params, measures, ctime, x_last = results[i]
+            params, measures, ctime, member = results[i]
             for measure, values in measures.items():
                 self._add_to_file_measures(measure, np.asarray(values).reshape(1, -1))
             self._add_to_file_computational_time(ctime)
             self._add_to_file_parameters(params)
-            dic_x[str(i + offset)] = np.array(x_last, dtype=np.float16)
-        self._write_to_file_reconstructions(dic_x)
+            members.append(member)
+        self._write_to_file_reconstructions(members)
 
     def _apply_point(self, keys, vals):
         params = {}
@@ -192,8 +199,18 @@ class SolverParameterStudy(ParameterStudy):
     def _add_to_file_computational_time(self, computational_time):
         write_to_file(self._get_path_to_file_computational_time(), str(computational_time) + "\n", "a")
 
-    def _write_to_file_reconstructions(self, dic):
-        np.savez_compressed(self._get_path_to_file_reconstructions(), **dic)
+    def _write_to_file_reconstructions(self, members):
+        """Same file as the reference's np.savez_compressed(path, **dic) (nsol/solver_parameter_study.py:320-321),
+        assembled from members that were deflated in parallel."""
+        path = self._get_path_to_file_reconstructions()
+        if not write_npz_members(path, members):
+            # archive needs zip64: let numpy write it (single-threaded)
+            import io
+            import zlib
+            dic = {}
+            for name, _, _, comp in members:
+                dic[name[:-4]] = np.lib.format.read_array(io.BytesIO(zlib.decompress(comp, -15)), allow_pickle=False)
+            np.savez_compressed(path, **dic)
 
     def _header_from_keys(self, keys):
         header = "## " + self._name

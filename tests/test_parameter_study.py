@@ -139,3 +139,21 @@ def test_primal_dual_study_batched_sweep_matches_sequential(tmp_path, golden):
     ref = orc.primal_dual_denoise(obs.reshape(-1), obs.shape, reg="TV", data="L2", alpha=alphas[3], L2=8, iterations=25,
                                   x_scale=float(obs.max()))
     assert np.array_equal(out["batched"]["3"], ref.astype(np.float16))
+
+
+def test_parallel_npz_writer_is_read_like_savez_compressed(tmp_path):
+    """The reconstructions file (nsol/solver_parameter_study.py:320-321: np.savez_compressed) assembled from
+    members deflated in parallel: np.load / zipfile see the same arrays as in numpy's own file."""
+    import zipfile
+    from nsol_b200.parameter_study import npz_members, write_npz_members
+    rng = np.random.RandomState(0)
+    dic = {"shape": (33, 20), "0": (rng.rand(660) * 255).astype(np.float16), "1": rng.rand(3, 4), "empty": np.zeros(0)}
+    mine, theirs = str(tmp_path / "mine.npz"), str(tmp_path / "numpy.npz")
+    assert write_npz_members(mine, npz_members(dic, threads=3))
+    np.savez_compressed(theirs, **dic)
+    a, b = np.load(mine), np.load(theirs)
+    assert a.files == b.files == list(dic.keys())
+    for k in dic:
+        assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k])
+    assert zipfile.ZipFile(mine).testzip() is None
+    assert all(i.compress_type == zipfile.ZIP_DEFLATED for i in zipfile.ZipFile(mine).infolist())

@@ -77,7 +77,27 @@ def main():
         st.run()
         return solver
 
+    # where the wall clock goes: time inside run_sweep (H2D, iterations, D2H) and inside the npz writer
+    import nsol_b200.solver_parameter_study as sps
+    spent = {"run_sweep": 0.0, "savez": 0.0}
+    orig_sweep, orig_savez = pd.PrimalDualSolver.run_sweep, sps.npz_members
+
+    def timed_sweep(self, alphas_):
+        t = time.perf_counter()
+        out = orig_sweep(self, alphas_)
+        spent["run_sweep"] += time.perf_counter() - t
+        return out
+
+    def timed_savez(*a, **k):
+        t = time.perf_counter()
+        out = orig_savez(*a, **k)
+        spent["savez"] += time.perf_counter() - t
+        return out
+
+    pd.PrimalDualSolver.run_sweep = timed_sweep
+    sps.npz_members = timed_savez
     study("TV")      # warm-up: plan allocation, page-locked pools
+    spent["run_sweep"] = spent["savez"] = 0.0
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -93,6 +113,7 @@ def main():
         line = {"workload": "C5: %d-point alpha sweep x {TV, Huber, TK1} PD on %dx%d, %d iterations" % (args.points, shape[0], shape[1], args.iterations),
                 "n_gpus": world, "dtype": args.dtype, "seconds": dt, "runs": runs, "runs_per_s": runs / dt,
                 "voxel_iters_per_s": runs * obs.size * args.iterations / dt,
+                "seconds_in_run_sweep_rank0": spent["run_sweep"], "seconds_in_npz_compression_rank0": spent["savez"],
                 "note": "wall clock of three PrimalDualSolverParameterStudy.run() calls incl. result gather and npz/txt writers"}
         # parity sample: three points solved one at a time
         worst = 0.0
