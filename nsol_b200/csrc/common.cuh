@@ -19,7 +19,7 @@ struct nsol_ctx {
     int pd_ty = 0;
     int pd_variant = 0;
     int lsmr_blocks = 0;
-    int lsmr_path = 0;      // 0 auto (cooperative single launch), 1 multi-kernel, 2 cooperative
+    int lsmr_path = 0;      // 0 auto, 1 multi-kernel (vector kernels where they apply), 2 cooperative single launch, 3 multi-kernel with the generic kernels
     int link_timeout_ms = 0; // in-kernel halo exchange: give up waiting for a neighbour after this long (0 = 5000)
     std::string err;
 };

@@ -656,6 +656,8 @@ static TapArgs<T> lsq_taps(const nsol_lsmr_plan *pl, int ax) {
     return t;
 }
 
+#include "lsmr_fastv.cuh"
+
 // blur passes along every numpy axis except the last (x): in -> optmp (-> opbuf); *result is what the
 // consumer's fused x-pass reads (in itself for 1-D problems or A = identity)
 template <typename T>
@@ -668,12 +670,86 @@ static int lsq_blur_front(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *i
     for (int ax = 0; ax + 1 < g.dim; ++ax) {
         void *dst = (src == pl->optmp) ? pl->opbuf : pl->optmp;
         const int kaxis = (g.dim == 3 && ax == 1) ? 1 : 2;
-        fast_blur_pass_kernel<T><<<grid, FAST_TH, 0, s>>>(g, lsq_taps<T>(pl, ax), kaxis, (const T *)src, (T *)dst, (const T *)halo_lo,
-                                                          (const T *)halo_hi);
+        if (fastv_ok(pl)) {
+            constexpr int VEC = FastvCfg<T>::VEC;
+            const dim3 vgrid((g.nx / VEC + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
+            const FastvGeom<T> fg = make_fastv_geom<T>(g);
+            FASTV_SWITCH_R(lsq_radius(pl, ax), (fastv_blur_pass_kernel<T, R, VEC><<<vgrid, FAST_TH, 0, s>>>(
+                                                   fg, lsq_taps_r<T, R>(pl, ax), kaxis, (const T *)src, (T *)dst, (const T *)halo_lo,
+                                                   (const T *)halo_hi)));
+        } else {
+            fast_blur_pass_kernel<T><<<grid, FAST_TH, 0, s>>>(g, lsq_taps<T>(pl, ax), kaxis, (const T *)src, (T *)dst, (const T *)halo_lo,
+                                                              (const T *)halo_hi);
+        }
         NSOL_LAUNCH_CHECK(pl->ctx);
         src = dst;
     }
     *result = src;
+    return NSOL_OK;
+}
+
+// forward / adjoint / update phases: vector kernels when they apply, the generic ones otherwise.
+// *nparts = number of partial sums written to pl->part.
+template <typename T>
+static int lsq_launch_fwd(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *op, const void *v_hi, cudaStream_t s, int *nparts) {
+    T *u = (T *)pl->u;
+    const T *v = (const T *)pl->v;
+    const int ax = g.dim - 1;
+    if (fastv_ok(pl)) {
+        constexpr int VEC = FastvCfg<T>::VEC;
+        const dim3 vgrid((g.nx / VEC + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
+        const FastvGeom<T> fg = make_fastv_geom<T>(g);
+        const int r = lsq_radius(pl, ax) < 0 ? 0 : lsq_radius(pl, ax);
+        FASTV_SWITCH_R(r, (fastv_fwd_kernel<T, R, VEC><<<vgrid, FAST_TH, 0, s>>>(fg, pl->S, lsq_taps_r<T, R>(pl, lsq_radius(pl, ax) < 0 ? -1 : ax),
+                                                                                  (const T *)op, v, u, pl->part, (const T *)v_hi)));
+        *nparts = (int)(vgrid.x * vgrid.y * vgrid.z);
+    } else {
+        const dim3 rgrid((g.nx + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
+        fast_fwd_kernel<T><<<rgrid, FAST_TH, 0, s>>>(g, pl->S, lsq_taps<T>(pl, ax), (const T *)op, v, u, pl->part, (const T *)v_hi);
+        *nparts = pl->row_blocks;
+    }
+    NSOL_LAUNCH_CHECK(pl->ctx);
+    return NSOL_OK;
+}
+
+template <typename T>
+static int lsq_launch_adj(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *op, int first, const void *uz_lo, cudaStream_t s, int *nparts) {
+    const T *u = (const T *)pl->u;
+    T *v = (T *)pl->v;
+    const int ax = g.dim - 1;
+    if (fastv_ok(pl)) {
+        constexpr int VEC = FastvCfg<T>::VEC;
+        const dim3 vgrid((g.nx / VEC + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
+        const FastvGeom<T> fg = make_fastv_geom<T>(g);
+        const int r = lsq_radius(pl, ax) < 0 ? 0 : lsq_radius(pl, ax);
+        FASTV_SWITCH_R(r, (fastv_adj_kernel<T, R, VEC><<<vgrid, FAST_TH, 0, s>>>(fg, pl->S, lsq_taps_r<T, R>(pl, lsq_radius(pl, ax) < 0 ? -1 : ax),
+                                                                                  (const T *)op, u, v, pl->part, first, (const T *)uz_lo)));
+        *nparts = (int)(vgrid.x * vgrid.y * vgrid.z);
+    } else {
+        const dim3 rgrid((g.nx + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
+        fast_adj_kernel<T><<<rgrid, FAST_TH, 0, s>>>(g, pl->S, lsq_taps<T>(pl, ax), (const T *)op, u, v, pl->part, first, (const T *)uz_lo);
+        *nparts = pl->row_blocks;
+    }
+    NSOL_LAUNCH_CHECK(pl->ctx);
+    return NSOL_OK;
+}
+
+template <typename T>
+static int lsq_launch_update(nsol_lsmr_plan *pl, const LsqGeom<T> &g, cudaStream_t s, int *nparts) {
+    T *v = (T *)pl->v, *h = (T *)pl->h, *hbar = (T *)pl->hbar, *x = (T *)pl->x;
+    constexpr int VEC = FastvCfg<T>::VEC;
+    if (fastv_ok(pl) && g.n % VEC == 0) {
+        const long long nvec = g.n / VEC;
+        long long want = (nvec + 2 * LSMR_THREADS - 1) / (2 * LSMR_THREADS);
+        const long long cap = (long long)pl->ctx->sm_count * 8;
+        const int nb = (int)(want < cap ? (want > 0 ? want : 1) : cap);
+        fastv_update_kernel<T, VEC><<<nb, LSMR_THREADS, 0, s>>>(nvec, pl->S, v, h, hbar, x, pl->part);
+        *nparts = nb;
+    } else {
+        lsmr_update_kernel<T><<<pl->nblocks, LSMR_THREADS, 0, s>>>(g.n, pl->S, v, h, hbar, x, pl->part);
+        *nparts = pl->nblocks;
+    }
+    NSOL_LAUNCH_CHECK(pl->ctx);
     return NSOL_OK;
 }
 
@@ -698,31 +774,25 @@ static int lsmr_solve_t(nsol_lsmr_plan *pl, double alpha, const void *b_dev, con
     NSOL_LAUNCH_CHECK(ctx);
     if (g.ny > 65535 || g.nz > 65535)
         return nsol_fail(ctx, NSOL_EINVAL, "lsmr (multi-kernel path): more than 65535 rows along y or z are not supported");
-    const dim3 rgrid((g.nx + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
-    const int rparts = pl->row_blocks;
-    const TapArgs<T> tx = lsq_taps<T>(pl, g.dim - 1);
+    int rparts = 0;
     const void *op = nullptr;
     NSOL_CHECK(lsq_blur_front<T>(pl, ge, u, &op, s));       // A^T = A (same mask, periodic)
-    fast_adj_kernel<T><<<rgrid, FAST_TH, 0, s>>>(ge, pl->S, tx, (const T *)op, u, v, part, 1, (const T *)nullptr);
-    NSOL_LAUNCH_CHECK(ctx);
+    NSOL_CHECK(lsq_launch_adj<T>(pl, ge, op, 1, nullptr, s, &rparts));
     lsmr_scalar_init_alpha<<<1, 1024, 0, s>>>(pl->S, part, rparts);
     NSOL_LAUNCH_CHECK(ctx);
     lsmr_init_vectors_kernel<T><<<nb, th, 0, s>>>(g.n, pl->S, v, h, hbar, x);
     NSOL_LAUNCH_CHECK(ctx);
     for (int it = 0; it < maxiter; ++it) {
         NSOL_CHECK(lsq_blur_front<T>(pl, ge, v, &op, s));
-        fast_fwd_kernel<T><<<rgrid, FAST_TH, 0, s>>>(ge, pl->S, tx, (const T *)op, v, u, part, (const T *)nullptr);
-        NSOL_LAUNCH_CHECK(ctx);
+        NSOL_CHECK(lsq_launch_fwd<T>(pl, ge, op, nullptr, s, &rparts));
         lsmr_scalar_beta<<<1, 1024, 0, s>>>(pl->S, part, rparts);
         NSOL_LAUNCH_CHECK(ctx);
         NSOL_CHECK(lsq_blur_front<T>(pl, ge, u, &op, s));
-        fast_adj_kernel<T><<<rgrid, FAST_TH, 0, s>>>(ge, pl->S, tx, (const T *)op, u, v, part, 0, (const T *)nullptr);
-        NSOL_LAUNCH_CHECK(ctx);
+        NSOL_CHECK(lsq_launch_adj<T>(pl, ge, op, 0, nullptr, s, &rparts));
         lsmr_scalar_alpha<<<1, 1024, 0, s>>>(pl->S, part, rparts);
         NSOL_LAUNCH_CHECK(ctx);
-        lsmr_update_kernel<T><<<nb, th, 0, s>>>(g.n, pl->S, v, h, hbar, x, part);
-        NSOL_LAUNCH_CHECK(ctx);
-        lsmr_scalar_tests<<<1, th, 0, s>>>(pl->S, part, nb);
+        NSOL_CHECK(lsq_launch_update<T>(pl, ge, s, &rparts));
+        lsmr_scalar_tests<<<1, 1024, 0, s>>>(pl->S, part, rparts);
         NSOL_LAUNCH_CHECK(ctx);
     }
     clip_kernel<T><<<nb, th, 0, s>>>(g.n, x, (T *)x_out, lo, hi);
@@ -818,7 +888,7 @@ static int lsmr_solve_coop(nsol_lsmr_plan *pl, double alpha, const void *b_dev, 
 // co-resident grid allows.
 static int lsmr_use_coop(nsol_lsmr_plan *pl) {
     if (pl->slab) return nsol_fail(pl->ctx, NSOL_ESTATE, "lsmr: a z-slab plan is driven phase by phase (nsol_lsmr_slab_phase)");
-    if (pl->ctx->lsmr_path == 1) return 0;
+    if (pl->ctx->lsmr_path == 1 || pl->ctx->lsmr_path == 3) return 0;
     if (pl->ctx->lsmr_path == 0 && pl->gv.n > (1ll << 17)) return 0;
     int rc = pl->gv.dtype == NSOL_F32 ? coop_prepare<float>(pl) : coop_prepare<double>(pl);
     if (rc != NSOL_OK) return rc;
@@ -1167,9 +1237,7 @@ static int lsmr_slab_phase_t(nsol_lsmr_plan *pl, int phase, double p0, double p1
     T *u = (T *)pl->u, *v = (T *)pl->v, *h = (T *)pl->h, *hbar = (T *)pl->hbar, *x = (T *)pl->x;
     double *part = pl->part;
     if (g.ny > 65535 || g.nz > 65535) return nsol_fail(ctx, NSOL_EINVAL, "lsmr slab: more than 65535 rows along y or z are not supported");
-    const dim3 rgrid((g.nx + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
-    const int rparts = pl->row_blocks;
-    const TapArgs<T> tx = lsq_taps<T>(pl, g.dim - 1);
+    int rparts = 0;
     const void *op = nullptr;
     switch (phase) {
     case NSOL_PH_RHS:            // u = [b; sqrt_alpha b_reg]; p0 = sqrt_alpha, i0 = 0: b_reg = 0  -> ss
@@ -1183,9 +1251,7 @@ static int lsmr_slab_phase_t(nsol_lsmr_plan *pl, int phase, double p0, double p1
     case NSOL_PH_ADJ_FIRST:
     case NSOL_PH_ADJ:            // needs the U0 and UZ halos -> ss
         NSOL_CHECK(lsq_blur_front<T>(pl, g, u, &op, s, pl->halo_u_lo, pl->halo_u_hi));
-        fast_adj_kernel<T><<<rgrid, FAST_TH, 0, s>>>(g, pl->S, tx, (const T *)op, u, v, part, phase == NSOL_PH_ADJ_FIRST ? 1 : 0,
-                                                      (const T *)pl->halo_uz_lo);
-        NSOL_LAUNCH_CHECK(ctx);
+        NSOL_CHECK(lsq_launch_adj<T>(pl, g, op, phase == NSOL_PH_ADJ_FIRST ? 1 : 0, pl->halo_uz_lo, s, &rparts));
         lsmr_reduce_ss_kernel<<<1, 1024, 0, s>>>(pl->S, part, rparts, pl->ssbuf, phase == NSOL_PH_ADJ_FIRST ? 1 : 0);
         break;
     case NSOL_PH_SCAL_INIT_ALPHA:
@@ -1195,8 +1261,7 @@ static int lsmr_slab_phase_t(nsol_lsmr_plan *pl, int phase, double p0, double p1
         break;
     case NSOL_PH_FWD:            // needs the V halos -> ss
         NSOL_CHECK(lsq_blur_front<T>(pl, g, v, &op, s, pl->halo_v_lo, pl->halo_v_hi));
-        fast_fwd_kernel<T><<<rgrid, FAST_TH, 0, s>>>(g, pl->S, tx, (const T *)op, v, u, part, (const T *)pl->halo_v_hi);
-        NSOL_LAUNCH_CHECK(ctx);
+        NSOL_CHECK(lsq_launch_fwd<T>(pl, g, op, pl->halo_v_hi, s, &rparts));
         lsmr_reduce_ss_kernel<<<1, 1024, 0, s>>>(pl->S, part, rparts, pl->ssbuf, 0);
         break;
     case NSOL_PH_SCAL_BETA:
@@ -1206,9 +1271,8 @@ static int lsmr_slab_phase_t(nsol_lsmr_plan *pl, int phase, double p0, double p1
         lsmr_scalar_alpha<<<1, 32, 0, s>>>(pl->S, pl->ssbuf, 1);
         break;
     case NSOL_PH_UPDATE:         // -> ss
-        lsmr_update_kernel<T><<<nb, th, 0, s>>>(g.n, pl->S, v, h, hbar, x, part);
-        NSOL_LAUNCH_CHECK(ctx);
-        lsmr_reduce_ss_kernel<<<1, 1024, 0, s>>>(pl->S, part, nb, pl->ssbuf, 0);
+        NSOL_CHECK(lsq_launch_update<T>(pl, g, s, &rparts));
+        lsmr_reduce_ss_kernel<<<1, 1024, 0, s>>>(pl->S, part, rparts, pl->ssbuf, 0);
         break;
     case NSOL_PH_SCAL_TESTS:
         lsmr_scalar_tests<<<1, 32, 0, s>>>(pl->S, pl->ssbuf, 1);

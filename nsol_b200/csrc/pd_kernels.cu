@@ -942,11 +942,13 @@ static void pd_launch_rd(const nsol_pd_plan *pl, const PdArgs<T> &a, dim3 grid, 
 // bulk-async (TMA) staged variant: 3-D, vector path only
 template <typename T, int VEC, int R, int D, bool LINK, bool UNIT>
 static int pd_launch_bulk_one(const nsol_pd_plan *pl, const PdArgs<T> &a, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
-    static size_t configured = 0;
-    if (smem > configured) {
+    // the opt-in is per device and per kernel instantiation; remember the largest size set on each device
+    static size_t configured[64] = {0};
+    const int dev = pl->ctx->device & 63;
+    if (smem > configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(pd_iter_bulk_kernel<T, VEC, R, D, LINK, UNIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return nsol_fail(pl->ctx, NSOL_ECUDA, "pd bulk: smem opt-in %zu -> %s", smem, cudaGetErrorString(e));
-        configured = smem;
+        configured[dev] = smem;
     }
     pd_iter_bulk_kernel<T, VEC, R, D, LINK, UNIT><<<grid, block, smem, s>>>(a);
     return NSOL_OK;

@@ -669,7 +669,7 @@ def test_standalone_prox_linear_least_squares(golden):
     assert rel_max(got, ref) < F64_LSMR_TOL
 
 
-@pytest.mark.parametrize("path", [1, 2])
+@pytest.mark.parametrize("path", [1, 2, 3])
 def test_lsmr_multi_kernel_and_cooperative_paths(golden, path):
     """Both LSMR implementations (1 = one kernel per phase + CUDA graph for ADMM, 2 = a single
     cooperative launch with grid.sync between phases) against the reference fixtures."""
@@ -712,6 +712,42 @@ def test_lsmr_multi_kernel_and_cooperative_paths(golden, path):
             assert rel_max(a, b) < F64_LSMR_TOL
     finally:
         ctx.set_tuning("lsmr_path", 0)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("shape,var", [((64, 48), [1.0, 1.0]), ((40, 36), [0.4, 3.5]), ((12, 16, 20), [1.0, 0.5, 1.7]),
+                                        ((130,), 1.0), ((24, 8), [1.0, 1.0])])
+def test_lsmr_vector_kernels_match_generic_kernels(shape, var, dtype):
+    """The radius-specialised 128-bit kernels (csrc/lsmr_fastv.cuh; lsmr_path 1) against the generic row-mapped
+    kernels (lsmr_path 3) and the oracle: anisotropic masks (different radius per axis, incl. radius 1 and 6),
+    rows as short as the mask allows, ADMM (B = grad) and Tikhonov TK0 (B = identity)."""
+    rng = np.random.RandomState(23)
+    obs = rng.rand(*shape) * 200 + 10
+    xs = float(obs.max())
+    A, A_adj, D, D_adj = deconv_callables(shape, var)
+    ctx = _lib.context()
+    out = {}
+    try:
+        for path in (1, 3):
+            ctx.set_tuning("lsmr_path", path)
+            s = admm.ADMMLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=D, B_adj=D_adj, x0=obs.flatten(), dimension=len(shape),
+                                      alpha=0.02, rho=0.3, iterations=3, iter_max=7, x_scale=xs, dtype=dtype)
+            s.run()
+            ident = lambda x: x.flatten()
+            t = tk.TikhonovLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=ident, B_adj=ident, x0=obs.flatten(), alpha=0.05,
+                                        iter_max=8, x_scale=xs, dtype=dtype)
+            t.run()
+            out[path] = (s.get_x(), t.get_x())
+    finally:
+        ctx.set_tuning("lsmr_path", 0)
+    tol = 1e-11 if dtype == "float64" else 5e-4
+    assert rel_max(out[1][0], out[3][0]) < tol and rel_max(out[1][1], out[3][1]) < tol
+    if dtype == "float64":
+        cov = var if len(shape) == 1 else np.diag(var)
+        Ao, Ao_adj, Do, Do_adj = orc.deconvolution_operators(shape, cov)
+        ref = orc.admm_tv(Ao, Ao_adj, Do, Do_adj, obs.reshape(-1), obs.reshape(-1), len(shape), alpha=0.02, rho=0.3, iterations=3,
+                          iter_max=7, x_scale=xs)
+        assert rel_max(out[1][0], ref) < F64_LSMR_TOL
 
 
 # ------------------------------------------------------------------ measures on the device (SURVEY 8f row 3)
