@@ -58,6 +58,9 @@ static FastvGeom<T> make_fastv_geom(const LsqGeom<T> &g) {
 }
 
 // ---- separable pass along y (kaxis 1) or z (kaxis 2), periodic; z-slab: halo planes instead of the wrap ----
+// Every thread produces FASTV_ROWS consecutive outputs of its line from one sweep over FASTV_ROWS + 2R inputs
+// (all loads issued up front): (ROWS + 2R) / ROWS loads per output instead of 2R + 1.
+#define FASTV_ROWS 8
 template <typename T, int R, int VEC>
 __global__ void __launch_bounds__(FAST_TH) fastv_blur_pass_kernel(FastvGeom<T> g, TapsR<T, R> tp, int kaxis, const T *__restrict__ in,
                                                                   T *__restrict__ out, const T *__restrict__ halo_lo,
@@ -65,47 +68,68 @@ __global__ void __launch_bounds__(FAST_TH) fastv_blur_pass_kernel(FastvGeom<T> g
     using V = Vec<T, VEC>;
     const int x = (int)(blockIdx.x * FAST_TH + threadIdx.x) * VEC;
     if (x >= g.nx) return;
-    const int y = (int)blockIdx.y, z = (int)blockIdx.z;
+    // the grid axis of the blurred direction counts groups of FASTV_ROWS positions
+    const int y = kaxis == 1 ? 0 : (int)blockIdx.y, z = kaxis == 2 ? 0 : (int)blockIdx.z;
+    const int pos0 = (kaxis == 1 ? (int)blockIdx.y : (int)blockIdx.z) * FASTV_ROWS;
     const long long plane = (long long)g.nx * g.ny;
     const long long st = kaxis == 1 ? (long long)g.nx : plane;
-    const int pos = kaxis == 1 ? y : z;
     const int ext = kaxis == 1 ? g.ny : g.nz;
-    const long long i = (long long)z * plane + (long long)y * g.nx + x;
-    const T *base = in + (i - (long long)pos * st);           // element at pos = 0 of this line
+    const long long line = (long long)z * plane + (long long)y * g.nx + x;    // element at position 0 of this line
+    const T *base = in + line;
     const long long po = (long long)y * g.nx + x;            // offset inside a plane (z-slab halos)
     const bool halo = kaxis == 2 && g.slab;
-    V acc = vec_zero<T, VEC>();
+    V val[FASTV_ROWS + 2 * R];
 #pragma unroll
-    for (int k = 0; k <= 2 * R; ++k) {
-        int q = pos - (k - R);
+    for (int j = 0; j < FASTV_ROWS + 2 * R; ++j) {
+        int q = pos0 - R + j;                                // input position (before the wrap)
         const T *src;
         if (halo) {
-            src = q < 0 ? halo_lo + (long long)(q + g.ghost) * st + po : (q >= g.nz ? halo_hi + (long long)(q - g.nz) * st + po : base + (long long)q * st);
+            src = q < 0 ? halo_lo + (long long)(q + g.ghost) * st + po
+                        : (q >= g.nz ? halo_hi + (long long)(q - g.nz < g.ghost ? q - g.nz : g.ghost - 1) * st + po : base + (long long)q * st);
         } else {
             q += q < 0 ? ext : 0;
-            q -= q >= ext ? ext : 0;
+            if (q >= ext) {
+                q -= ext;
+                if (q >= ext) q %= ext;                      // only inputs of a partial group's unused outputs get here
+            }
             src = base + (long long)q * st;
         }
-        const V val = vec_load<T, VEC>(src);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) acc.v[v] += tp.t[k] * val.v[v];
+        val[j] = vec_load<T, VEC>(src);
     }
-    vec_store<T, VEC>(out + i, acc);
+#pragma unroll
+    for (int o = 0; o < FASTV_ROWS; ++o) {
+        if (pos0 + o < ext) {
+            V acc = vec_zero<T, VEC>();
+#pragma unroll
+            for (int k = 0; k <= 2 * R; ++k) {               // input position (pos0 + o) - (k - R): same tap order as fast_blur_line
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc.v[v] += tp.t[k] * val[o + 2 * R - k].v[v];
+            }
+            vec_store<T, VEC>(out + line + (long long)(pos0 + o) * st, acc);
+        }
+    }
 }
 
-// x-blur of VEC consecutive outputs of one row (periodic): reads VEC + 2R inputs; tap order as fast_blur_line
+// x-blur of VEC consecutive outputs of one row (periodic): reads the aligned 128-bit vectors covering
+// [x - R, x + VEC - 1 + R]; tap order as fast_blur_line
 template <typename T, int R, int VEC>
 __device__ __forceinline__ Vec<T, VEC> fastv_blur_x(const TapsR<T, R> &tp, const T *__restrict__ row, int x, int nx) {
     Vec<T, VEC> out;
     if (R == 0) return vec_load<T, VEC>(row + x);
-    T val[VEC + 2 * R];
-    if (x - R >= 0 && x + VEC - 1 + R < nx) {
+    constexpr int A = (R + VEC - 1) / VEC * VEC;             // halo rounded up to whole vectors
+    constexpr int NV = (VEC + 2 * A) / VEC;
+    T val[VEC + 2 * A];
+    if (x - A >= 0 && x + VEC + A <= nx) {
 #pragma unroll
-        for (int j = 0; j < VEC + 2 * R; ++j) val[j] = row[x - R + j];
+        for (int j = 0; j < NV; ++j) {
+            const Vec<T, VEC> w = vec_load<T, VEC>(row + x - A + j * VEC);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) val[j * VEC + v] = w.v[v];
+        }
     } else {
 #pragma unroll
-        for (int j = 0; j < VEC + 2 * R; ++j) {
-            int q = x - R + j;
+        for (int j = A - R; j < VEC + A + R; ++j) {
+            int q = x - A + j;
             q += q < 0 ? nx : 0;
             q -= q >= nx ? nx : 0;
             val[j] = row[q];
@@ -115,7 +139,7 @@ __device__ __forceinline__ Vec<T, VEC> fastv_blur_x(const TapsR<T, R> &tp, const
     for (int v = 0; v < VEC; ++v) {
         T acc = T(0);
 #pragma unroll
-        for (int k = 0; k <= 2 * R; ++k) acc += tp.t[k] * val[v + 2 * R - k];     // input position (x + v) - (k - R)
+        for (int k = 0; k <= 2 * R; ++k) acc += tp.t[k] * val[A + v + R - k];     // input position (x + v) - (k - R)
         out.v[v] = acc;
     }
     return out;

@@ -672,7 +672,9 @@ static int lsq_blur_front(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *i
         const int kaxis = (g.dim == 3 && ax == 1) ? 1 : 2;
         if (fastv_ok(pl)) {
             constexpr int VEC = FastvCfg<T>::VEC;
-            const dim3 vgrid((g.nx / VEC + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
+            dim3 vgrid((g.nx / VEC + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
+            if (kaxis == 1) vgrid.y = (g.ny + FASTV_ROWS - 1) / FASTV_ROWS;
+            else vgrid.z = (g.nz + FASTV_ROWS - 1) / FASTV_ROWS;
             const FastvGeom<T> fg = make_fastv_geom<T>(g);
             FASTV_SWITCH_R(lsq_radius(pl, ax), (fastv_blur_pass_kernel<T, R, VEC><<<vgrid, FAST_TH, 0, s>>>(
                                                    fg, lsq_taps_r<T, R>(pl, ax), kaxis, (const T *)src, (T *)dst, (const T *)halo_lo,
