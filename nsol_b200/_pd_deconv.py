@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 from nsol_b200 import _lib
-from nsol_b200.linear_solver import LsmrPlan, probe_least_squares
+from nsol_b200.linear_solver import acquire_lsmr_plan, probe_least_squares
 
 
 def run_pd_deconvolution(solver, cfg):
@@ -33,14 +33,11 @@ def run_pd_deconvolution(solver, cfg):
     iters = int(solver._iterations)
     x_out = _lib.context().result_empty(n, np.float64)
     its = np.empty((iters + 1, n), dtype=np.float64) if solver._observer is not None else None
-    plan = LsmrPlan(info, solver._dtype)
-    try:
-        ctx = plan.ctx
-        ctx.check(ctx.lib.nsol_pd_deconv_run_host(
-            plan.handle, C.byref(desc), iters, int(iter_max), float(prox_scale), b.ctypes.data, x0s.ctypes.data,
-            x_out.ctypes.data, its.ctypes.data if its is not None else None, None))
-    finally:
-        plan.close()
+    plan = acquire_lsmr_plan(solver, info, solver._dtype)       # kept across runs (parameter studies)
+    ctx = plan.ctx
+    ctx.check(ctx.lib.nsol_pd_deconv_run_host(
+        plan.handle, C.byref(desc), iters, int(iter_max), float(prox_scale), b.ctypes.data, x0s.ctypes.data,
+        x_out.ctypes.data, its.ctypes.data if its is not None else None, None))
     if its is not None:
         for i in range(iters + 1):
             solver._observer.add_x(np.array(its[i]))

@@ -10,7 +10,7 @@ outer/inner loop runs on the device (``nsol_admm_run_host``) without host synchr
 """
 import numpy as np
 
-from nsol_b200.linear_solver import LinearSolver, LsmrPlan
+from nsol_b200.linear_solver import LinearSolver, acquire_lsmr_plan
 
 
 class ADMMLinearSolver(LinearSolver):
@@ -61,19 +61,16 @@ class ADMMLinearSolver(LinearSolver):
             raise ValueError("ADMMLinearSolver: dimension=%d but B is a %dD gradient" % (self._dimension, info["dim"]))
         n = self._x0.size
         iters = int(self._iterations)
-        plan = LsmrPlan(info, self._dtype)
-        try:
-            ctx = plan.ctx
-            b = np.ascontiguousarray(self._b, dtype=np.float64)
-            x0 = np.ascontiguousarray(self._x0, dtype=np.float64)   # v = B(x0) (:171); lsmr itself is cold-started
-            x_out = ctx.result_empty(n, np.float64)
-            its = np.empty((iters + 1, n), dtype=np.float64) if self._observer is not None else None
-            ctx.check(ctx.lib.nsol_admm_run_host(
-                plan.handle, float(self._alpha), float(self._rho), iters, int(self._iter_max), 1.0,
-                float(self._x_scale), b.ctypes.data, x0.ctypes.data, x_out.ctypes.data,
-                its.ctypes.data if its is not None else None, None))
-        finally:
-            plan.close()
+        plan = acquire_lsmr_plan(self, info, self._dtype)       # kept across runs (parameter studies)
+        ctx = plan.ctx
+        b = np.ascontiguousarray(self._b, dtype=np.float64)
+        x0 = np.ascontiguousarray(self._x0, dtype=np.float64)   # v = B(x0) (:171); lsmr itself is cold-started
+        x_out = ctx.result_empty(n, np.float64)
+        its = np.empty((iters + 1, n), dtype=np.float64) if self._observer is not None else None
+        ctx.check(ctx.lib.nsol_admm_run_host(
+            plan.handle, float(self._alpha), float(self._rho), iters, int(self._iter_max), 1.0,
+            float(self._x_scale), b.ctypes.data, x0.ctypes.data, x_out.ctypes.data,
+            its.ctypes.data if its is not None else None, None))
         if its is not None:
             # nsol/admm_linear_solver.py:168-169, 186-187
             for i in range(iters + 1):

@@ -248,7 +248,7 @@ struct PdStep {
 #ifndef NSOL_PD_MINB_F32
 #define NSOL_PD_MINB_F32 2
 #endif
-template <typename T, int VEC, bool HAS_Y, int REG, int DATA, bool LINK>
+template <typename T, int VEC, bool HAS_Y, int REG, int DATA, bool LINK, bool UNIT>
 __global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : NSOL_PD_MINB_F64) pd_iter_kernel(const PdArgs<T> a) {
     using V = Vec<T, VEC>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : NSOL_
         V xb_m = load_xbar_own(z0 - 1, off - sz);
         V pz_m = z0 > 0 ? vec_load<T, VEC>(a.pz_in + off - sz) : vec_load_cg<T, VEC>(a.halo_pz_below + hrow);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) pz_prev.v[v] = dual_update<T, REG>(pz_m.v[v], xb_c.v[v], xb_m.v[v], wz, sigma, div_g);
+        for (int v = 0; v < VEC; ++v) pz_prev.v[v] = dual_update<T, REG, UNIT>(pz_m.v[v], xb_c.v[v], xb_m.v[v], wz, sigma, div_g);
     }
     if (HAS_Y) {
         T *buf = s_xb + (z0 & 1) * (TY + 2) * tile_w;
@@ -377,9 +377,9 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : NSOL_
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             T hi = (v + 1 < VEC) ? xb_c.v[(v + 1) % VEC] : x_right;
-            pnx.v[v] = dual_update<T, REG>(cur.px.v[v], hi, xb_c.v[v], wx, sigma, div_g);
-            if (HAS_Y) pny.v[v] = dual_update<T, REG>(cur.py.v[v], xup.v[v], xb_c.v[v], wy, sigma, div_g);
-            if (has_z) pnz.v[v] = dual_update<T, REG>(cur.pz.v[v], cur.xbn.v[v], xb_c.v[v], wz, sigma, div_g);
+            pnx.v[v] = dual_update<T, REG, UNIT>(cur.px.v[v], hi, xb_c.v[v], wx, sigma, div_g);
+            if (HAS_Y) pny.v[v] = dual_update<T, REG, UNIT>(cur.py.v[v], xup.v[v], xb_c.v[v], wy, sigma, div_g);
+            if (has_z) pnz.v[v] = dual_update<T, REG, UNIT>(cur.pz.v[v], cur.xbn.v[v], xb_c.v[v], wz, sigma, div_g);
         }
         if (active) {
             vec_store<T, VEC>(a.px_out + off, pnx);
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : NSOL_
         }
         // p'_x of the voxel left of this thread's first voxel
         T pnx_left = shfl_up_t(pnx.v[VEC - 1], 1);
-        if (lane == 0) pnx_left = need_l ? dual_update<T, REG>(cur.pxl, xb_c.v[0], xl_c, wx, sigma, div_g) : T(0);
+        if (lane == 0) pnx_left = need_l ? dual_update<T, REG, UNIT>(cur.pxl, xb_c.v[0], xl_c, wx, sigma, div_g) : T(0);
 
         V pny_dn = vec_zero<T, VEC>();
         if (HAS_Y) {
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : NSOL_
                 V h = vec_zero<T, VEC>();
                 if (need_dn) {
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) h.v[v] = dual_update<T, REG>(cur.pydn.v[v], xb_c.v[v], xdn.v[v], wy, sigma, div_g);
+                    for (int v = 0; v < VEC; ++v) h.v[v] = dual_update<T, REG, UNIT>(cur.pydn.v[v], xb_c.v[v], xdn.v[v], wy, sigma, div_g);
                 }
                 vec_store<T, VEC>(pbuf + s_col, h);
             }
@@ -416,9 +416,9 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : NSOL_
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             T lo = (v == 0) ? pnx_left : pnx.v[(v + VEC - 1) % VEC];
-            T div = madd(wx, lo, (-wx) * pnx.v[v]);                                   // Dx^T p_x
-            if (HAS_Y) div = div + madd(wy, pny_dn.v[v], (-wy) * pny.v[v]);            // += Dy^T p_y
-            if (has_z) div = div + madd(wz, pz_prev.v[v], (-wz) * pnz.v[v]);           // += Dz^T p_z
+            T div = wdiff<T, UNIT>(wx, lo, pnx.v[v]);                                   // Dx^T p_x
+            if (HAS_Y) div = div + wdiff<T, UNIT>(wy, pny_dn.v[v], pny.v[v]);            // += Dy^T p_y
+            if (has_z) div = div + wdiff<T, UNIT>(wz, pz_prev.v[v], pnz.v[v]);           // += Dz^T p_z
             primal_update<T, DATA>(cur.x.v[v], cur.b.v[v], div, tau, tl, theta, div_f, xnew.v[v], xbnew.v[v]);
         }
         if (active) {
@@ -924,11 +924,19 @@ template <typename T, int VEC, bool HAS_Y>
 static void pd_launch_rd(const nsol_pd_plan *pl, const PdArgs<T> &a, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
     const int reg = pl->desc.reg, data = pl->desc.data;
     const bool link = pl->link_on;
-#define NSOL_PD_CASE(R, D)                                                                 \
-    if (reg == R && data == D) {                                                           \
-        if (link) pd_iter_kernel<T, VEC, HAS_Y, R, D, true><<<grid, block, smem, s>>>(a);  \
-        else pd_iter_kernel<T, VEC, HAS_Y, R, D, false><<<grid, block, smem, s>>>(a);      \
-        return;                                                                            \
+    // unit spacing (every BASELINE configuration): the w * a products are exact and dropped (vector kernels only)
+    constexpr bool CAN_UNIT = VEC > 1;
+    const bool unit = CAN_UNIT && a.wx == T(1) && (!HAS_Y || a.wy == T(1)) && (!a.has_z || a.wz == T(1));
+#define NSOL_PD_CASE(R, D)                                                                                   \
+    if (reg == R && data == D) {                                                                             \
+        if (unit) {                                                                                          \
+            if (link) pd_iter_kernel<T, VEC, HAS_Y, R, D, true, CAN_UNIT><<<grid, block, smem, s>>>(a);      \
+            else pd_iter_kernel<T, VEC, HAS_Y, R, D, false, CAN_UNIT><<<grid, block, smem, s>>>(a);          \
+        } else {                                                                                             \
+            if (link) pd_iter_kernel<T, VEC, HAS_Y, R, D, true, false><<<grid, block, smem, s>>>(a);         \
+            else pd_iter_kernel<T, VEC, HAS_Y, R, D, false, false><<<grid, block, smem, s>>>(a);             \
+        }                                                                                                    \
+        return;                                                                                              \
     }
     NSOL_PD_CASE(NSOL_REG_TV, NSOL_DATA_L2)
     NSOL_PD_CASE(NSOL_REG_TV, NSOL_DATA_L1)

@@ -31,6 +31,10 @@ class LinearSolver(Solver):
         self._dtype = dtype
         self._lsq = None
 
+    def release(self):
+        """Free the device memory held by this solver (the cached LSMR plan)."""
+        release_lsmr_plan(self)
+
     def get_A(self):
         return self._A
 
@@ -164,6 +168,31 @@ def probe_least_squares(A, A_adj, B, B_adj, n):
     if int(np.prod(shape)) != n:
         raise ValueError("operators reshape x0 (%d values) to %s" % (n, (shape,)))
     return dict(a_kind=a_kind, a_op=a_op, b_kind=b_kind, shape=tuple(shape), spacing=tuple(spacing), dim=dim)
+
+
+def acquire_lsmr_plan(owner, info, dtype):
+    """The device plan of ``owner`` (a solver object) for this least-squares problem: created on first use and
+    kept across run() calls -- a parameter study re-runs one solver object many times, and allocating /
+    freeing ~14 device arrays costs several times the 512^2 ADMM solve itself.  A solver whose operators,
+    grid or dtype changed gets a new plan.  Freed by ``release_lsmr_plan`` or with the solver object."""
+    taps = None
+    if info["a_kind"] == "conv":
+        taps = tuple(tuple(float(v) for v in np.asarray(t).reshape(-1)) for t in info["a_op"].taps)
+    key = (tuple(info["shape"]), tuple(info["spacing"]), info["a_kind"], info["b_kind"], taps, _lib.dtype_code(dtype))
+    cached = getattr(owner, "_lsmr_plan_cache", None)
+    if cached is not None and cached[0] == key and cached[1].handle is not None:
+        return cached[1]
+    release_lsmr_plan(owner)
+    plan = LsmrPlan(info, dtype)
+    owner._lsmr_plan_cache = (key, plan)
+    return plan
+
+
+def release_lsmr_plan(owner):
+    cached = getattr(owner, "_lsmr_plan_cache", None)
+    if cached is not None:
+        cached[1].close()
+        owner._lsmr_plan_cache = None
 
 
 class LsmrPlan(object):

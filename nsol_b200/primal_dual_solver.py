@@ -157,7 +157,10 @@ class PrimalDualSolver(Solver):
         return h
 
     def release(self):
-        """Free the device memory held by this solver (plan + device-resident result)."""
+        """Free the device memory held by this solver (plan + device-resident result; the LSMR plan of the
+        deconvolution wiring)."""
+        from nsol_b200.linear_solver import release_lsmr_plan
+        release_lsmr_plan(self)
         plan = getattr(self, "_plan", None)
         if plan is not None:
             if self._fetch_result is not None:

@@ -14,7 +14,7 @@ branches of the reference (:161-220) are out of scope and raise ``ValueError``.
 import numpy as np
 
 from nsol_b200 import _lib
-from nsol_b200.linear_solver import LinearSolver, LsmrPlan
+from nsol_b200.linear_solver import LinearSolver, acquire_lsmr_plan
 
 EPS = 1e-10   # nsol/definitions.py:11
 
@@ -52,21 +52,18 @@ class TikhonovLinearSolver(LinearSolver):
         if self._bounds is not None:
             self._x0 = np.clip(self._x0, self._bounds[0], self._bounds[1])   # :143 (x0 is not passed to lsmr)
         lo, hi = (-np.inf, np.inf) if self._bounds is None else (float(self._bounds[0]), float(self._bounds[1]))
-        plan = LsmrPlan(info, self._dtype)
-        try:
-            ctx = plan.ctx
-            b = np.ascontiguousarray(self._b, dtype=np.float64)
-            rows = info["dim"] * n if info["b_kind"] == "grad" else n
-            b_reg = None
-            if np.ndim(self._b_reg) != 0 or float(self._b_reg) != 0.0:
-                b_reg = np.ascontiguousarray(np.broadcast_to(np.asarray(self._b_reg, dtype=np.float64), (rows,)))
-            x_out = ctx.result_empty(n, np.float64)
-            ctx.check(ctx.lib.nsol_tikhonov_run_host(
-                plan.handle, float(self._alpha), 1.0, float(self._x_scale), b.ctypes.data,
-                b_reg.ctypes.data if b_reg is not None else None, int(self._iter_max), lo, hi,
-                x_out.ctypes.data, None))
-        finally:
-            plan.close()
+        plan = acquire_lsmr_plan(self, info, self._dtype)       # kept across runs (parameter studies)
+        ctx = plan.ctx
+        b = np.ascontiguousarray(self._b, dtype=np.float64)
+        rows = info["dim"] * n if info["b_kind"] == "grad" else n
+        b_reg = None
+        if np.ndim(self._b_reg) != 0 or float(self._b_reg) != 0.0:
+            b_reg = np.ascontiguousarray(np.broadcast_to(np.asarray(self._b_reg, dtype=np.float64), (rows,)))
+        x_out = ctx.result_empty(n, np.float64)
+        ctx.check(ctx.lib.nsol_tikhonov_run_host(
+            plan.handle, float(self._alpha), 1.0, float(self._x_scale), b.ctypes.data,
+            b_reg.ctypes.data if b_reg is not None else None, int(self._iter_max), lo, hi,
+            x_out.ctypes.data, None))
         self._set_result(x_out)
         if self._observer is not None:
             self._observer.add_x(self.get_x())
