@@ -399,3 +399,298 @@ static bool fastv_ok(const nsol_lsmr_plan *pl) {
     case 5: { constexpr int R = 5; CALL; } break; \
     default: { constexpr int R = 6; CALL; } break; \
     }
+
+// =====================================================================================================
+// Fused 2-D forward / adjoint kernels: both blur passes inside the consumer (no separate pass kernel, no
+// scratch array).  A warp owns a strip of W = 32 * VEC columns and marches down a chunk of rows: every new
+// input row is blurred along x through a warp-private shared-memory row (with its periodic halo columns) and
+// pushed into a register ring of 2R+1 x-blurred rows; the blur along the rows is a dot product over the ring.
+// DRAM traffic is the algorithmic 7 words (forward) / 5 words (adjoint) per pixel; the rows needed a second time
+// (v[z], v[z+1] for the gradient; the 2R rows of ring warm-up per chunk) come from L1 / L2.
+// The blur is evaluated x-first (the separate-pass path goes rows-first): same taps, different rounding order.
+// =====================================================================================================
+#define FUSED2D_WARPS 4
+
+template <typename T, int VEC, int RX>
+struct Fused2dRow {
+    static constexpr int A = RX == 0 ? 0 : (RX + VEC - 1) / VEC * VEC;   // halo columns, whole vectors
+    static constexpr int W = 32 * VEC;
+    static constexpr int LEN = W + 2 * A;
+};
+
+// Per-lane addressing of one input row of the warp's strip: own VEC columns + (edge lanes) one halo vector.
+// The loads of row j+1 are issued before row j is consumed (software pipelining), so the x-blur never waits
+// on a global load it has just issued.
+template <typename T, int VEC, int RX>
+struct Fused2dLane {
+    using V = Vec<T, VEC>;
+    using L = Fused2dRow<T, VEC, RX>;
+    static constexpr int HV = L::A / VEC;                // halo vectors per side
+    int x, lane;
+    bool active, has_halo;
+    int halo_col, halo_slot;                             // column of this lane's halo vector / its slot in the shared row
+
+    __device__ __forceinline__ void init(int xw0, int nx, int lane_) {
+        lane = lane_;
+        x = xw0 + lane * VEC;
+        active = x < nx;
+        has_halo = RX > 0 && lane < 2 * HV;
+        const int wcols = min(L::W, nx - xw0);           // columns of this warp inside the row
+        // lanes 0..HV-1: left halo vectors, HV..2HV-1: right halo vectors (periodic; whole vectors wrap together)
+        int c = lane < HV ? xw0 - L::A + lane * VEC : xw0 + wcols + (lane - HV) * VEC;
+        c += c < 0 ? nx : 0;
+        c -= c >= nx ? nx : 0;
+        halo_col = c;
+        halo_slot = lane < HV ? lane * VEC : L::A + wcols + (lane - HV) * VEC;
+    }
+    __device__ __forceinline__ void load(const T *__restrict__ row, V &raw, V &hal) const {
+        raw = active ? vec_load<T, VEC>(row + x) : vec_zero<T, VEC>();
+        if (has_halo) hal = vec_load<T, VEC>(row + halo_col);
+    }
+    // x-blur of the row whose vectors are (raw, hal); buf = the warp's shared-memory row of this parity
+    __device__ __forceinline__ V blur(const TapsR<T, RX> &tx, const V &raw, const V &hal, T *buf) const {
+        if (RX == 0) return raw;
+        if (active) vec_store<T, VEC>(buf + L::A + lane * VEC, raw);      // (the slots past a partial strip hold the right halo)
+        if (has_halo) vec_store<T, VEC>(buf + halo_slot, hal);
+        __syncwarp();
+        V out = vec_zero<T, VEC>();
+        if (active) {
+            T val[VEC + 2 * L::A];
+#pragma unroll
+            for (int j = 0; j < (VEC + 2 * L::A) / VEC; ++j) {
+                const V w = vec_load<T, VEC>(buf + lane * VEC + j * VEC);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) val[j * VEC + v] = w.v[v];
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                T acc = T(0);
+#pragma unroll
+                for (int k = 0; k <= 2 * RX; ++k) acc += tx.t[k] * val[L::A + v + RX - k];
+                out.v[v] = acc;
+            }
+        }
+        return out;
+    }
+};
+
+struct Fused2dGeom {
+    int nx, nz, zc;
+    long long n;
+};
+
+__device__ __forceinline__ int fused2d_wrap(int z, int nz) {
+    z += z < 0 ? nz : 0;
+    z -= z >= nz ? nz : 0;
+    return z;
+}
+
+template <typename T, int RX, int RZ, int VEC>
+__global__ void __launch_bounds__(32 * FUSED2D_WARPS) fused2d_fwd_kernel(Fused2dGeom g, T wx, T wz, const LsmrScalars *__restrict__ S,
+                                                                         TapsR<T, RX> tx, TapsR<T, RZ> tz, const T *__restrict__ vhat,
+                                                                         T *__restrict__ u, double *__restrict__ part) {
+    using V = Vec<T, VEC>;
+    using L = Fused2dRow<T, VEC, RX>;
+    __shared__ __align__(16) T srow[FUSED2D_WARPS][2][L::LEN];
+    if (S->done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int xw0 = ((int)blockIdx.x * FUSED2D_WARPS + warp) * L::W;      // first column of the warp's strip
+    const bool warp_in = xw0 < g.nx;
+    const int z0 = (int)blockIdx.y * g.zc;
+    const int z1 = min(g.nz, z0 + g.zc);
+    const T inv_alpha = (T)S->inv_alpha, inv_beta = (T)S->inv_beta, malpha = (T)(-S->alpha), sa = (T)S->sqrt_alpha;
+    T *u0 = u, *u1 = u + g.n, *u2 = u + 2 * g.n;
+    double acc = 0.0;
+    if (warp_in) {
+        Fused2dLane<T, VEC, RX> ln;
+        ln.init(xw0, g.nx, lane);
+        const int x = ln.x;
+        const bool active = ln.active;
+        V ring[2 * RZ + 1];
+#pragma unroll
+        for (int i = 0; i <= 2 * RZ; ++i) ring[i] = vec_zero<T, VEC>();
+        const int steps = (z1 - z0) + 2 * RZ;
+        V raw_n = vec_zero<T, VEC>(), hal_n = vec_zero<T, VEC>();
+        ln.load(vhat + (long long)fused2d_wrap(z0 - RZ, g.nz) * g.nx, raw_n, hal_n);
+        for (int j = 0; j < steps; ++j) {
+            const V raw = raw_n, hal = hal_n;
+            if (j + 1 < steps) ln.load(vhat + (long long)fused2d_wrap(z0 - RZ + j + 1, g.nz) * g.nx, raw_n, hal_n);   // next input row
+            // operands of the output row z = z0 + j - 2 RZ, issued before the blur of this step
+            const bool outp = j >= 2 * RZ;
+            const int z = z0 + j - 2 * RZ;
+            const long long i0 = (long long)z * g.nx + x;
+            V vr = vec_zero<T, VEC>(), vd = vec_zero<T, VEC>(), a0 = vr, a1 = vr, a2 = vr;
+            T right = T(0);
+            if (outp && active) {
+                vr = vec_load<T, VEC>(vhat + i0);
+                if (z + 1 < g.nz) vd = vec_load<T, VEC>(vhat + i0 + g.nx);
+                if (lane == 31 && x + VEC < g.nx) right = vhat[i0 + VEC];
+                a0 = vec_load<T, VEC>(u0 + i0);
+                a1 = vec_load<T, VEC>(u1 + i0);
+                a2 = vec_load<T, VEC>(u2 + i0);
+            }
+            const V hx = ln.blur(tx, raw, hal, srow[warp][j & 1]);
+#pragma unroll
+            for (int i = 0; i < 2 * RZ; ++i) ring[i] = ring[i + 1];
+            ring[2 * RZ] = hx;                           // ring[i] = x-blurred row z - RZ + i
+            if (!outp) continue;
+            const T nb = __shfl_down_sync(0xffffffffu, vr.v[0], 1);      // first value of the lane to the right
+            if (lane != 31) right = (x + VEC < g.nx) ? nb : T(0);
+            if (active) {
+                V vc;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) vc.v[v] = vr.v[v] * inv_alpha;
+                const T rgt = right * inv_alpha;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    T av = T(0);
+#pragma unroll
+                    for (int k = 0; k <= 2 * RZ; ++k) av += tz.t[k] * ring[2 * RZ - k].v[v];      // row z - (k - RZ)
+                    T un = (a0.v[v] * inv_beta) * malpha + av * inv_alpha;
+                    a0.v[v] = un;
+                    acc += (double)un * (double)un;
+                    const T hi = (v + 1 < VEC) ? vc.v[(v + 1) % VEC] : rgt;
+                    const T dx = wx * hi + (-wx) * vc.v[v];
+                    un = (a1.v[v] * inv_beta) * malpha + sa * dx;
+                    a1.v[v] = un;
+                    acc += (double)un * (double)un;
+                    const T hz = (z + 1 < g.nz) ? vd.v[v] * inv_alpha : T(0);
+                    const T dz = wz * hz + (-wz) * vc.v[v];
+                    un = (a2.v[v] * inv_beta) * malpha + sa * dz;
+                    a2.v[v] = un;
+                    acc += (double)un * (double)un;
+                }
+                vec_store<T, VEC>(u0 + i0, a0);
+                vec_store<T, VEC>(u1 + i0, a1);
+                vec_store<T, VEC>(u2 + i0, a2);
+            }
+        }
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) part[(long long)blockIdx.y * gridDim.x + blockIdx.x] = acc;
+}
+
+template <typename T, int RX, int RZ, int VEC>
+__global__ void __launch_bounds__(32 * FUSED2D_WARPS) fused2d_adj_kernel(Fused2dGeom g, T wx, T wz, const LsmrScalars *__restrict__ S,
+                                                                         TapsR<T, RX> tx, TapsR<T, RZ> tz, const T *__restrict__ u,
+                                                                         T *__restrict__ vhat, double *__restrict__ part, int first) {
+    using V = Vec<T, VEC>;
+    using L = Fused2dRow<T, VEC, RX>;
+    __shared__ __align__(16) T srow[FUSED2D_WARPS][2][L::LEN];
+    if (S->done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int xw0 = ((int)blockIdx.x * FUSED2D_WARPS + warp) * L::W;
+    const bool warp_in = xw0 < g.nx;
+    const int z0 = (int)blockIdx.y * g.zc;
+    const int z1 = min(g.nz, z0 + g.zc);
+    const T inv_alpha = (T)S->inv_alpha, inv_beta = (T)S->inv_beta, mbeta = (T)(-S->beta), sa = (T)S->sqrt_alpha;
+    const T *u0 = u, *u1 = u + g.n, *u2 = u + 2 * g.n;
+    double acc = 0.0;
+    if (warp_in) {
+        Fused2dLane<T, VEC, RX> ln;
+        ln.init(xw0, g.nx, lane);
+        const int x = ln.x;
+        const bool active = ln.active;
+        V ring[2 * RZ + 1];
+#pragma unroll
+        for (int i = 0; i <= 2 * RZ; ++i) ring[i] = vec_zero<T, VEC>();
+        V u2_prev = vec_zero<T, VEC>();                  // u2 row z - 1 (zero above the first row: Dz^T boundary)
+        if (active && z0 > 0) u2_prev = vec_load<T, VEC>(u2 + (long long)(z0 - 1) * g.nx + x);
+        const int steps = (z1 - z0) + 2 * RZ;
+        V raw_n = vec_zero<T, VEC>(), hal_n = vec_zero<T, VEC>();
+        ln.load(u0 + (long long)fused2d_wrap(z0 - RZ, g.nz) * g.nx, raw_n, hal_n);
+        for (int j = 0; j < steps; ++j) {
+            const V raw = raw_n, hal = hal_n;
+            if (j + 1 < steps) ln.load(u0 + (long long)fused2d_wrap(z0 - RZ + j + 1, g.nz) * g.nx, raw_n, hal_n);
+            const bool outp = j >= 2 * RZ;
+            const int z = z0 + j - 2 * RZ;
+            const long long i0 = (long long)z * g.nx + x;
+            V b1 = vec_zero<T, VEC>(), b2 = b1, vv = b1;
+            T left = T(0);
+            if (outp && active) {
+                b1 = vec_load<T, VEC>(u1 + i0);
+                b2 = vec_load<T, VEC>(u2 + i0);
+                if (!first) vv = vec_load<T, VEC>(vhat + i0);
+                if (lane == 0 && x > 0) left = u1[i0 - 1];
+            }
+            const V hx = ln.blur(tx, raw, hal, srow[warp][j & 1]);
+#pragma unroll
+            for (int i = 0; i < 2 * RZ; ++i) ring[i] = ring[i + 1];
+            ring[2 * RZ] = hx;
+            if (!outp) continue;
+            const T nb = __shfl_up_sync(0xffffffffu, b1.v[VEC - 1], 1);   // last value of the lane to the left
+            if (lane != 0) left = nb;
+            if (active) {
+                const T lft = left * inv_beta;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    T av = T(0);
+#pragma unroll
+                    for (int k = 0; k <= 2 * RZ; ++k) av += tz.t[k] * ring[2 * RZ - k].v[v];
+                    T r = av * inv_beta;
+                    const T lo = (v == 0) ? lft : b1.v[(v + VEC - 1) % VEC] * inv_beta;
+                    T div = wx * lo + (-wx) * (b1.v[v] * inv_beta);
+                    const T loz = (z > 0) ? u2_prev.v[v] * inv_beta : T(0);
+                    div = div + (wz * loz + (-wz) * (b2.v[v] * inv_beta));
+                    r = r + sa * div;
+                    const T vn = first ? r : (vv.v[v] * inv_alpha) * mbeta + r;
+                    vv.v[v] = vn;
+                    acc += (double)vn * (double)vn;
+                }
+                vec_store<T, VEC>(vhat + i0, vv);
+            }
+            u2_prev = b2;
+        }
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) part[(long long)blockIdx.y * gridDim.x + blockIdx.x] = acc;
+}
+
+// when the fused 2-D kernels apply: 2-D, A = separable blur, B = grad, no slab mode, enough rows to amortise the ring
+// warm-up (or forced by the "lsmr_fuse2d" tuning knob: 1 = on whenever possible, 2 = off)
+static bool fused2d_ok(const nsol_lsmr_plan *pl, int b_op) {
+    const GridView &gv = pl->gv;
+    if (gv.dim != 2 || pl->slab || pl->desc.a_op != NSOL_A_BLUR || b_op != NSOL_B_GRAD || !fastv_ok(pl)) return false;
+    if (pl->ctx->lsmr_fuse2d == 2) return false;
+    const int rz = pl->desc.radius[0], rx = pl->desc.radius[1];
+    if (rz != rx || rz < 1) return false;                    // instantiated for isotropic masks only
+    if (gv.nz < 2 * rz + 1) return false;
+    if (pl->ctx->lsmr_fuse2d == 1) return true;
+    return gv.n >= (1ll << 22);                              // from 2048^2: below, the row-mapped kernels have more threads in flight
+}
+
+static int fused2d_rows_per_chunk(const nsol_lsmr_plan *pl, int vec) {
+    const GridView &gv = pl->gv;
+    const int strips = (gv.nx + 32 * vec * FUSED2D_WARPS - 1) / (32 * vec * FUSED2D_WARPS);
+    // aim at >= 2 blocks of 128 threads per SM and warp-strip; never fewer than 16 rows per chunk
+    int zc = 64;
+    while (zc > 16 && (long long)strips * ((gv.nz + zc - 1) / zc) < (long long)pl->ctx->sm_count * 8) zc /= 2;
+    if (pl->ctx->lsmr_fuse2d == 1 && gv.nz < 64) zc = gv.nz < 8 ? gv.nz : 8;     // tests: several chunks on small images
+    return zc;
+}
+
+template <typename T>
+static int fused2d_launch(nsol_lsmr_plan *pl, bool forward, int first, cudaStream_t s, int *nparts) {
+    constexpr int VEC = FastvCfg<T>::VEC;
+    const GridView &gv = pl->gv;
+    Fused2dGeom g;
+    g.nx = gv.nx;
+    g.nz = gv.nz;
+    g.n = gv.n;
+    g.zc = fused2d_rows_per_chunk(pl, VEC);
+    const dim3 grid((gv.nx + 32 * VEC * FUSED2D_WARPS - 1) / (32 * VEC * FUSED2D_WARPS), (gv.nz + g.zc - 1) / g.zc, 1);
+    const T wx = (T)gv.w[0], wz = (T)gv.w[1];
+    const int r = pl->desc.radius[0];
+    if (forward) {
+        FASTV_SWITCH_R(r, (fused2d_fwd_kernel<T, (R < 1 ? 1 : R), (R < 1 ? 1 : R), VEC><<<grid, 32 * FUSED2D_WARPS, 0, s>>>(
+                              g, wx, wz, pl->S, lsq_taps_r<T, (R < 1 ? 1 : R)>(pl, 1), lsq_taps_r<T, (R < 1 ? 1 : R)>(pl, 0), (const T *)pl->v,
+                              (T *)pl->u, pl->part)));
+    } else {
+        FASTV_SWITCH_R(r, (fused2d_adj_kernel<T, (R < 1 ? 1 : R), (R < 1 ? 1 : R), VEC><<<grid, 32 * FUSED2D_WARPS, 0, s>>>(
+                              g, wx, wz, pl->S, lsq_taps_r<T, (R < 1 ? 1 : R)>(pl, 1), lsq_taps_r<T, (R < 1 ? 1 : R)>(pl, 0), (const T *)pl->u,
+                              (T *)pl->v, pl->part, first)));
+    }
+    *nparts = (int)(grid.x * grid.y);
+    NSOL_LAUNCH_CHECK(pl->ctx);
+    return NSOL_OK;
+}

@@ -693,10 +693,14 @@ static int lsq_blur_front(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *i
 // forward / adjoint / update phases: vector kernels when they apply, the generic ones otherwise.
 // *nparts = number of partial sums written to pl->part.
 template <typename T>
-static int lsq_launch_fwd(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *op, const void *v_hi, cudaStream_t s, int *nparts) {
+static int lsq_launch_fwd(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *halo_lo, const void *halo_hi, const void *v_hi,
+                          cudaStream_t s, int *nparts) {
     T *u = (T *)pl->u;
     const T *v = (const T *)pl->v;
     const int ax = g.dim - 1;
+    if (fused2d_ok(pl, g.b_op)) return fused2d_launch<T>(pl, true, 0, s, nparts);
+    const void *op = nullptr;
+    NSOL_CHECK(lsq_blur_front<T>(pl, g, v, &op, s, halo_lo, halo_hi));
     if (fastv_ok(pl)) {
         constexpr int VEC = FastvCfg<T>::VEC;
         const dim3 vgrid((g.nx / VEC + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
@@ -715,10 +719,14 @@ static int lsq_launch_fwd(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *o
 }
 
 template <typename T>
-static int lsq_launch_adj(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *op, int first, const void *uz_lo, cudaStream_t s, int *nparts) {
+static int lsq_launch_adj(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *halo_lo, const void *halo_hi, int first, const void *uz_lo,
+                          cudaStream_t s, int *nparts) {
     const T *u = (const T *)pl->u;
     T *v = (T *)pl->v;
     const int ax = g.dim - 1;
+    if (fused2d_ok(pl, g.b_op)) return fused2d_launch<T>(pl, false, first, s, nparts);
+    const void *op = nullptr;
+    NSOL_CHECK(lsq_blur_front<T>(pl, g, u, &op, s, halo_lo, halo_hi));       // A^T = A (same mask, periodic)
     if (fastv_ok(pl)) {
         constexpr int VEC = FastvCfg<T>::VEC;
         const dim3 vgrid((g.nx / VEC + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
@@ -777,20 +785,16 @@ static int lsmr_solve_t(nsol_lsmr_plan *pl, double alpha, const void *b_dev, con
     if (g.ny > 65535 || g.nz > 65535)
         return nsol_fail(ctx, NSOL_EINVAL, "lsmr (multi-kernel path): more than 65535 rows along y or z are not supported");
     int rparts = 0;
-    const void *op = nullptr;
-    NSOL_CHECK(lsq_blur_front<T>(pl, ge, u, &op, s));       // A^T = A (same mask, periodic)
-    NSOL_CHECK(lsq_launch_adj<T>(pl, ge, op, 1, nullptr, s, &rparts));
+    NSOL_CHECK(lsq_launch_adj<T>(pl, ge, nullptr, nullptr, 1, nullptr, s, &rparts));
     lsmr_scalar_init_alpha<<<1, 1024, 0, s>>>(pl->S, part, rparts);
     NSOL_LAUNCH_CHECK(ctx);
     lsmr_init_vectors_kernel<T><<<nb, th, 0, s>>>(g.n, pl->S, v, h, hbar, x);
     NSOL_LAUNCH_CHECK(ctx);
     for (int it = 0; it < maxiter; ++it) {
-        NSOL_CHECK(lsq_blur_front<T>(pl, ge, v, &op, s));
-        NSOL_CHECK(lsq_launch_fwd<T>(pl, ge, op, nullptr, s, &rparts));
+        NSOL_CHECK(lsq_launch_fwd<T>(pl, ge, nullptr, nullptr, nullptr, s, &rparts));
         lsmr_scalar_beta<<<1, 1024, 0, s>>>(pl->S, part, rparts);
         NSOL_LAUNCH_CHECK(ctx);
-        NSOL_CHECK(lsq_blur_front<T>(pl, ge, u, &op, s));
-        NSOL_CHECK(lsq_launch_adj<T>(pl, ge, op, 0, nullptr, s, &rparts));
+        NSOL_CHECK(lsq_launch_adj<T>(pl, ge, nullptr, nullptr, 0, nullptr, s, &rparts));
         lsmr_scalar_alpha<<<1, 1024, 0, s>>>(pl->S, part, rparts);
         NSOL_LAUNCH_CHECK(ctx);
         NSOL_CHECK(lsq_launch_update<T>(pl, ge, s, &rparts));
@@ -1240,7 +1244,6 @@ static int lsmr_slab_phase_t(nsol_lsmr_plan *pl, int phase, double p0, double p1
     double *part = pl->part;
     if (g.ny > 65535 || g.nz > 65535) return nsol_fail(ctx, NSOL_EINVAL, "lsmr slab: more than 65535 rows along y or z are not supported");
     int rparts = 0;
-    const void *op = nullptr;
     switch (phase) {
     case NSOL_PH_RHS:            // u = [b; sqrt_alpha b_reg]; p0 = sqrt_alpha, i0 = 0: b_reg = 0  -> ss
         lsmr_rhs_kernel<T><<<nb, th, 0, s>>>(g, pl->rows_b, (const T *)pl->bbuf, i0 ? (const T *)pl->breg : (const T *)nullptr, p0, u, part);
@@ -1252,8 +1255,7 @@ static int lsmr_slab_phase_t(nsol_lsmr_plan *pl, int phase, double p0, double p1
         break;
     case NSOL_PH_ADJ_FIRST:
     case NSOL_PH_ADJ:            // needs the U0 and UZ halos -> ss
-        NSOL_CHECK(lsq_blur_front<T>(pl, g, u, &op, s, pl->halo_u_lo, pl->halo_u_hi));
-        NSOL_CHECK(lsq_launch_adj<T>(pl, g, op, phase == NSOL_PH_ADJ_FIRST ? 1 : 0, pl->halo_uz_lo, s, &rparts));
+        NSOL_CHECK(lsq_launch_adj<T>(pl, g, pl->halo_u_lo, pl->halo_u_hi, phase == NSOL_PH_ADJ_FIRST ? 1 : 0, pl->halo_uz_lo, s, &rparts));
         lsmr_reduce_ss_kernel<<<1, 1024, 0, s>>>(pl->S, part, rparts, pl->ssbuf, phase == NSOL_PH_ADJ_FIRST ? 1 : 0);
         break;
     case NSOL_PH_SCAL_INIT_ALPHA:
@@ -1262,8 +1264,7 @@ static int lsmr_slab_phase_t(nsol_lsmr_plan *pl, int phase, double p0, double p1
         lsmr_init_vectors_kernel<T><<<nb, th, 0, s>>>(g.n, pl->S, v, h, hbar, x);
         break;
     case NSOL_PH_FWD:            // needs the V halos -> ss
-        NSOL_CHECK(lsq_blur_front<T>(pl, g, v, &op, s, pl->halo_v_lo, pl->halo_v_hi));
-        NSOL_CHECK(lsq_launch_fwd<T>(pl, g, op, pl->halo_v_hi, s, &rparts));
+        NSOL_CHECK(lsq_launch_fwd<T>(pl, g, pl->halo_v_lo, pl->halo_v_hi, pl->halo_v_hi, s, &rparts));
         lsmr_reduce_ss_kernel<<<1, 1024, 0, s>>>(pl->S, part, rparts, pl->ssbuf, 0);
         break;
     case NSOL_PH_SCAL_BETA:

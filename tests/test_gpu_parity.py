@@ -750,6 +750,43 @@ def test_lsmr_vector_kernels_match_generic_kernels(shape, var, dtype):
         assert rel_max(out[1][0], ref) < F64_LSMR_TOL
 
 
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("shape,var", [((40, 36), 1.0), ((70, 132), 1.0), ((33, 260), 0.4), ((9, 8), 1.0), ((64, 48), 3.5)])
+def test_lsmr_fused_2d_kernels_match_generic_kernels(shape, var, dtype):
+    """The fused 2-D forward / adjoint kernels (both blur passes inside the consumer: shared-memory x-blur +
+    register ring along the rows; used for large images, forced here with lsmr_fuse2d = 1) against the generic
+    kernels and the oracle: partial warp strips, several row chunks with periodic ring warm-up, radius 2, 3 and 6,
+    the smallest image the ring allows."""
+    rng = np.random.RandomState(29)
+    obs = rng.rand(*shape) * 200 + 10
+    xs = float(obs.max())
+    A, A_adj, D, D_adj = deconv_callables(shape, [var, var])
+    ctx = _lib.context()
+    out = {}
+    try:
+        for tag, path, fuse in (("fused", 1, 1), ("generic", 3, 2)):
+            ctx.set_tuning("lsmr_path", path)
+            ctx.set_tuning("lsmr_fuse2d", fuse)
+            s = admm.ADMMLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=D, B_adj=D_adj, x0=obs.flatten(), dimension=2,
+                                      alpha=0.02, rho=0.3, iterations=3, iter_max=7, x_scale=xs, dtype=dtype)
+            s.run()
+            tk1 = tk.TikhonovLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=D, B_adj=D_adj, x0=obs.flatten(), alpha=0.05,
+                                          iter_max=8, x_scale=xs, dtype=dtype)
+            tk1.run()
+            out[tag] = (s.get_x(), tk1.get_x())
+    finally:
+        ctx.set_tuning("lsmr_path", 0)
+        ctx.set_tuning("lsmr_fuse2d", 0)
+    tol = 1e-11 if dtype == "float64" else 5e-4
+    assert rel_max(out["fused"][0], out["generic"][0]) < tol, rel_max(out["fused"][0], out["generic"][0])
+    assert rel_max(out["fused"][1], out["generic"][1]) < tol
+    if dtype == "float64":
+        Ao, Ao_adj, Do, Do_adj = orc.deconvolution_operators(shape, np.diag([var, var]))
+        ref = orc.admm_tv(Ao, Ao_adj, Do, Do_adj, obs.reshape(-1), obs.reshape(-1), 2, alpha=0.02, rho=0.3, iterations=3,
+                          iter_max=7, x_scale=xs)
+        assert rel_max(out["fused"][0], ref) < F64_LSMR_TOL
+
+
 # ------------------------------------------------------------------ measures on the device (SURVEY 8f row 3)
 def test_similarity_and_prior_measures_on_device():
     """SimilarityMeasures / PriorMeasures evaluated by device reductions equal the reference formulas
