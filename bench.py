@@ -3,7 +3,8 @@
 voxel-iterations/s of the fused 3-D TV-L2 primal-dual (Chambolle-Pock) iteration at 512^3.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype float64|float32]
-                    [--size 512] [--iters 100] [--scaling weak|strong] [--impl reference]
+                    [--size 512] [--iters 100] [--scaling weak|strong] [--halo auto|p2p|nccl]
+                    [--other-configs] [--secondary-dtype] [--impl reference]
 
 One "step" = one full solve: reset (x = xbar = b/x_scale, p = 0) + ``iters`` fused
 primal-dual iterations over the volume (BASELINE config 4: alpha=0.05, L2=8, ALG2).
@@ -16,7 +17,8 @@ primal-dual iterations over the volume (BASELINE config 4: alpha=0.05, L2=8, ALG
   cpu_baseline  the oracle port of the reference loop (same scipy.ndimage / numpy call
              structure as nsol/primal_dual_solver.py:232-261) on a bounded sample.
 Multi-GPU (torchrun, one rank per GPU): z-slab decomposition with a 3-plane halo
-exchange per iteration (nsol_b200/distributed.py).
+exchange per iteration, by default inside the iteration kernels over CUDA-IPC mapped peer
+memory (--halo p2p; NCCL send/recv with --halo nccl; nsol_b200/distributed.py).
 ``--impl reference`` times the CPU port alone on rank 0 (the reference is pure Python and
 cannot travel to the GPU box).
 """
@@ -505,6 +507,10 @@ def main():
     if rank == 0:
         esz = 4 if args.dtype == "float32" else 8
         achieved = 11 * esz * nvox_loc / (main_res["iter_ms"] * 1e-3) / 1e9
+        # default variants (csrc/pd_kernels.cu): TMA bulk-async kernel for float64 3-D, register-pipelined LDG for float32
+        variant = int(os.environ.get("NSOL_PD_VARIANT", "0")) or (2 if args.dtype == "float64" else 1)
+        kernel_name = ("pd_iter_bulk_kernel" if variant == 2 else "pd_iter_kernel") + \
+            "<%s, TV, L2, link=%d, unit=1>" % ("double" if args.dtype == "float64" else "float", 1 if halo_mode[0] == "p2p" else 0)
         line = {
             "metric": METRIC, "value": main_res["value"], "unit": "voxel-iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
@@ -520,7 +526,7 @@ def main():
             "gpu_launches": main_res["launches"],
             "clocks": main_res["clocks"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic("f64" if args.dtype == "float64" else "f32", nvox_loc), "peak_source": peak_src, "kernel": "pd_iter_kernel",
+                         "traffic": measured_traffic("f64" if args.dtype == "float64" else "f32", nvox_loc), "peak_source": peak_src, "kernel": kernel_name,
                          "algorithmic_bytes_per_launch": 11 * esz * nvox_loc, "avg_launch_ms": main_res["iter_ms"],
                          "copy_gbs_this_gpu": copy_gbs, "frac_of_copy_this_gpu": achieved / copy_gbs},
         }

@@ -1,7 +1,7 @@
 // pd_bulk_kernel.cuh -- 3-D fused primal-dual iteration with TMA bulk-async staged tiles.
 //
 // Same arithmetic, thread mapping and z-marching as pd_iter_kernel (pd_kernels.cu), but the
-// global loads do not go through registers: lane 0 of every warp issues 1-D bulk copies
+// global loads do not go through registers: one elected lane of every warp issues 1-D bulk copies
 // (cp.async.bulk.shared.global, SASS UBLKCP -- the TMA unit) of the warp's contiguous row
 // segments of xbar/p/x/b for plane z+S-1 into a warp-private ring of S shared-memory stages,
 // completion is signalled on an mbarrier (expect_tx / complete_tx), and all lanes read plane z
@@ -12,6 +12,9 @@
 // (xbar[x0-1], xbar[x0+W], p_x[x0-1]) arrive with the row; the y-halo rows of the CTA's edge
 // warps are extra bulk copies.  The xbar / p'_y exchange between the warps of a CTA is unchanged
 // (shared memory, one __syncthreads per plane).
+// The warp's row index is broadcast from lane 0 so the compiler keeps the whole issue path (addresses,
+// byte counts, predicates) on the uniform datapath; template parameters: LINK = in-kernel z-slab halo
+// exchange over peer memory (pd_kernels.cu), UNIT = unit grid spacing (the w * a products are exact and dropped).
 #pragma once
 
 #ifndef NSOL_PD_STAGES
