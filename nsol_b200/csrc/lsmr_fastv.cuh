@@ -410,6 +410,9 @@ static bool fastv_ok(const nsol_lsmr_plan *pl) {
 // The blur is evaluated x-first (the separate-pass path goes rows-first): same taps, different rounding order.
 // =====================================================================================================
 #define FUSED2D_WARPS 4
+#ifndef FUSED2D_MINB
+#define FUSED2D_MINB 5   // 96 registers -> 5 CTAs = 20 warps per SM (measured: 4 CTAs 625 us, 5 CTAs 572 us, 6 CTAs with spills 664 us at 4096^2 float64)
+#endif
 
 template <typename T, int VEC, int RX>
 struct Fused2dRow {
@@ -486,7 +489,7 @@ __device__ __forceinline__ int fused2d_wrap(int z, int nz) {
 }
 
 template <typename T, int RX, int RZ, int VEC>
-__global__ void __launch_bounds__(32 * FUSED2D_WARPS) fused2d_fwd_kernel(Fused2dGeom g, T wx, T wz, const LsmrScalars *__restrict__ S,
+__global__ void __launch_bounds__(32 * FUSED2D_WARPS, FUSED2D_MINB) fused2d_fwd_kernel(Fused2dGeom g, T wx, T wz, const LsmrScalars *__restrict__ S,
                                                                          TapsR<T, RX> tx, TapsR<T, RZ> tz, const T *__restrict__ vhat,
                                                                          T *__restrict__ u, double *__restrict__ part) {
     using V = Vec<T, VEC>;
@@ -571,7 +574,7 @@ __global__ void __launch_bounds__(32 * FUSED2D_WARPS) fused2d_fwd_kernel(Fused2d
 }
 
 template <typename T, int RX, int RZ, int VEC>
-__global__ void __launch_bounds__(32 * FUSED2D_WARPS) fused2d_adj_kernel(Fused2dGeom g, T wx, T wz, const LsmrScalars *__restrict__ S,
+__global__ void __launch_bounds__(32 * FUSED2D_WARPS, FUSED2D_MINB) fused2d_adj_kernel(Fused2dGeom g, T wx, T wz, const LsmrScalars *__restrict__ S,
                                                                          TapsR<T, RX> tx, TapsR<T, RZ> tz, const T *__restrict__ u,
                                                                          T *__restrict__ vhat, double *__restrict__ part, int first) {
     using V = Vec<T, VEC>;
