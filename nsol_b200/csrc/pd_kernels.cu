@@ -245,11 +245,16 @@ struct PdStep {
 #ifndef NSOL_PD_MINB_F64
 #define NSOL_PD_MINB_F64 1
 #endif
+// 2-D / 1-D float64 (128-thread CTAs, no shared memory): the kernel is latency-bound at 104 registers = 16 warps per
+// SM (ncu: issue slots 26 %, long-scoreboard 10); capping the registers buys warps
+#ifndef NSOL_PD_MINB_F64_2D
+#define NSOL_PD_MINB_F64_2D 3   // 80 registers (60 B of spills): 6 CTAs = 24 warps per SM; batched 1024^2 sweep 0.906 -> 0.945 of the roofline
+#endif
 #ifndef NSOL_PD_MINB_F32
 #define NSOL_PD_MINB_F32 2
 #endif
 template <typename T, int VEC, bool HAS_Y, int REG, int DATA, bool LINK, bool UNIT>
-__global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : NSOL_PD_MINB_F64) pd_iter_kernel(const PdArgs<T> a) {
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : (HAS_Y ? NSOL_PD_MINB_F64 : NSOL_PD_MINB_F64_2D)) pd_iter_kernel(const PdArgs<T> a) {
     using V = Vec<T, VEC>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
