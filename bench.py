@@ -312,7 +312,7 @@ def main():
     ap.add_argument("--iters", type=int, default=100, help="primal-dual iterations per step (solve)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--ref-size", type=int, default=256)
-    ap.add_argument("--ref-iters", type=int, default=2)
+    ap.add_argument("--ref-iters", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--overlap", action="store_true",
