@@ -482,6 +482,13 @@ struct Fused2dGeom {
     long long n;
 };
 
+// cp.async (LDGSTS) staging of the operand rows of the NEXT output row: bytes in flight without registers
+__device__ __forceinline__ void fused2d_cp16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void fused2d_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void fused2d_wait_prev() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
 __device__ __forceinline__ int fused2d_wrap(int z, int nz) {
     z += z < 0 ? nz : 0;
     z -= z >= nz ? nz : 0;
@@ -495,6 +502,7 @@ __global__ void __launch_bounds__(32 * FUSED2D_WARPS, FUSED2D_MINB) fused2d_fwd_
     using V = Vec<T, VEC>;
     using L = Fused2dRow<T, VEC, RX>;
     __shared__ __align__(16) T srow[FUSED2D_WARPS][2][L::LEN];
+    __shared__ __align__(16) T sop[FUSED2D_WARPS][2][5][L::W];            // operand rows of the next / current output row
     if (S->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int xw0 = ((int)blockIdx.x * FUSED2D_WARPS + warp) * L::W;      // first column of the warp's strip
@@ -515,28 +523,41 @@ __global__ void __launch_bounds__(32 * FUSED2D_WARPS, FUSED2D_MINB) fused2d_fwd_
         const int steps = (z1 - z0) + 2 * RZ;
         V raw_n = vec_zero<T, VEC>(), hal_n = vec_zero<T, VEC>();
         ln.load(vhat + (long long)fused2d_wrap(z0 - RZ, g.nz) * g.nx, raw_n, hal_n);
+        T right_n = T(0);
         for (int j = 0; j < steps; ++j) {
             const V raw = raw_n, hal = hal_n;
+            T right = right_n;
             if (j + 1 < steps) ln.load(vhat + (long long)fused2d_wrap(z0 - RZ + j + 1, g.nz) * g.nx, raw_n, hal_n);   // next input row
-            // operands of the output row z = z0 + j - 2 RZ, issued before the blur of this step
-            const bool outp = j >= 2 * RZ;
-            const int z = z0 + j - 2 * RZ;
-            const long long i0 = (long long)z * g.nx + x;
-            V vr = vec_zero<T, VEC>(), vd = vec_zero<T, VEC>(), a0 = vr, a1 = vr, a2 = vr;
-            T right = T(0);
-            if (outp && active) {
-                vr = vec_load<T, VEC>(vhat + i0);
-                if (z + 1 < g.nz) vd = vec_load<T, VEC>(vhat + i0 + g.nx);
-                if (lane == 31 && x + VEC < g.nx) right = vhat[i0 + VEC];
-                a0 = vec_load<T, VEC>(u0 + i0);
-                a1 = vec_load<T, VEC>(u1 + i0);
-                a2 = vec_load<T, VEC>(u2 + i0);
+            // operand rows of the NEXT output row (z + 1) into the other stage: in flight during this step's work
+            const int z = z0 + j - 2 * RZ;               // output row of this step (if j >= 2 RZ)
+            if (j + 1 >= 2 * RZ && j + 1 < steps && active) {
+                const long long in = (long long)(z + 1) * g.nx + x;
+                T *st = &sop[warp][(j + 1) & 1][0][lane * VEC];
+                fused2d_cp16(st, vhat + in);
+                if (z + 2 < g.nz) fused2d_cp16(st + L::W, vhat + in + g.nx);
+                fused2d_cp16(st + 2 * L::W, u0 + in);
+                fused2d_cp16(st + 3 * L::W, u1 + in);
+                fused2d_cp16(st + 4 * L::W, u2 + in);
+                right_n = (lane == 31 && x + VEC < g.nx) ? vhat[in + VEC] : T(0);
             }
+            fused2d_commit();
+            const bool outp = j >= 2 * RZ;
+            const long long i0 = (long long)z * g.nx + x;
             const V hx = ln.blur(tx, raw, hal, srow[warp][j & 1]);
 #pragma unroll
             for (int i = 0; i < 2 * RZ; ++i) ring[i] = ring[i + 1];
             ring[2 * RZ] = hx;                           // ring[i] = x-blurred row z - RZ + i
             if (!outp) continue;
+            fused2d_wait_prev();                         // the group committed one step ago (this row's operands) has landed
+            V vr = vec_zero<T, VEC>(), vd = vec_zero<T, VEC>(), a0 = vr, a1 = vr, a2 = vr;
+            if (active) {
+                const T *st = &sop[warp][j & 1][0][lane * VEC];
+                vr = vec_load<T, VEC>(st);
+                if (z + 1 < g.nz) vd = vec_load<T, VEC>(st + L::W);
+                a0 = vec_load<T, VEC>(st + 2 * L::W);
+                a1 = vec_load<T, VEC>(st + 3 * L::W);
+                a2 = vec_load<T, VEC>(st + 4 * L::W);
+            }
             const T nb = __shfl_down_sync(0xffffffffu, vr.v[0], 1);      // first value of the lane to the right
             if (lane != 31) right = (x + VEC < g.nx) ? nb : T(0);
             if (active) {
@@ -580,6 +601,7 @@ __global__ void __launch_bounds__(32 * FUSED2D_WARPS, FUSED2D_MINB) fused2d_adj_
     using V = Vec<T, VEC>;
     using L = Fused2dRow<T, VEC, RX>;
     __shared__ __align__(16) T srow[FUSED2D_WARPS][2][L::LEN];
+    __shared__ __align__(16) T sop[FUSED2D_WARPS][2][3][L::W];            // operand rows of the next / current output row
     if (S->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int xw0 = ((int)blockIdx.x * FUSED2D_WARPS + warp) * L::W;
@@ -602,25 +624,36 @@ __global__ void __launch_bounds__(32 * FUSED2D_WARPS, FUSED2D_MINB) fused2d_adj_
         const int steps = (z1 - z0) + 2 * RZ;
         V raw_n = vec_zero<T, VEC>(), hal_n = vec_zero<T, VEC>();
         ln.load(u0 + (long long)fused2d_wrap(z0 - RZ, g.nz) * g.nx, raw_n, hal_n);
+        T left_n = T(0);
         for (int j = 0; j < steps; ++j) {
             const V raw = raw_n, hal = hal_n;
+            T left = left_n;
             if (j + 1 < steps) ln.load(u0 + (long long)fused2d_wrap(z0 - RZ + j + 1, g.nz) * g.nx, raw_n, hal_n);
-            const bool outp = j >= 2 * RZ;
             const int z = z0 + j - 2 * RZ;
-            const long long i0 = (long long)z * g.nx + x;
-            V b1 = vec_zero<T, VEC>(), b2 = b1, vv = b1;
-            T left = T(0);
-            if (outp && active) {
-                b1 = vec_load<T, VEC>(u1 + i0);
-                b2 = vec_load<T, VEC>(u2 + i0);
-                if (!first) vv = vec_load<T, VEC>(vhat + i0);
-                if (lane == 0 && x > 0) left = u1[i0 - 1];
+            if (j + 1 >= 2 * RZ && j + 1 < steps && active) {        // operand rows of the next output row
+                const long long in = (long long)(z + 1) * g.nx + x;
+                T *st = &sop[warp][(j + 1) & 1][0][lane * VEC];
+                fused2d_cp16(st, u1 + in);
+                fused2d_cp16(st + L::W, u2 + in);
+                if (!first) fused2d_cp16(st + 2 * L::W, vhat + in);
+                left_n = (lane == 0 && x > 0) ? u1[in - 1] : T(0);
             }
+            fused2d_commit();
+            const bool outp = j >= 2 * RZ;
+            const long long i0 = (long long)z * g.nx + x;
             const V hx = ln.blur(tx, raw, hal, srow[warp][j & 1]);
 #pragma unroll
             for (int i = 0; i < 2 * RZ; ++i) ring[i] = ring[i + 1];
             ring[2 * RZ] = hx;
             if (!outp) continue;
+            fused2d_wait_prev();
+            V b1 = vec_zero<T, VEC>(), b2 = b1, vv = b1;
+            if (active) {
+                const T *st = &sop[warp][j & 1][0][lane * VEC];
+                b1 = vec_load<T, VEC>(st);
+                b2 = vec_load<T, VEC>(st + L::W);
+                if (!first) vv = vec_load<T, VEC>(st + 2 * L::W);
+            }
             const T nb = __shfl_up_sync(0xffffffffu, b1.v[VEC - 1], 1);   // last value of the lane to the left
             if (lane != 0) left = nb;
             if (active) {
