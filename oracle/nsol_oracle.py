@@ -411,11 +411,13 @@ def sym_ortho(a, b):
     return c, s, r
 
 
-def lsmr(matvec, rmatvec, b, n, maxiter, atol=0.0, btol=0.0, conlim=1e8, damp=0.0):
+def lsmr(matvec, rmatvec, b, n, maxiter, atol=0.0, btol=0.0, conlim=1e8, damp=0.0, norm=None):
     """LSMR (Fong & Saunders) as scipy runs it for the reference call
     ``lsmr(A, b, maxiter=iter_max, atol=0, btol=0)`` (cold start, x0=None),
-    nsol/tikhonov_linear_solver.py:149-154.  Returns (x, istop, itn)."""
-    norm = np.linalg.norm
+    nsol/tikhonov_linear_solver.py:149-154.  Returns (x, istop, itn).
+    ``norm``: 2-norm callable (default np.linalg.norm); the z-slab tests pass an all-reduced norm so that
+    the same recurrences run on the local slab of every rank."""
+    norm = norm or np.linalg.norm
     b = np.asarray(b, dtype=np.float64)
     u = b
     normb = norm(b)
@@ -556,7 +558,7 @@ def lsmr(matvec, rmatvec, b, n, maxiter, atol=0.0, btol=0.0, conlim=1e8, damp=0.
 # Tikhonov (lsmr / linear branch) -- nsol/tikhonov_linear_solver.py
 # --------------------------------------------------------------------------
 def tikhonov_lsmr(A, A_adj, B, B_adj, b, x0, alpha=0.01, b_reg=0, iter_max=10,
-                  x_scale=1.0, bounds=(0, np.inf)):
+                  x_scale=1.0, bounds=(0, np.inf), norm=None):
     """``TikhonovLinearSolver.run()`` with minimizer="lsmr", data_loss="linear":
     augmented system [A; sqrt(alpha) B] x = [b; sqrt(alpha) b_reg]
     (nsol/tikhonov_linear_solver.py:226-274), LSMR cold start (:149-154), clip to
@@ -577,7 +579,7 @@ def tikhonov_lsmr(A, A_adj, B, B_adj, b, x0, alpha=0.01, b_reg=0, iter_max=10,
         rhs[m_up:] = sa * b_regs
     else:
         fw, bw, rhs = A, A_adj, bs
-    x = lsmr(fw, bw, np.array(rhs), n, maxiter=iter_max)[0]
+    x = lsmr(fw, bw, np.array(rhs), n, maxiter=iter_max, norm=norm)[0]
     if bounds is not None:
         x = np.clip(x, bounds[0], bounds[1])
     return x * x_scale
@@ -605,7 +607,7 @@ def admm_shrink_iso(t, ell, dim):
 
 
 def admm_tv(A, A_adj, B, B_adj, b, x0, dim, alpha=0.01, rho=0.5, iterations=10,
-            iter_max=10, x_scale=1.0, keep_iterates=False):
+            iter_max=10, x_scale=1.0, keep_iterates=False, norm=None):
     """``ADMMLinearSolver.run()`` -- nsol/admm_linear_solver.py:165-237 with
     b_reg = 0: v = B(x0), w = 0; per iteration x <- Tikhonov/LSMR solve with
     b_reg = v - w and weight rho (x_scale=1, bounds (0, inf)), t = B(x) + w,
@@ -618,7 +620,7 @@ def admm_tv(A, A_adj, B, B_adj, b, x0, dim, alpha=0.01, rho=0.5, iterations=10,
     iterates = [x * x_scale] if keep_iterates else None
     for _ in range(iterations):
         x = tikhonov_lsmr(A, A_adj, B, B_adj, bs, x, alpha=rho, b_reg=v - w + 0.0,
-                          iter_max=iter_max, x_scale=1.0)
+                          iter_max=iter_max, x_scale=1.0, norm=norm)
         t = B(x) + w - 0.0
         v = admm_shrink_iso(t, alpha / rho, dim)
         w = t - v
