@@ -894,6 +894,8 @@ extern "C" int nsol_pd_plan_link_connect(nsol_pd_plan *pl, void *block_below, vo
 extern "C" int nsol_pd_plan_link_open(nsol_pd_plan *pl, const void *handle_below64, const void *handle_above64) {
     if (!pl) return NSOL_EINVAL;
     nsol_ctx *ctx = pl->ctx;
+    if (!pl->link_block) return nsol_fail(ctx, NSOL_ESTATE, "pd link: call nsol_pd_plan_link_create first");
+    if (pl->link_on) return nsol_fail(ctx, NSOL_ESTATE, "pd link: already connected");
     NSOL_CHECK(nsol_bind_device(ctx));
     void *below = nullptr, *above = nullptr;
     cudaIpcMemHandle_t h;
