@@ -732,3 +732,142 @@ static int fused2d_launch(nsol_lsmr_plan *pl, bool forward, int first, cudaStrea
     NSOL_LAUNCH_CHECK(pl->ctx);
     return NSOL_OK;
 }
+
+// =====================================================================================================
+// Vector versions of the per-solve / per-outer-iteration kernels (right-hand side, start vectors, clip, ADMM shrink):
+// once per 10 LSMR iterations, but 21 words per pixel together -- as scalar grid-stride kernels with a 64-bit
+// division per element they cost about two LSMR iterations.
+// =====================================================================================================
+// u = [b; sqrt_alpha * b_reg], partial ||u||^2.  nvec = n / VEC vectors per block of u.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(LSMR_THREADS) fastv_rhs_kernel(long long nvec, int rows_b, const T *__restrict__ b, const T *__restrict__ breg,
+                                                                 T sqrt_alpha, T *__restrict__ u, double *__restrict__ part) {
+    using V = Vec<T, VEC>;
+    const long long total = nvec * (1 + rows_b);
+    double acc = 0.0;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (long long)gridDim.x * blockDim.x) {
+        V v;
+        if (j < nvec) v = vec_load<T, VEC>(b + j * VEC);
+        else if (breg) {
+            v = vec_load<T, VEC>(breg + (j - nvec) * VEC);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) v.v[e] = sqrt_alpha * v.v[e];
+        } else v = vec_zero<T, VEC>();
+        vec_store<T, VEC>(u + j * VEC, v);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc += (double)v.v[e] * (double)v.v[e];
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+// h = v, hbar = 0, x = 0   (lsmr.py:277-278, 253)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(LSMR_THREADS) fastv_init_vectors_kernel(long long nvec, const LsmrScalars *__restrict__ S, const T *__restrict__ vhat,
+                                                                          T *__restrict__ h, T *__restrict__ hbar, T *__restrict__ x) {
+    using V = Vec<T, VEC>;
+    const T inv_alpha = (T)S->inv_alpha;
+    const V zero = vec_zero<T, VEC>();
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nvec; j += (long long)gridDim.x * blockDim.x) {
+        V v = vec_load<T, VEC>(vhat + j * VEC);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) v.v[e] = v.v[e] * inv_alpha;
+        vec_store<T, VEC>(h + j * VEC, v);
+        vec_store<T, VEC>(hbar + j * VEC, zero);
+        vec_store<T, VEC>(x + j * VEC, zero);
+    }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(LSMR_THREADS) fastv_clip_kernel(long long nvec, const T *__restrict__ in, T *__restrict__ out, double lo, double hi) {
+    using V = Vec<T, VEC>;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nvec; j += (long long)gridDim.x * blockDim.x) {
+        V v = vec_load<T, VEC>(in + j * VEC);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            double d = (double)v.v[e];
+            d = d < lo ? lo : (d > hi ? hi : d);     // np.clip
+            v.v[e] = (T)d;
+        }
+        vec_store<T, VEC>(out + j * VEC, v);
+    }
+}
+
+// ADMM: t = B x + w_in ; v = shrink_iso(t, ell) ; w = t - v ; b_reg = v - w      (admm_linear_solver.py:208-216, 222, 239-253)
+// plain: v = B x, w = 0, b_reg = v (start of the run, :171-172).  Row-mapped like the forward kernel.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(FAST_TH) fastv_shrink_kernel(FastvGeom<T> g, const T *__restrict__ x, const T *w_in, T ell, T *v_out, T *w_out,
+                                                               T *breg_out, const T *__restrict__ x_hi, int plain) {
+    using V = Vec<T, VEC>;
+    const int x0 = (int)(blockIdx.x * FAST_TH + threadIdx.x) * VEC;
+    if (x0 >= g.nx) return;
+    const int y = (int)blockIdx.y, z = (int)blockIdx.z;
+    const long long plane = (long long)g.nx * g.ny;
+    const long long i = (long long)z * plane + (long long)y * g.nx + x0;
+    const V xc = vec_load<T, VEC>(x + i);
+    V t[3], ss;
+    // component 0: along x
+    {
+        const T right = (x0 + VEC < g.nx) ? x[i + VEC] : T(0);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const T hi = (e + 1 < VEC) ? xc.v[(e + 1) % VEC] : right;
+            t[0].v[e] = g.wx * hi + (-g.wx) * xc.v[e];
+        }
+    }
+    int nc = 1;
+    if (g.dim == 3) {   // component 1: along y
+        V hv = vec_zero<T, VEC>();
+        if (y + 1 < g.ny) hv = vec_load<T, VEC>(x + i + g.nx);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) t[1].v[e] = g.wy * hv.v[e] + (-g.wy) * xc.v[e];
+        nc = 2;
+    }
+    if (g.dim >= 2) {   // last component: along z
+        V hv = vec_zero<T, VEC>();
+        if (z + 1 < g.nz) hv = vec_load<T, VEC>(x + i + plane);
+        else if (g.slab && g.grad_hi) hv = vec_load<T, VEC>(x_hi + (long long)y * g.nx + x0);
+        V tz;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) tz.v[e] = g.wz * hv.v[e] + (-g.wz) * xc.v[e];
+        if (nc == 2) t[2] = tz;     // static register slots (no dynamically indexed local array)
+        else t[1] = tz;
+        nc += 1;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (k < nc) {
+            if (w_in) {
+                const V wv = vec_load<T, VEC>(w_in + (long long)k * g.n + i);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) t[k].v[e] = t[k].v[e] + wv.v[e];
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) ss.v[e] = (k == 0) ? t[k].v[e] * t[k].v[e] : ss.v[e] + t[k].v[e] * t[k].v[e];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (k < nc) {
+            V vk, wk, bk;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                if (plain) {
+                    vk.v[e] = t[k].v[e];
+                    wk.v[e] = T(0);
+                    bk.v[e] = t[k].v[e];
+                } else {
+                    const T nrm = sqrt_t(ss.v[e]);
+                    const bool on = nrm > ell;
+                    const T soft = max_t(nrm - ell, T(0));     // |n| = n >= 0, sign(n) = 1 where n > ell
+                    vk.v[e] = on ? soft * t[k].v[e] / nrm : T(0);
+                    wk.v[e] = t[k].v[e] - vk.v[e];
+                    bk.v[e] = vk.v[e] - wk.v[e];
+                }
+            }
+            vec_store<T, VEC>(v_out + (long long)k * g.n + i, vk);
+            vec_store<T, VEC>(w_out + (long long)k * g.n + i, wk);
+            if (breg_out) vec_store<T, VEC>(breg_out + (long long)k * g.n + i, bk);
+        }
+    }
+}

@@ -763,6 +763,63 @@ static int lsq_launch_update(nsol_lsmr_plan *pl, const LsqGeom<T> &g, cudaStream
     return NSOL_OK;
 }
 
+// number of blocks of a flat streaming kernel over nvec 16-byte vectors
+static int lsq_flat_blocks(const nsol_lsmr_plan *pl, long long nvec) {
+    long long want = (nvec + LSMR_THREADS - 1) / LSMR_THREADS;
+    const long long cap = pl->ctx->lsmr_blocks > 0 ? pl->ctx->lsmr_blocks : (long long)pl->ctx->sm_count * 8;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+template <typename T>
+static int lsq_launch_rhs(nsol_lsmr_plan *pl, const LsqGeom<T> &g, int rows_b, const void *b, const void *breg, double sa, cudaStream_t s, int *nparts) {
+    constexpr int VEC = FastvCfg<T>::VEC;
+    if (fastv_ok(pl)) {
+        const long long nvec = g.n / VEC;
+        const int nb = lsq_flat_blocks(pl, nvec * (1 + rows_b));
+        fastv_rhs_kernel<T, VEC><<<nb, LSMR_THREADS, 0, s>>>(nvec, rows_b, (const T *)b, (const T *)breg, (T)sa, (T *)pl->u, pl->part);
+        *nparts = nb;
+    } else {
+        lsmr_rhs_kernel<T><<<pl->nblocks, LSMR_THREADS, 0, s>>>(g, rows_b, (const T *)b, (const T *)breg, sa, (T *)pl->u, pl->part);
+        *nparts = pl->nblocks;
+    }
+    NSOL_LAUNCH_CHECK(pl->ctx);
+    return NSOL_OK;
+}
+
+template <typename T>
+static int lsq_launch_init_vectors(nsol_lsmr_plan *pl, const LsqGeom<T> &g, cudaStream_t s) {
+    constexpr int VEC = FastvCfg<T>::VEC;
+    T *v = (T *)pl->v, *h = (T *)pl->h, *hbar = (T *)pl->hbar, *x = (T *)pl->x;
+    if (fastv_ok(pl)) fastv_init_vectors_kernel<T, VEC><<<lsq_flat_blocks(pl, g.n / VEC), LSMR_THREADS, 0, s>>>(g.n / VEC, pl->S, v, h, hbar, x);
+    else lsmr_init_vectors_kernel<T><<<pl->nblocks, LSMR_THREADS, 0, s>>>(g.n, pl->S, v, h, hbar, x);
+    NSOL_LAUNCH_CHECK(pl->ctx);
+    return NSOL_OK;
+}
+
+template <typename T>
+static int lsq_launch_clip(nsol_lsmr_plan *pl, const LsqGeom<T> &g, void *out, double lo, double hi, cudaStream_t s) {
+    constexpr int VEC = FastvCfg<T>::VEC;
+    if (fastv_ok(pl)) fastv_clip_kernel<T, VEC><<<lsq_flat_blocks(pl, g.n / VEC), LSMR_THREADS, 0, s>>>(g.n / VEC, (const T *)pl->x, (T *)out, lo, hi);
+    else clip_kernel<T><<<pl->nblocks, LSMR_THREADS, 0, s>>>(g.n, (const T *)pl->x, (T *)out, lo, hi);
+    NSOL_LAUNCH_CHECK(pl->ctx);
+    return NSOL_OK;
+}
+
+template <typename T>
+static int lsq_launch_shrink(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *x, const void *w_in, double ell, void *v, void *w, void *breg,
+                             const void *x_hi, int plain, cudaStream_t s) {
+    constexpr int VEC = FastvCfg<T>::VEC;
+    if (fastv_ok(pl)) {
+        const dim3 vgrid((g.nx / VEC + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
+        fastv_shrink_kernel<T, VEC><<<vgrid, FAST_TH, 0, s>>>(make_fastv_geom<T>(g), (const T *)x, (const T *)w_in, (T)ell, (T *)v, (T *)w, (T *)breg,
+                                                              (const T *)x_hi, plain);
+    } else {
+        admm_shrink_kernel<T><<<pl->nblocks, LSMR_THREADS, 0, s>>>(g, (const T *)x, (const T *)w_in, (T)ell, (T *)v, (T *)w, (T *)breg, (const T *)x_hi, plain);
+    }
+    NSOL_LAUNCH_CHECK(pl->ctx);
+    return NSOL_OK;
+}
+
 template <typename T>
 static int lsmr_solve_t(nsol_lsmr_plan *pl, double alpha, const void *b_dev, const void *breg_dev, int maxiter, double lo, double hi,
                         void *x_out, cudaStream_t s) {
@@ -778,9 +835,9 @@ static int lsmr_solve_t(nsol_lsmr_plan *pl, double alpha, const void *b_dev, con
     T *u = (T *)pl->u, *v = (T *)pl->v, *h = (T *)pl->h, *hbar = (T *)pl->hbar, *x = (T *)pl->x;
     double *part = pl->part;
 
-    lsmr_rhs_kernel<T><<<nb, th, 0, s>>>(ge, rows_b, (const T *)b_dev, (const T *)breg_dev, sa, u, part);
-    NSOL_LAUNCH_CHECK(ctx);
-    lsmr_scalar_init_beta<<<1, th, 0, s>>>(pl->S, part, nb, sa, maxiter);
+    int rhs_parts = 0;
+    NSOL_CHECK(lsq_launch_rhs<T>(pl, ge, rows_b, b_dev, breg_dev, sa, s, &rhs_parts));
+    lsmr_scalar_init_beta<<<1, 1024, 0, s>>>(pl->S, part, rhs_parts, sa, maxiter);
     NSOL_LAUNCH_CHECK(ctx);
     if (g.ny > 65535 || g.nz > 65535)
         return nsol_fail(ctx, NSOL_EINVAL, "lsmr (multi-kernel path): more than 65535 rows along y or z are not supported");
@@ -788,8 +845,7 @@ static int lsmr_solve_t(nsol_lsmr_plan *pl, double alpha, const void *b_dev, con
     NSOL_CHECK(lsq_launch_adj<T>(pl, ge, nullptr, nullptr, 1, nullptr, s, &rparts));
     lsmr_scalar_init_alpha<<<1, 1024, 0, s>>>(pl->S, part, rparts);
     NSOL_LAUNCH_CHECK(ctx);
-    lsmr_init_vectors_kernel<T><<<nb, th, 0, s>>>(g.n, pl->S, v, h, hbar, x);
-    NSOL_LAUNCH_CHECK(ctx);
+    NSOL_CHECK(lsq_launch_init_vectors<T>(pl, ge, s));
     for (int it = 0; it < maxiter; ++it) {
         NSOL_CHECK(lsq_launch_fwd<T>(pl, ge, nullptr, nullptr, nullptr, s, &rparts));
         lsmr_scalar_beta<<<1, 1024, 0, s>>>(pl->S, part, rparts);
@@ -801,8 +857,7 @@ static int lsmr_solve_t(nsol_lsmr_plan *pl, double alpha, const void *b_dev, con
         lsmr_scalar_tests<<<1, 1024, 0, s>>>(pl->S, part, rparts);
         NSOL_LAUNCH_CHECK(ctx);
     }
-    clip_kernel<T><<<nb, th, 0, s>>>(g.n, x, (T *)x_out, lo, hi);
-    NSOL_LAUNCH_CHECK(ctx);
+    NSOL_CHECK(lsq_launch_clip<T>(pl, ge, x_out, lo, hi, s));
     return NSOL_OK;
 }
 
@@ -1001,8 +1056,7 @@ static int admm_iterations_t(nsol_lsmr_plan *pl, double alpha, double rho, int i
         // x <- clip(lsmr([A; sqrt(rho) B], [b; sqrt(rho)(v - w)]), 0, inf)   (:205, :220-237; x0 is not passed to lsmr)
         NSOL_CHECK(lsmr_solve_any(pl, rho, b_dev, breg, iter_max, 0.0, INFINITY, x_dev, st));
         // t = B x + w ; v = prox_g(t, alpha/rho) ; w = t - v   (:208-216)
-        admm_shrink_kernel<T><<<nb, th, 0, st>>>(g, (const T *)x_dev, w, (T)(alpha / rho), v, w, breg);
-        NSOL_LAUNCH_CHECK(ctx);
+        NSOL_CHECK(lsq_launch_shrink<T>(pl, g, x_dev, w, alpha / rho, v, w, breg, nullptr, 0, st));
         return NSOL_OK;
     };
     const int coop = lsmr_use_coop(pl);
@@ -1246,9 +1300,8 @@ static int lsmr_slab_phase_t(nsol_lsmr_plan *pl, int phase, double p0, double p1
     int rparts = 0;
     switch (phase) {
     case NSOL_PH_RHS:            // u = [b; sqrt_alpha b_reg]; p0 = sqrt_alpha, i0 = 0: b_reg = 0  -> ss
-        lsmr_rhs_kernel<T><<<nb, th, 0, s>>>(g, pl->rows_b, (const T *)pl->bbuf, i0 ? (const T *)pl->breg : (const T *)nullptr, p0, u, part);
-        NSOL_LAUNCH_CHECK(ctx);
-        lsmr_reduce_ss_kernel<<<1, 1024, 0, s>>>(pl->S, part, nb, pl->ssbuf, 1);
+        NSOL_CHECK(lsq_launch_rhs<T>(pl, g, pl->rows_b, pl->bbuf, i0 ? pl->breg : nullptr, p0, s, &rparts));
+        lsmr_reduce_ss_kernel<<<1, 1024, 0, s>>>(pl->S, part, rparts, pl->ssbuf, 1);
         break;
     case NSOL_PH_SCAL_INIT_BETA:  // p0 = sqrt_alpha, i0 = maxiter
         lsmr_scalar_init_beta<<<1, 32, 0, s>>>(pl->S, pl->ssbuf, 1, p0, i0);
@@ -1261,8 +1314,8 @@ static int lsmr_slab_phase_t(nsol_lsmr_plan *pl, int phase, double p0, double p1
     case NSOL_PH_SCAL_INIT_ALPHA:
         lsmr_scalar_init_alpha<<<1, 32, 0, s>>>(pl->S, pl->ssbuf, 1);
         NSOL_LAUNCH_CHECK(ctx);
-        lsmr_init_vectors_kernel<T><<<nb, th, 0, s>>>(g.n, pl->S, v, h, hbar, x);
-        break;
+        NSOL_CHECK(lsq_launch_init_vectors<T>(pl, g, s));
+        return NSOL_OK;
     case NSOL_PH_FWD:            // needs the V halos -> ss
         NSOL_CHECK(lsq_launch_fwd<T>(pl, g, pl->halo_v_lo, pl->halo_v_hi, pl->halo_v_hi, s, &rparts));
         lsmr_reduce_ss_kernel<<<1, 1024, 0, s>>>(pl->S, part, rparts, pl->ssbuf, 0);
@@ -1281,16 +1334,14 @@ static int lsmr_slab_phase_t(nsol_lsmr_plan *pl, int phase, double p0, double p1
         lsmr_scalar_tests<<<1, 32, 0, s>>>(pl->S, pl->ssbuf, 1);
         break;
     case NSOL_PH_CLIP:           // xbuf = clip(x, p0, p1)
-        clip_kernel<T><<<nb, th, 0, s>>>(g.n, x, (T *)pl->xbuf, p0, p1);
-        break;
+        NSOL_CHECK(lsq_launch_clip<T>(pl, g, pl->xbuf, p0, p1, s));
+        return NSOL_OK;
     case NSOL_PH_ADMM_INIT:      // needs the X halo: v = grad(xbuf), w = 0, b_reg = v
-        admm_shrink_kernel<T><<<nb, th, 0, s>>>(g, (const T *)pl->xbuf, (const T *)nullptr, T(0), (T *)pl->admm_v, (T *)pl->admm_w,
-                                                (T *)pl->breg, (const T *)pl->halo_x_hi, 1);
-        break;
+        NSOL_CHECK(lsq_launch_shrink<T>(pl, g, pl->xbuf, nullptr, 0.0, pl->admm_v, pl->admm_w, pl->breg, pl->halo_x_hi, 1, s));
+        return NSOL_OK;
     case NSOL_PH_ADMM_SHRINK:    // needs the X halo: p0 = ell = alpha / rho
-        admm_shrink_kernel<T><<<nb, th, 0, s>>>(g, (const T *)pl->xbuf, (const T *)pl->admm_w, (T)p0, (T *)pl->admm_v, (T *)pl->admm_w,
-                                                (T *)pl->breg, (const T *)pl->halo_x_hi, 0);
-        break;
+        NSOL_CHECK(lsq_launch_shrink<T>(pl, g, pl->xbuf, pl->admm_w, p0, pl->admm_v, pl->admm_w, pl->breg, pl->halo_x_hi, 0, s));
+        return NSOL_OK;
     default:
         return nsol_fail(ctx, NSOL_EINVAL, "lsmr slab: unknown phase %d", phase);
     }
