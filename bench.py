@@ -528,7 +528,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic("f64" if args.dtype == "float64" else "f32", nvox_loc), "peak_source": peak_src, "kernel": kernel_name,
                          "algorithmic_bytes_per_launch": 11 * esz * nvox_loc, "avg_launch_ms": main_res["iter_ms"],
-                         "copy_gbs_this_gpu": copy_gbs, "frac_of_copy_this_gpu": achieved / copy_gbs},
+                         "copy_gbs_this_gpu": copy_gbs, "frac_of_copy_this_gpu": achieved / copy_gbs,
+                         "frac_of_nominal_8000_gbs": achieved / 8000.0},
         }
         if "e2e" in main_res:
             line["e2e"] = main_res["e2e"]
