@@ -1003,9 +1003,13 @@ static void pd_tiling(const nsol_ctx *ctx, const GridView &gv, int vecw, int *ty
     const int tile_w = (has_y ? 32 : 128) * vecw;
     int zc = ctx->pd_zc;
     if (zc <= 0) {
-        // measured on B200 at 512^3 (profiles/r1_tuning.md): 16 planes per chunk; shorter chunks only
-        // when the volume would otherwise give fewer than ~4 CTAs per SM
-        zc = 16;
+        // measured on B200 at 512^3: 16 planes per chunk for the register-pipelined kernels (profiles/r1_tuning.md),
+        // 8 for the TMA bulk-async kernel since its instruction count was cut (profiles/r1_tuning_v2.log: 4 planes
+        // 0.950, 6 0.986, 8 0.991, 10 0.985, 12 0.978, 16 0.969 of the roofline, 24 0.958, 32 0.938, 128 0.890);
+        // shorter chunks only when the volume would otherwise give fewer than ~4 CTAs per SM
+        const bool bulk = has_y && vecw > 1 && (ctx->pd_variant == 2 || (ctx->pd_variant == 0 && gv.dtype == NSOL_F64 && NSOL_PD_DEFAULT_VARIANT_F64 == 2) ||
+                                                (ctx->pd_variant == 0 && gv.dtype == NSOL_F32 && NSOL_PD_DEFAULT_VARIANT_F32 == 2));
+        zc = bulk ? 8 : 16;
         const long long tiles = (long long)((gv.nx + tile_w - 1) / tile_w) * (has_y ? (gv.ny + ty - 1) / ty : 1) * gv.batch;
         while (zc > 4 && tiles * ((gv.nz + zc - 1) / zc) < (long long)ctx->sm_count * 4) zc /= 2;
         // thin z-slabs with the in-kernel halo exchange: keep the two boundary chunks (whose CTAs end
