@@ -825,14 +825,12 @@ static int lsmr_solve_t(nsol_lsmr_plan *pl, double alpha, const void *b_dev, con
                         void *x_out, cudaStream_t s) {
     nsol_ctx *ctx = pl->ctx;
     const LsqGeom<T> g = make_geom<T>(pl);
-    const int nb = pl->nblocks, th = LSMR_THREADS;
     // alpha <= EPS: plain system A x = b (tikhonov_linear_solver.py:241-248)
     const bool use_b = alpha > 1e-10 && pl->rows_b > 0;
     LsqGeom<T> ge = g;
     if (!use_b) ge.b_op = NSOL_B_NONE;
     const int rows_b = use_b ? pl->rows_b : 0;
     const double sa = use_b ? sqrt(alpha) : 0.0;
-    T *u = (T *)pl->u, *v = (T *)pl->v, *h = (T *)pl->h, *hbar = (T *)pl->hbar, *x = (T *)pl->x;
     double *part = pl->part;
 
     int rhs_parts = 0;
@@ -1043,7 +1041,6 @@ static int admm_iterations_t(nsol_lsmr_plan *pl, double alpha, double rho, int i
                              double x_scale, double *iterates_host, cudaStream_t s) {
     nsol_ctx *ctx = pl->ctx;
     const LsqGeom<T> g = make_geom<T>(pl);
-    const int nb = pl->nblocks, th = LSMR_THREADS;
     const size_t n = (size_t)pl->gv.n;
     T *v = (T *)pl->admm_v, *w = (T *)pl->admm_w, *breg = (T *)pl->breg;
     // v = B(x0) - b_reg (b_reg = 0), w = 0  (admm_linear_solver.py:171-172): shrink with ell < 0 keeps v = t
@@ -1135,7 +1132,7 @@ extern "C" int nsol_admm_run_dev(nsol_lsmr_plan *pl, double alpha, double rho, i
     if (!b_dev || !x0_dev || !x_dev) return nsol_fail(ctx, NSOL_EINVAL, "admm run: NULL array");
     NSOL_CHECK(admm_check(pl, alpha, rho, iterations, iter_max));
     NSOL_CHECK(nsol_bind_device(ctx));
-    cudaStream_t st;
+    cudaStream_t st = nullptr;
     NSOL_CHECK(admm_stream(pl, s, &st));
     if (x_dev != x0_dev) NSOL_CUDA(ctx, cudaMemcpyAsync(x_dev, x0_dev, (size_t)pl->gv.n * pl->esz, cudaMemcpyDeviceToDevice, st));
     if (pl->gv.dtype == NSOL_F32) return admm_iterations_t<float>(pl, alpha, rho, iterations, iter_max, b_dev, x_dev, 1.0, nullptr, st);
@@ -1151,7 +1148,7 @@ extern "C" int nsol_admm_run_host(nsol_lsmr_plan *pl, double alpha, double rho, 
     if (in_scale == 0.0 || out_scale == 0.0) return nsol_fail(ctx, NSOL_EINVAL, "admm run: scales must be non-zero");
     NSOL_CHECK(admm_check(pl, alpha, rho, iterations, iter_max));
     NSOL_CHECK(nsol_bind_device(ctx));
-    cudaStream_t st;
+    cudaStream_t st = nullptr;
     NSOL_CHECK(admm_stream(pl, s, &st));
     const size_t n = (size_t)pl->gv.n;
     NSOL_CHECK(lsq_ensure_stage(pl, 2 * n * sizeof(double)));
@@ -1293,8 +1290,6 @@ template <typename T>
 static int lsmr_slab_phase_t(nsol_lsmr_plan *pl, int phase, double p0, double p1, int i0, cudaStream_t s) {
     nsol_ctx *ctx = pl->ctx;
     const LsqGeom<T> g = make_geom<T>(pl);
-    const int nb = pl->nblocks, th = LSMR_THREADS;
-    T *u = (T *)pl->u, *v = (T *)pl->v, *h = (T *)pl->h, *hbar = (T *)pl->hbar, *x = (T *)pl->x;
     double *part = pl->part;
     if (g.ny > 65535 || g.nz > 65535) return nsol_fail(ctx, NSOL_EINVAL, "lsmr slab: more than 65535 rows along y or z are not supported");
     int rparts = 0;
@@ -1482,7 +1477,7 @@ extern "C" int nsol_pd_deconv_run_host(nsol_lsmr_plan *pl, const nsol_pd_desc *p
     if (gv.dim != pl->gv.dim || gv.nx != pl->gv.nx || gv.ny != pl->gv.ny || gv.nz != pl->gv.nz || gv.dtype != pl->gv.dtype || gv.batch != 1)
         return nsol_fail(ctx, NSOL_EINVAL, "pd deconvolution: pd.grid must equal the plan's grid (batch 1)");
     NSOL_CHECK(nsol_bind_device(ctx));
-    cudaStream_t st;
+    cudaStream_t st = nullptr;
     NSOL_CHECK(admm_stream(pl, s, &st));
     const size_t n = (size_t)pl->gv.n;
     NSOL_CHECK(lsq_ensure_stage(pl, 2 * n * sizeof(double)));
