@@ -139,3 +139,44 @@ def test_gaussian_mask_is_separable_for_diagonal_cov():
     rec = np.multiply.outer(np.multiply.outer(taps[0], taps[1]), taps[2])
     assert np.max(np.abs(rec - m)) < 1e-16
     assert kernels.separable_taps(kernels.Kernels2D().get_gaussian(np.array([[1.0, 0.6], [0.6, 2.0]]))) is None
+
+
+def test_lsmr_plan_cache_keys_on_operators_grid_and_dtype(monkeypatch):
+    """linear_solver.acquire_lsmr_plan: a solver object keeps its device plan across run() calls and gets a new one
+    (the old one released) when the blur taps, the grid, B or the dtype change."""
+    import nsol_b200.linear_solver as ls
+    made, closed = [], []
+
+    class FakePlan(object):
+        def __init__(self, info, dtype):
+            self.handle = object()
+            made.append((info["shape"], dtype))
+
+        def close(self):
+            closed.append(self)
+            self.handle = None
+
+    monkeypatch.setattr(ls, "LsmrPlan", FakePlan)
+
+    class Op(object):
+        def __init__(self, taps):
+            self.taps = taps
+
+    class Owner(object):
+        pass
+
+    t3 = [np.array([0.25, 0.5, 0.25])] * 2
+    info = dict(shape=(8, 6), spacing=(1.0, 1.0), a_kind="conv", b_kind="grad", a_op=Op(t3))
+    o = Owner()
+    p1 = ls.acquire_lsmr_plan(o, info, None)
+    assert ls.acquire_lsmr_plan(o, dict(info, a_op=Op([t.copy() for t in t3])), "float64") is p1     # equal taps, same dtype
+    p2 = ls.acquire_lsmr_plan(o, dict(info, a_op=Op([np.array([0.2, 0.6, 0.2])] * 2)), None)
+    assert p2 is not p1 and closed == [p1]
+    p3 = ls.acquire_lsmr_plan(o, dict(info, a_op=Op([np.array([0.2, 0.6, 0.2])] * 2)), "float32")
+    p4 = ls.acquire_lsmr_plan(o, dict(info, a_op=Op([np.array([0.2, 0.6, 0.2])] * 2), shape=(8, 8)), "float32")
+    p5 = ls.acquire_lsmr_plan(o, dict(info, a_op=Op([np.array([0.2, 0.6, 0.2])] * 2), shape=(8, 8), b_kind="identity"), "float32")
+    assert len({id(p) for p in (p1, p2, p3, p4, p5)}) == 5 and closed == [p1, p2, p3, p4]
+    ls.release_lsmr_plan(o)
+    assert closed[-1] is p5 and o._lsmr_plan_cache is None
+    ls.release_lsmr_plan(o)          # idempotent
+    assert len(made) == 5
