@@ -871,3 +871,116 @@ __global__ void __launch_bounds__(FAST_TH) fastv_shrink_kernel(FastvGeom<T> g, c
         }
     }
 }
+
+// =====================================================================================================
+// Vector versions of the primal-dual deconvolution kernels (pdd_dual / pdd_arg / pdd_relax in lsmr_kernels.cu):
+// same arithmetic per element (the divisions of the reference are kept), row-mapped, 16 bytes of x per thread.
+// =====================================================================================================
+// p <- prox_g*(p + sigma grad(xbar))   (primal_dual_solver.py:242-243; proximal_operators.py:139-140, 157-159)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(FAST_TH) fastv_pdd_dual_kernel(FastvGeom<T> g, const T *__restrict__ xbar, T *__restrict__ p, T sigma, T den, int reg) {
+    using V = Vec<T, VEC>;
+    const int x0 = (int)(blockIdx.x * FAST_TH + threadIdx.x) * VEC;
+    if (x0 >= g.nx) return;
+    const int y = (int)blockIdx.y, z = (int)blockIdx.z;
+    const long long plane = (long long)g.nx * g.ny;
+    const long long i = (long long)z * plane + (long long)y * g.nx + x0;
+    const V xc = vec_load<T, VEC>(xbar + i);
+    auto finish = [&](int k, const V &gk) {
+        V q = vec_load<T, VEC>(p + (long long)k * g.n + i);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            T v = q.v[e] + sigma * gk.v[e];
+            if (reg != NSOL_REG_TV) v = v / den;
+            if (reg != NSOL_REG_TK1) v = v / max_t(T(1), abs_t(v));
+            q.v[e] = v;
+        }
+        vec_store<T, VEC>(p + (long long)k * g.n + i, q);
+    };
+    {
+        const T right = (x0 + VEC < g.nx) ? xbar[i + VEC] : T(0);
+        V gk;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const T hi = (e + 1 < VEC) ? xc.v[(e + 1) % VEC] : right;
+            gk.v[e] = g.wx * hi + (-g.wx) * xc.v[e];
+        }
+        finish(0, gk);
+    }
+    if (g.dim == 3) {
+        V hv = vec_zero<T, VEC>(), gk;
+        if (y + 1 < g.ny) hv = vec_load<T, VEC>(xbar + i + g.nx);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) gk.v[e] = g.wy * hv.v[e] + (-g.wy) * xc.v[e];
+        finish(1, gk);
+    }
+    if (g.dim >= 2) {
+        V hv = vec_zero<T, VEC>(), gk;
+        if (z + 1 < g.nz) hv = vec_load<T, VEC>(xbar + i + plane);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) gk.v[e] = g.wz * hv.v[e] + (-g.wz) * xc.v[e];
+        finish(g.dim - 1, gk);
+    }
+}
+
+// b_reg <- (x - tau grad_adj(p)) / prox_scale   (primal_dual_solver.py:246; tikhonov b_reg / x_scale)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(FAST_TH) fastv_pdd_arg_kernel(FastvGeom<T> g, const T *__restrict__ x, const T *__restrict__ p, T tau, T prox_scale,
+                                                                T *__restrict__ breg) {
+    using V = Vec<T, VEC>;
+    const int x0 = (int)(blockIdx.x * FAST_TH + threadIdx.x) * VEC;
+    if (x0 >= g.nx) return;
+    const int y = (int)blockIdx.y, z = (int)blockIdx.z;
+    const long long plane = (long long)g.nx * g.ny;
+    const long long i = (long long)z * plane + (long long)y * g.nx + x0;
+    V div;
+    {
+        const T *pk = p;
+        const V pv = vec_load<T, VEC>(pk + i);
+        const T left = (x0 > 0) ? pk[i - 1] : T(0);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const T lo = (e == 0) ? left : pv.v[(e + VEC - 1) % VEC];
+            div.v[e] = g.wx * lo + (-g.wx) * pv.v[e];
+        }
+    }
+    if (g.dim == 3) {
+        const T *pk = p + g.n;
+        const V pv = vec_load<T, VEC>(pk + i);
+        V lv = vec_zero<T, VEC>();
+        if (y > 0) lv = vec_load<T, VEC>(pk + i - g.nx);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) div.v[e] = div.v[e] + (g.wy * lv.v[e] + (-g.wy) * pv.v[e]);
+    }
+    if (g.dim >= 2) {
+        const T *pk = p + (long long)(g.dim - 1) * g.n;
+        const V pv = vec_load<T, VEC>(pk + i);
+        V lv = vec_zero<T, VEC>();
+        if (z > 0) lv = vec_load<T, VEC>(pk + i - plane);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) div.v[e] = div.v[e] + (g.wz * lv.v[e] + (-g.wz) * pv.v[e]);
+    }
+    const V xv = vec_load<T, VEC>(x + i);
+    V out;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) out.v[e] = (xv.v[e] - tau * div.v[e]) / prox_scale;
+    vec_store<T, VEC>(breg + i, out);
+}
+
+// x+ = y * prox_scale ; xbar = x+ + theta (x+ - x) ; x = x+   (solver.py:117-118; primal_dual_solver.py:253)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(LSMR_THREADS) fastv_pdd_relax_kernel(long long nvec, const T *__restrict__ yv, T prox_scale, T theta, T *__restrict__ x,
+                                                                       T *__restrict__ xbar) {
+    using V = Vec<T, VEC>;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nvec; j += (long long)gridDim.x * blockDim.x) {
+        const V a = vec_load<T, VEC>(yv + j * VEC), xo = vec_load<T, VEC>(x + j * VEC);
+        V xn, xb;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            xn.v[e] = a.v[e] * prox_scale;
+            xb.v[e] = xn.v[e] + theta * (xn.v[e] - xo.v[e]);
+        }
+        vec_store<T, VEC>(xbar + j * VEC, xb);
+        vec_store<T, VEC>(x + j * VEC, xn);
+    }
+}

@@ -1421,6 +1421,10 @@ static int pd_deconv_t(nsol_lsmr_plan *pl, const nsol_pd_desc *pd, int iteration
     LsqGeom<T> g = make_geom<T>(pl);
     const int nb = pl->nblocks, th = LSMR_THREADS;
     const size_t n = (size_t)pl->gv.n;
+    constexpr int VEC = FastvCfg<T>::VEC;
+    const bool vec = fastv_ok(pl) && g.ny <= 65535 && g.nz <= 65535;      // row-mapped 128-bit kernels (csrc/lsmr_fastv.cuh)
+    const FastvGeom<T> fg = make_fastv_geom<T>(g);
+    const dim3 vgrid((g.nx / VEC + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
     // state: x = pl->xbuf, xbar = pl->h reuse is not possible (LSMR owns h) -> admm_v holds [xbar | y | spare], admm_w holds p
     T *x = (T *)pl->xbuf, *xbar = (T *)pl->admm_v, *p = (T *)pl->admm_w, *breg = (T *)pl->breg;
     T *y = (pl->gv.dim >= 2) ? xbar + n : nullptr;
@@ -1438,14 +1442,22 @@ static int pd_deconv_t(nsol_lsmr_plan *pl, const nsol_pd_desc *pd, int iteration
     if (iterates_host) rc = lsq_download(pl, x, pd->x_scale, iterates_host, s);
     for (int it = 0; it < iterations && rc == NSOL_OK; ++it) {
         const double *r = &rows[(size_t)it * 8];
-        pdd_dual_kernel<T><<<nb, th, 0, s>>>(g, xbar, p, (T)r[0], (T)r[4], pd->reg);
-        ctx->launches++;
-        pdd_arg_kernel<T><<<nb, th, 0, s>>>(g, x, p, (T)r[1], (T)prox_scale, breg);
-        ctx->launches++;
+        if (vec) {
+            fastv_pdd_dual_kernel<T, VEC><<<vgrid, FAST_TH, 0, s>>>(fg, xbar, p, (T)r[0], (T)r[4], pd->reg);
+            ctx->launches++;
+            fastv_pdd_arg_kernel<T, VEC><<<vgrid, FAST_TH, 0, s>>>(fg, x, p, (T)r[1], (T)prox_scale, breg);
+            ctx->launches++;
+        } else {
+            pdd_dual_kernel<T><<<nb, th, 0, s>>>(g, xbar, p, (T)r[0], (T)r[4], pd->reg);
+            ctx->launches++;
+            pdd_arg_kernel<T><<<nb, th, 0, s>>>(g, x, p, (T)r[1], (T)prox_scale, breg);
+            ctx->launches++;
+        }
         // tikhonov: alpha = 1 / (tau * lambda), b_reg = y / prox_scale, B = I  (proximal_operators.py:58-75)
         rc = lsmr_solve_any(pl, 1.0 / r[2], pl->bbuf, breg, iter_max, 0.0, INFINITY, ybuf, s);
         if (rc != NSOL_OK) break;
-        pdd_relax_kernel<T><<<nb, th, 0, s>>>((long long)n, (const T *)ybuf, (T)prox_scale, (T)r[3], x, xbar);
+        if (vec) fastv_pdd_relax_kernel<T, VEC><<<lsq_flat_blocks(pl, (long long)n / VEC), th, 0, s>>>((long long)n / VEC, (const T *)ybuf, (T)prox_scale, (T)r[3], x, xbar);
+        else pdd_relax_kernel<T><<<nb, th, 0, s>>>((long long)n, (const T *)ybuf, (T)prox_scale, (T)r[3], x, xbar);
         ctx->launches++;
         if (iterates_host) rc = lsq_download(pl, x, pd->x_scale, iterates_host + (size_t)(it + 1) * n, s);
     }
