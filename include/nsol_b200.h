@@ -280,6 +280,11 @@ int nsol_tikhonov_run_host(nsol_lsmr_plan *plan, double alpha, double in_scale, 
 int nsol_admm_run_host(nsol_lsmr_plan *plan, double alpha, double rho, int iterations, int iter_max,
                        double in_scale, double out_scale, const double *b_host, const double *x0_host,
                        double *x_host, double *iterates_host, nsol_stream s);
+/* ADMMLinearSolver(..., b_reg=...): the solver's own offset of the regulariser rows
+ * (nsol/admm_linear_solver.py:100, used at :171 v0 = B x0 - b_reg, :208 t = B x + w - b_reg,
+ * :222 Tikhonov b_reg = v - w + b_reg).  dim*N float64 host values, divided by in_scale (= x_scale);
+ * kept by the plan for every following nsol_admm_run_*.  NULL restores the default b_reg = 0. */
+int nsol_admm_set_b_reg_host(nsol_lsmr_plan *plan, const double *b_reg_host, double in_scale, nsol_stream s);
 /* PrimalDualSolver.run() + get_x() for the deconvolution wiring
  * (nsol/deconvolution_solver_parameter_study_interface.py:255-280, 303-325):
  *   prox_g_conj in {tv, huber}, B = grad, and

@@ -110,6 +110,7 @@ SIGNATURES = {
                                          C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "nsol_admm_run_host": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsol_admm_set_b_reg_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "nsol_pd_deconv_run_host": (C.c_int, [C.c_void_p, C.POINTER(PdDesc), C.c_int, C.c_int, C.c_double, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsol_admm_run_dev": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p,
@@ -287,7 +288,14 @@ class _PinnedArray(np.ndarray):
         return obj
 
     def __array_finalize__(self, obj):
-        self._nsol_owner = getattr(obj, "_nsol_owner", None)
+        # only views of the page-locked buffer keep it alive; arrays numpy allocates for results derived from
+        # this one (ufunc outputs, copies: base is None) must not pin it
+        self._nsol_owner = getattr(obj, "_nsol_owner", None) if self.base is not None else None
+
+    def __array_wrap__(self, out_arr, context=None, return_scalar=False):
+        # results of arithmetic on a solver result are plain ndarrays, as with the reference
+        out = np.asarray(out_arr).view(np.ndarray) if isinstance(out_arr, np.ndarray) else out_arr
+        return out[()] if return_scalar else out
 
 
 class DeviceBuffer(object):

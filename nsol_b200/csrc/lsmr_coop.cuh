@@ -38,6 +38,7 @@ struct CoopArgs {
     int admm_iters;
     T ell;
     T *admm_v, *admm_w;
+    const T *admm_c;              // the ADMM solver's own b_reg (dim * N) or NULL
 };
 
 // Row-wise work distribution for the stencil phases: a work item is a run of up to COOP_RUN
@@ -308,6 +309,7 @@ __global__ void __launch_bounds__(LSMR_THREADS) lsmr_coop_kernel(const CoopArgs<
                 for (int k = 0; k < g.dim; ++k) {
                     const T hi = (idx[g.axis[k]] + 1 < g.extent[k]) ? a.xout[i + g.stride[k]] : T(0);
                     T tk = g.w[k] * hi + (-g.w[k]) * xc + a.admm_w[(long long)k * n + i];
+                    if (a.admm_c) tk = tk - a.admm_c[(long long)k * n + i];
                     t[k] = tk;
                     ss = (k == 0) ? tk * tk : ss + tk * tk;
                 }
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(LSMR_THREADS) lsmr_coop_kernel(const CoopArgs<
                     const T wk = t[k] - vk;
                     a.admm_v[(long long)k * n + i] = vk;
                     a.admm_w[(long long)k * n + i] = wk;
-                    a.breg[(long long)k * n + i] = vk - wk;
+                    a.breg[(long long)k * n + i] = a.admm_c ? (vk - wk) + a.admm_c[(long long)k * n + i] : vk - wk;
                 }
             });
             grid.sync();

@@ -797,7 +797,7 @@ __global__ void __launch_bounds__(LSMR_THREADS) fastv_clip_kernel(long long nvec
 // plain: v = B x, w = 0, b_reg = v (start of the run, :171-172).  Row-mapped like the forward kernel.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(FAST_TH) fastv_shrink_kernel(FastvGeom<T> g, const T *__restrict__ x, const T *w_in, T ell, T *v_out, T *w_out,
-                                                               T *breg_out, const T *__restrict__ x_hi, int plain) {
+                                                               T *breg_out, const T *__restrict__ x_hi, int plain, const T *__restrict__ c) {
     using V = Vec<T, VEC>;
     const int x0 = (int)(blockIdx.x * FAST_TH + threadIdx.x) * VEC;
     if (x0 >= g.nx) return;
@@ -842,6 +842,11 @@ __global__ void __launch_bounds__(FAST_TH) fastv_shrink_kernel(FastvGeom<T> g, c
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) t[k].v[e] = t[k].v[e] + wv.v[e];
             }
+            if (c) {       // the solver's own b_reg: t = B x + w - c   (admm_linear_solver.py:208)
+                const V cv = vec_load<T, VEC>(c + (long long)k * g.n + i);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) t[k].v[e] = t[k].v[e] - cv.v[e];
+            }
 #pragma unroll
             for (int e = 0; e < VEC; ++e) ss.v[e] = (k == 0) ? t[k].v[e] * t[k].v[e] : ss.v[e] + t[k].v[e] * t[k].v[e];
         }
@@ -864,6 +869,11 @@ __global__ void __launch_bounds__(FAST_TH) fastv_shrink_kernel(FastvGeom<T> g, c
                     wk.v[e] = t[k].v[e] - vk.v[e];
                     bk.v[e] = vk.v[e] - wk.v[e];
                 }
+            }
+            if (c && breg_out) {       // b_reg of the next solve = v - w + c   (:222)
+                const V cv = vec_load<T, VEC>(c + (long long)k * g.n + i);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) bk.v[e] = bk.v[e] + cv.v[e];
             }
             vec_store<T, VEC>(v_out + (long long)k * g.n + i, vk);
             vec_store<T, VEC>(w_out + (long long)k * g.n + i, wk);

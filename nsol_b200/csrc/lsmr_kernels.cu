@@ -469,11 +469,13 @@ __global__ void clip_kernel(long long n, const T *__restrict__ in, T *__restrict
     }
 }
 
-// ADMM: t = B x + w_in ; v = shrink_iso(t, ell) ; w = t - v      (admm_linear_solver.py:208-216, 239-253)
-// optionally also breg_out = v - w  (the b_reg of the next Tikhonov solve, :222)
+// ADMM: t = B x + w_in - c ; v = shrink_iso(t, ell) ; w = t - v      (admm_linear_solver.py:208-216, 239-253)
+// optionally also breg_out = v - w + c  (the b_reg of the next Tikhonov solve, :222); c = the solver's own b_reg / x_scale
+// (dim * N values, NULL = 0: admm_linear_solver.py:100)
 template <typename T>
 __global__ void admm_shrink_kernel(LsqGeom<T> g, const T *__restrict__ x, const T *__restrict__ w_in, T ell, T *__restrict__ v_out,
-                                   T *__restrict__ w_out, T *__restrict__ breg_out, const T *__restrict__ x_hi = nullptr, int plain = 0) {
+                                   T *__restrict__ w_out, T *__restrict__ breg_out, const T *__restrict__ x_hi = nullptr, int plain = 0,
+                                   const T *__restrict__ c = nullptr) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += (long long)gridDim.x * blockDim.x) {
         int idx[3];
         lsq_decode(g, i, idx);
@@ -485,14 +487,15 @@ __global__ void admm_shrink_kernel(LsqGeom<T> g, const T *__restrict__ x, const 
             if (g.slab && g.grad_hi && g.axis[k] == 2 && idx[2] + 1 == g.nz) hi = x_hi[lsq_plane_off(g, idx)];
             T tk = g.w[k] * hi + (-g.w[k]) * xc;
             if (w_in) tk = tk + w_in[(long long)k * g.n + i];
+            if (c) tk = tk - c[(long long)k * g.n + i];
             t[k] = tk;
             ss = (k == 0) ? tk * tk : ss + tk * tk;
         }
-        if (plain) {      // v = B x, w = 0, b_reg = v  (start of the ADMM run, admm_linear_solver.py:171-172)
+        if (plain) {      // v = B x - c, w = 0, b_reg = v + c  (start of the ADMM run, admm_linear_solver.py:171-172, :222)
             for (int k = 0; k < g.dim; ++k) {
                 v_out[(long long)k * g.n + i] = t[k];
                 w_out[(long long)k * g.n + i] = T(0);
-                breg_out[(long long)k * g.n + i] = t[k];
+                breg_out[(long long)k * g.n + i] = c ? t[k] + c[(long long)k * g.n + i] : t[k];
             }
             continue;
         }
@@ -504,7 +507,7 @@ __global__ void admm_shrink_kernel(LsqGeom<T> g, const T *__restrict__ x, const 
             const T wk = t[k] - vk;
             v_out[(long long)k * g.n + i] = vk;
             w_out[(long long)k * g.n + i] = wk;
-            if (breg_out) breg_out[(long long)k * g.n + i] = vk - wk;
+            if (breg_out) breg_out[(long long)k * g.n + i] = c ? (vk - wk) + c[(long long)k * g.n + i] : vk - wk;
         }
     }
 }
@@ -527,6 +530,7 @@ struct nsol_lsmr_plan {
     void *opbuf = nullptr, *optmp = nullptr;   // A v / A^T u and separable scratch
     void *breg = nullptr;                      // b_reg staging (rows_b * N)
     void *admm_v = nullptr, *admm_w = nullptr; // ADMM split variables (dim * N each)
+    void *admm_c = nullptr;                    // the ADMM solver's own b_reg / x_scale (dim * N; NULL = 0), nsol_admm_set_b_reg_host
     void *bbuf = nullptr, *xbuf = nullptr;     // scaled observation / current solution (N)
     void *stage = nullptr;                     // float64 host-transfer staging
     size_t stage_bytes = 0;
@@ -551,7 +555,7 @@ struct nsol_lsmr_plan {
 extern "C" void nsol_lsmr_plan_destroy(nsol_lsmr_plan *pl) {
     if (!pl) return;
     if (pl->ctx) nsol_bind_device(pl->ctx);
-    void *ptrs[] = {pl->u, pl->v, pl->h, pl->hbar, pl->x, pl->opbuf, pl->optmp, pl->breg, pl->admm_v, pl->admm_w,
+    void *ptrs[] = {pl->u, pl->v, pl->h, pl->hbar, pl->x, pl->opbuf, pl->optmp, pl->breg, pl->admm_v, pl->admm_w, pl->admm_c,
                     pl->bbuf, pl->xbuf, pl->stage, pl->part, pl->S, pl->taps_dev, pl->coop_part,
                     pl->halo_v_lo, pl->halo_v_hi, pl->halo_u_lo, pl->halo_u_hi, pl->halo_uz_lo, pl->halo_x_hi, pl->ssbuf};
     for (void *p : ptrs) cudaFree(p);
@@ -812,9 +816,10 @@ static int lsq_launch_shrink(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void
     if (fastv_ok(pl)) {
         const dim3 vgrid((g.nx / VEC + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
         fastv_shrink_kernel<T, VEC><<<vgrid, FAST_TH, 0, s>>>(make_fastv_geom<T>(g), (const T *)x, (const T *)w_in, (T)ell, (T *)v, (T *)w, (T *)breg,
-                                                              (const T *)x_hi, plain);
+                                                              (const T *)x_hi, plain, (const T *)pl->admm_c);
     } else {
-        admm_shrink_kernel<T><<<pl->nblocks, LSMR_THREADS, 0, s>>>(g, (const T *)x, (const T *)w_in, (T)ell, (T *)v, (T *)w, (T *)breg, (const T *)x_hi, plain);
+        admm_shrink_kernel<T><<<pl->nblocks, LSMR_THREADS, 0, s>>>(g, (const T *)x, (const T *)w_in, (T)ell, (T *)v, (T *)w, (T *)breg, (const T *)x_hi, plain,
+                                                                   (const T *)pl->admm_c);
     }
     NSOL_LAUNCH_CHECK(pl->ctx);
     return NSOL_OK;
@@ -935,6 +940,7 @@ static int lsmr_solve_coop(nsol_lsmr_plan *pl, double alpha, const void *b_dev, 
     a.admm_iters = admm_iters;
     a.ell = (T)ell;
     a.admm_v = (T *)pl->admm_v; a.admm_w = (T *)pl->admm_w;
+    a.admm_c = (const T *)pl->admm_c;
     void *params[] = {(void *)&a};
     NSOL_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)lsmr_coop_kernel<T>, dim3(pl->coop_blocks), dim3(LSMR_THREADS), params, 0, s));
     ctx->launches++;
@@ -1045,9 +1051,14 @@ static int admm_iterations_t(nsol_lsmr_plan *pl, double alpha, double rho, int i
     T *v = (T *)pl->admm_v, *w = (T *)pl->admm_w, *breg = (T *)pl->breg;
     // v = B(x0) - b_reg (b_reg = 0), w = 0  (admm_linear_solver.py:171-172): shrink with ell < 0 keeps v = t
     // -> do it explicitly: v = grad(x0), w = 0, b_reg_next = v - w = v
-    NSOL_CHECK(nsol_grad(ctx, &pl->grid, x_dev, v, s));
-    NSOL_CUDA(ctx, cudaMemsetAsync(w, 0, n * pl->gv.dim * sizeof(T), s));
-    NSOL_CUDA(ctx, cudaMemcpyAsync(breg, v, n * pl->gv.dim * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    if (pl->admm_c) {
+        if (g.ny > 65535 || g.nz > 65535) return nsol_fail(ctx, NSOL_EINVAL, "admm: more than 65535 rows along y or z are not supported with b_reg");
+        NSOL_CHECK(lsq_launch_shrink<T>(pl, g, x_dev, nullptr, 0.0, v, w, breg, nullptr, 1, s));    // v = B x0 - c, w = 0, b_reg = v + c
+    } else {
+        NSOL_CHECK(nsol_grad(ctx, &pl->grid, x_dev, v, s));
+        NSOL_CUDA(ctx, cudaMemsetAsync(w, 0, n * pl->gv.dim * sizeof(T), s));
+        NSOL_CUDA(ctx, cudaMemcpyAsync(breg, v, n * pl->gv.dim * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    }
     if (iterates_host) NSOL_CHECK(lsq_download(pl, x_dev, x_scale, iterates_host, s));
     auto outer_iteration = [&](cudaStream_t st) -> int {
         // x <- clip(lsmr([A; sqrt(rho) B], [b; sqrt(rho)(v - w)]), 0, inf)   (:205, :220-237; x0 is not passed to lsmr)
@@ -1163,6 +1174,36 @@ extern "C" int nsol_admm_run_host(nsol_lsmr_plan *pl, double alpha, double rho, 
     else rc = admm_iterations_t<double>(pl, alpha, rho, iterations, iter_max, pl->bbuf, pl->xbuf, out_scale, iterates_host, st);
     NSOL_CHECK(rc);
     return lsq_download(pl, pl->xbuf, out_scale, x_host, st);
+}
+
+// The ADMM solver's own b_reg (ADMMLinearSolver(..., b_reg=...), nsol/admm_linear_solver.py:100): dim * N float64 host
+// values, stored as b_reg / in_scale in the plan's dtype and used by every following ADMM run
+// (v0 = B x0 - b_reg, t = B x + w - b_reg, Tikhonov b_reg = v - w + b_reg; :171, :208, :222).  NULL = 0 (default).
+extern "C" int nsol_admm_set_b_reg_host(nsol_lsmr_plan *pl, const double *b_reg_host, double in_scale, nsol_stream s) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    NSOL_CHECK(nsol_bind_device(ctx));
+    if (!b_reg_host) {
+        if (pl->admm_c) {
+            NSOL_CUDA(ctx, cudaDeviceSynchronize());
+            cudaFree(pl->admm_c);
+            pl->admm_c = nullptr;
+        }
+        return NSOL_OK;
+    }
+    if (in_scale == 0.0) return nsol_fail(ctx, NSOL_EINVAL, "admm b_reg: scale must be non-zero");
+    cudaStream_t st = nullptr;
+    NSOL_CHECK(admm_stream(pl, s, &st));
+    const size_t nreg = (size_t)pl->gv.n * pl->gv.dim;
+    if (!pl->admm_c) {
+        NSOL_CUDA(ctx, cudaMalloc(&pl->admm_c, nreg * pl->esz));
+        pl->bytes += nreg * pl->esz;
+    }
+    NSOL_CHECK(lsq_ensure_stage(pl, nreg * sizeof(double)));
+    NSOL_CUDA(ctx, cudaMemcpyAsync(pl->stage, b_reg_host, nreg * sizeof(double), cudaMemcpyHostToDevice, st));
+    NSOL_CHECK(nsol_scale_convert(ctx, (int64_t)nreg, NSOL_F64, pl->stage, pl->gv.dtype, pl->admm_c, in_scale, 1, st));
+    NSOL_CUDA(ctx, cudaStreamSynchronize(st));      // b_reg_host may be a temporary
+    return NSOL_OK;
 }
 
 extern "C" int nsol_admm_shrink(nsol_ctx *ctx, const nsol_grid *grid, const void *x_dev, const void *w_in_dev, double ell, void *v_dev,

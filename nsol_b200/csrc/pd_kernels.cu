@@ -154,16 +154,22 @@ struct ConstDiv<float> {
 // projection onto [-1, 1]: q / max(1, |q|) is q itself for |q| <= 1 and q/|q| = +-1 exactly
 // otherwise, so the reference's division (proximal_operators.py:140,159) is a clamp, bit for bit
 // float64: decided on the exponent word with integer instructions (|q| >= 1  <=>  the high word without
-// its sign is >= 0x3ff00000): 5 integer instructions instead of the ~12 of fmin(fmax()) with its NaN
-// handling.  Same bits as the division for every finite q, including +-1 and -0.
+// its sign is >= 0x3ff00000): a handful of integer instructions instead of the ~12 of fmin(fmax()) with its
+// NaN handling.  Same bits as the division for every finite q, including +-1 and -0; NaN stays NaN and
+// +-Inf becomes NaN (Inf / Inf), as in numpy -- a non-finite observation must stay visible in the result.
 __device__ __forceinline__ double clamp_unit(double q) {
     const int hi = __double2hiint(q);
-    const bool sat = (unsigned)(hi & 0x7fffffff) >= 0x3ff00000u;
-    const int rhi = sat ? ((hi & (int)0x80000000) | 0x3ff00000) : hi;
+    const unsigned mag = (unsigned)(hi & 0x7fffffff);
+    const bool sat = mag >= 0x3ff00000u;
+    int rhi = sat ? ((hi & (int)0x80000000) | 0x3ff00000) : hi;
     const int rlo = sat ? 0 : __double2loint(q);
+    rhi = mag >= 0x7ff00000u ? 0x7ff80000 : rhi;
     return __hiloint2double(rhi, rlo);
 }
-__device__ __forceinline__ float clamp_unit(float q) { return fminf(fmaxf(q, -1.0f), 1.0f); }
+__device__ __forceinline__ float clamp_unit(float q) {
+    const float c = fminf(fmaxf(q, -1.0f), 1.0f);
+    return fabsf(q) < __int_as_float(0x7f800000) ? c : __int_as_float(0x7fc00000);
+}
 
 // UNIT: spacing 1 (w == 1, every configuration of BASELINE.json): 1*a and (-1)*a are exact, so
 // fl(fl(w*hi) + fl((-w)*lo)) == fl(hi - lo) bit for bit and the two multiplications are dropped

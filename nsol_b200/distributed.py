@@ -29,6 +29,11 @@ def partition_round_robin(n_items, rank, world):
     return list(range(int(rank), int(n_items), int(world)))
 
 
+def _peer(dist, group, r):
+    """Rank ``r`` of ``group`` as the global rank the P2P ops address."""
+    return r if group is None else dist.get_global_rank(group, r)
+
+
 class HaloExchanger(object):
     """Neighbour exchange of the three boundary planes of a z-slab.
 
@@ -53,13 +58,15 @@ class HaloExchanger(object):
         dist = self.torch.distributed
         ops = []
         if self.has_above:
-            ops.append(dist.P2POp(dist.isend, xbar_last, self.rank + 1, self.group))
-            ops.append(dist.P2POp(dist.isend, pz_last, self.rank + 1, self.group))
-            ops.append(dist.P2POp(dist.irecv, self.xbar_above, self.rank + 1, self.group))
+            up = _peer(dist, self.group, self.rank + 1)
+            ops.append(dist.P2POp(dist.isend, xbar_last, up, self.group))
+            ops.append(dist.P2POp(dist.isend, pz_last, up, self.group))
+            ops.append(dist.P2POp(dist.irecv, self.xbar_above, up, self.group))
         if self.has_below:
-            ops.append(dist.P2POp(dist.isend, xbar_first, self.rank - 1, self.group))
-            ops.append(dist.P2POp(dist.irecv, self.xbar_below, self.rank - 1, self.group))
-            ops.append(dist.P2POp(dist.irecv, self.pz_below, self.rank - 1, self.group))
+            dn = _peer(dist, self.group, self.rank - 1)
+            ops.append(dist.P2POp(dist.isend, xbar_first, dn, self.group))
+            ops.append(dist.P2POp(dist.irecv, self.xbar_below, dn, self.group))
+            ops.append(dist.P2POp(dist.irecv, self.pz_below, dn, self.group))
         return dist.batch_isend_irecv(ops) if ops else []
 
     @staticmethod
@@ -98,10 +105,12 @@ class SlabPrimalDual(object):
       (``HaloExchanger``), optionally overlapped with the interior chunks (``overlap=True``).
     ``halo="auto"`` tries p2p and falls back to nccl (all ranks together, with a warning)."""
 
-    def __init__(self, ctx, desc, plane_numel, np_dtype, rank, world, device, halo="auto"):
+    def __init__(self, ctx, desc, plane_numel, np_dtype, rank, world, device, halo="auto", group=None):
         import ctypes as C
         self.C = C
         self.ctx = ctx
+        self.group = group
+        self._unchecked = False      # launches queued since the last link-status check
         self.np_dtype = np_dtype
         self.plane_numel = plane_numel
         self.device = device
@@ -130,7 +139,7 @@ class SlabPrimalDual(object):
         if self.mode == "nccl":
             import torch
             tdtype = torch.float32 if np.dtype(np_dtype) == np.float32 else torch.float64
-            self.halo = HaloExchanger(rank, world, plane_numel, tdtype, device)
+            self.halo = HaloExchanger(rank, world, plane_numel, tdtype, device, group)
             ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
             ctx.check(ctx.lib.nsol_pd_plan_set_halo(self.plan, ptr(self.halo.xbar_above), ptr(self.halo.xbar_below),
                                                    ptr(self.halo.pz_below)))
@@ -148,7 +157,7 @@ class SlabPrimalDual(object):
             err = "rank %d: %s" % (self.rank, e)
         mine = bytes(handle.raw) if err is None else None
         handles = [None] * self.world
-        dist.all_gather_object(handles, mine)
+        dist.all_gather_object(handles, mine, group=self.group)
         if any(hd is None for hd in handles):
             err = err or "a rank could not export its link block"
         else:
@@ -159,7 +168,7 @@ class SlabPrimalDual(object):
             except Exception as e:
                 err = "rank %d: %s" % (self.rank, e)
         errs = [None] * self.world
-        dist.all_gather_object(errs, err)
+        dist.all_gather_object(errs, err, group=self.group)
         errs = [e for e in errs if e]
         if errs and err is None:
             # somebody failed: this rank must not stay in link mode on its own
@@ -187,6 +196,7 @@ class SlabPrimalDual(object):
         lib, ctx, plan = self.ctx.lib, self.ctx, self.plan
         if self.mode in ("single", "p2p"):
             ctx.check(lib.nsol_pd_plan_iterate(plan, n, stream))
+            self._unchecked = self._unchecked or self.mode == "p2p"
             return
         if not overlap or lib.nsol_pd_plan_chunks(plan) < 3:
             for _ in range(n):
@@ -204,27 +214,43 @@ class SlabPrimalDual(object):
         self._halo_fresh = True     # the halos now belong to the current state
 
     def check(self, stream):
-        """Synchronise and raise if an in-kernel halo wait timed out."""
+        """Synchronise and raise if an in-kernel halo wait timed out (the iterates are then invalid: the
+        kernels carried on with stale halo planes)."""
+        self._unchecked = False
         self.ctx.check(self.ctx.lib.nsol_pd_plan_link_status(self.plan, stream))
 
-    def reset_host(self, b_host_ptr, x0_host_ptr, stream):
+    def reset_host(self, b_host_ptr, x0_host_ptr, stream, check=True):
+        """New solve.  With the in-kernel exchange, ``check`` first verifies that no halo wait of the previous
+        solve timed out (synchronises; pass False inside a timed loop and call ``check()`` afterwards)."""
+        if check and self._unchecked:
+            self.check(stream)
         self._halo_fresh = False
         self.ctx.check(self.ctx.lib.nsol_pd_plan_reset_host(self.plan, b_host_ptr, x0_host_ptr, stream))
 
-    def reset_dev(self, b_dev_ptr, x0_dev_ptr, stream):
+    def reset_dev(self, b_dev_ptr, x0_dev_ptr, stream, check=True):
+        if check and self._unchecked:
+            self.check(stream)
         self._halo_fresh = False
         self.ctx.check(self.ctx.lib.nsol_pd_plan_reset_dev(self.plan, b_dev_ptr, x0_dev_ptr, stream))
 
     def close(self):
         if self.plan is not None:
+            err = None
             if self.mode == "p2p":
                 # the neighbours' kernels write into this rank's link block: everybody finishes first
                 import torch
                 import torch.distributed as dist
                 torch.cuda.synchronize()
-                dist.barrier()
+                if self._unchecked:
+                    try:
+                        self.check(None)
+                    except RuntimeError as e:       # still tear down in lockstep with the other ranks
+                        err = e
+                dist.barrier(group=self.group)
             self.ctx.lib.nsol_pd_plan_destroy(self.plan)
             self.plan = None
+            if err is not None:
+                raise err
 
 
 # ---------------------------------------------------------------------------------------------
@@ -367,14 +393,15 @@ def exchange_slab_halos(dist, group, rank, world, items):
             continue
         # order matters when both neighbours are the same rank (world == 2, ring): the k-th send to a
         # peer pairs with the peer's k-th receive from this rank
+        gup, gdn = (_peer(dist, group, up) if has_up else up), (_peer(dist, group, dn) if has_dn else dn)
         if v["send_first"] is not None and has_dn:
-            ops.append(dist.P2POp(dist.isend, v["send_first"], dn, group))
+            ops.append(dist.P2POp(dist.isend, v["send_first"], gdn, group))
         if v["send_last"] is not None and has_up:
-            ops.append(dist.P2POp(dist.isend, v["send_last"], up, group))
+            ops.append(dist.P2POp(dist.isend, v["send_last"], gup, group))
         if v["recv_hi"] is not None and has_up and v["send_first"] is not None:
-            ops.append(dist.P2POp(dist.irecv, v["recv_hi"], up, group))
+            ops.append(dist.P2POp(dist.irecv, v["recv_hi"], gup, group))
         if v["recv_lo"] is not None and has_dn and v["send_last"] is not None:
-            ops.append(dist.P2POp(dist.irecv, v["recv_lo"], dn, group))
+            ops.append(dist.P2POp(dist.irecv, v["recv_lo"], gdn, group))
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()

@@ -20,7 +20,7 @@ import numpy as np
 
 from nsol_b200 import _lib
 from nsol_b200 import _trace
-from nsol_b200.solver import Solver
+from nsol_b200.solver import Solver, _memory_key
 
 _ALG_TYPES = ("ALG2", "ALG2_AHMOD", "ALG3")
 
@@ -40,6 +40,7 @@ class PrimalDualSolver(Solver):
         self._alg_type = alg_type
         self._dtype = dtype          # additive option: "float64" (default) | "float32"
         self._config = None          # cached result of probing the callables
+        self._dist = None            # z-slab sharding over a torch.distributed group (see distribute())
 
     # -- setters / getters (nsol/primal_dual_solver.py:120-197) ------------------
     def set_alpha(self, alpha):
@@ -71,6 +72,21 @@ class PrimalDualSolver(Solver):
 
     def get_dtype(self):
         return "float32" if _lib.dtype_code(self._dtype) == _lib.F32 else "float64"
+
+    def distribute(self, group=None, halo="auto"):
+        """Shard ONE tall volume over the ranks of an initialised ``torch.distributed`` process group (additive
+        API; the reference is single-process).  Every rank constructs the solver on ITS z-slab -- contiguous
+        planes along numpy axis 0, rank order = slab order: ``x0`` / the prox's observation are the slab, ``B`` /
+        ``B_conj`` are gradient operators of the slab's shape, ``x_scale`` is the same on every rank -- and all
+        ranks call ``run()`` together.  The halo planes travel inside the iteration kernels over NVLink peer
+        memory (``halo="p2p"``) or by NCCL send/recv (``"nccl"``); ``get_x()`` returns the rank's slab of the
+        solution, bit-identical to the corresponding planes of the unsharded solve."""
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("PrimalDualSolver.distribute: torch.distributed is not initialised")
+        self.release()
+        self._dist = {"group": group, "halo": halo, "rank": dist.get_rank(group), "world": dist.get_world_size(group)}
+        return self
 
     def print_statistics(self, fmt="%.3e"):
         pass
@@ -114,7 +130,8 @@ class PrimalDualSolver(Solver):
             b = np.asarray(f1[3], dtype=np.float64).reshape(-1)
             if b.size != n:
                 raise ValueError("PrimalDualSolver: prox_f observation has %d values, x0 has %d" % (b.size, n))
-            cfg.update(kind="denoise", data="L1" if f1[0] == "prox_ell1" else "L2", b=b, b_scale=f1[4])
+            cfg.update(kind="denoise", data="L1" if f1[0] == "prox_ell1" else "L2", b=b, b_scale=f1[4],
+                       b_src=_memory_key(f1[3]))
         elif f1[0] == "prox_lls" and f1[1] == ("arg",) and f1[2] == t1:
             cfg.update(kind="deconv", lls=f1)
         else:
@@ -143,22 +160,49 @@ class PrimalDualSolver(Solver):
         desc._keep = arr
         return desc
 
+    def _x0_is_observation(self, cfg, b):
+        """True when the caller's x0 was the very array the prox holds as its observation and the two scales agree
+        (the reference's denoising wiring: ``b = x0 = observed.flatten()``, nsol/application/run_denoising.py:95-97).
+        Then x0 / x_scale is evaluated on the device from the one uploaded copy of b (the same IEEE division the
+        host did) and the second host->device copy -- 1 GiB at 512^3 -- is skipped.  A strided sample guards
+        against the array having been modified since construction."""
+        if cfg.get("b_src") is None or cfg["b_src"] != getattr(self, "_x0_src", None):
+            return False
+        if float(cfg["b_scale"]) != float(self._x_scale) or b.size != self._x0.size or b.size == 0:
+            return False
+        idx = np.linspace(0, b.size - 1, num=min(b.size, 64)).astype(np.int64)
+        return bool(np.array_equal(np.asarray(self._x0)[idx], b[idx] / float(self._x_scale)))
+
     # -- device plan (kept between runs of the same solver: no reallocation in a sweep) ---------
     def _acquire_plan(self, ctx, cfg, desc):
-        key = (cfg["shape"], cfg["spacing"], int(desc.grid.dtype), int(desc.grid.batch))
+        key = (cfg["shape"], cfg["spacing"], int(desc.grid.dtype), int(desc.grid.batch), None if self._dist is None else
+               (self._dist["rank"], self._dist["world"], self._dist["halo"]))
         plan = getattr(self, "_plan", None)
         if plan is not None and self._plan_key == key:
             ctx.check(ctx.lib.nsol_pd_plan_update(plan, C.byref(desc)))
             return plan
         self.release()
-        h = C.c_void_p()
-        ctx.check(ctx.lib.nsol_pd_plan_create(ctx.handle, C.byref(desc), C.byref(h)))
+        if self._dist is not None:
+            # every rank creates its slab plan and exchanges link handles with its neighbours (collective)
+            import torch
+            from nsol_b200.distributed import SlabPrimalDual
+            shape = cfg["shape"]
+            if len(shape) < 2:
+                raise ValueError("PrimalDualSolver.distribute: z-slab sharding needs a 2-D or 3-D grid")
+            device = torch.device("cuda", torch.cuda.current_device())
+            self._slab = SlabPrimalDual(ctx, desc, int(np.prod(shape[1:])), _lib.np_dtype(int(desc.grid.dtype)),
+                                        self._dist["rank"], self._dist["world"], device, halo=self._dist["halo"],
+                                        group=self._dist["group"])
+            h = self._slab.plan
+        else:
+            h = C.c_void_p()
+            ctx.check(ctx.lib.nsol_pd_plan_create(ctx.handle, C.byref(desc), C.byref(h)))
         self._plan, self._plan_key, self._plan_ctx = h, key, ctx
         return h
 
     def release(self):
         """Free the device memory held by this solver (plan + device-resident result; the LSMR plan of the
-        deconvolution wiring)."""
+        deconvolution wiring).  With ``distribute()`` this is collective: every rank must call it."""
         from nsol_b200.linear_solver import release_lsmr_plan
         release_lsmr_plan(self)
         plan = getattr(self, "_plan", None)
@@ -166,13 +210,20 @@ class PrimalDualSolver(Solver):
             if self._fetch_result is not None:
                 self._x_unscaled = self._fetch_result()
                 self._fetch_result = None
-            self._plan_ctx.lib.nsol_pd_plan_destroy(plan)
+            slab = getattr(self, "_slab", None)
+            if slab is not None:
+                slab.close()
+                self._slab = None
+            else:
+                self._plan_ctx.lib.nsol_pd_plan_destroy(plan)
             self._plan = None
 
     def __del__(self):
         try:
+            from nsol_b200.linear_solver import release_lsmr_plan
+            release_lsmr_plan(self)
             plan = getattr(self, "_plan", None)
-            if plan is not None:
+            if plan is not None and getattr(self, "_slab", None) is None:
                 self._plan_ctx.lib.nsol_pd_plan_destroy(plan)
                 self._plan = None
         except Exception:
@@ -181,19 +232,35 @@ class PrimalDualSolver(Solver):
     def _run(self):
         cfg = self._probe()
         if cfg["kind"] == "deconv":
+            if self._dist is not None:
+                raise TypeError("PrimalDualSolver.distribute: only the denoising prox maps are sharded")
             from nsol_b200._pd_deconv import run_pd_deconvolution
             return run_pd_deconvolution(self, cfg)
         ctx = _lib.context()
         lib = ctx.lib
         n = self._x0.size
         desc = self._make_desc(cfg, [float(self._alpha)])
-        x0 = np.ascontiguousarray(self._x0, dtype=np.float64)
         b = np.ascontiguousarray(cfg["b"], dtype=np.float64)
+        same = self._x0_is_observation(cfg, b)
+        if same:
+            desc.x0_scale = desc.b_scale        # x = xbar = b / x_scale, evaluated on the device from the copy of b
+            x0 = None
+        else:
+            x0 = np.ascontiguousarray(self._x0, dtype=np.float64)
         iters = int(self._iterations)
         if iters < 0:
             raise ValueError("iterations must be >= 0")
         plan = self._acquire_plan(ctx, cfg, desc)
-        ctx.check(lib.nsol_pd_plan_reset_host(plan, b.ctypes.data, x0.ctypes.data, None))
+        slab = getattr(self, "_slab", None)
+        ctx.check(lib.nsol_pd_plan_reset_host(plan, b.ctypes.data, x0.ctypes.data if x0 is not None else None, None))
+        if slab is not None:
+            slab._halo_fresh = False
+
+        def iterate(k):
+            if slab is not None:
+                slab.iterate(k, None)
+            else:
+                ctx.check(lib.nsol_pd_plan_iterate(plan, k, None))
 
         def fetch():
             out = ctx.result_empty(n, np.float64)
@@ -204,8 +271,10 @@ class PrimalDualSolver(Solver):
         if self._observer is not None and not getattr(self._observer, "get_store_iterates", lambda: True)():
             reqs = self._observer.device_measure_requests(n)
         if self._observer is None:
-            ctx.check(lib.nsol_pd_plan_iterate(plan, iters, None))
+            iterate(iters)
         elif reqs is not None:
+            if slab is not None:
+                raise TypeError("PrimalDualSolver.distribute: device-side measures see the local slab only; use a storing Observer")
             # measures as device reductions on the resident iterate
             from nsol_b200.similarity_measures import device_stats, from_stats
             refs = {}
@@ -222,7 +291,7 @@ class PrimalDualSolver(Solver):
             try:
                 for i in range(iters + 1):
                     if i > 0:
-                        ctx.check(lib.nsol_pd_plan_iterate(plan, 1, None))
+                        iterate(1)
                     ctx.check(lib.nsol_pd_plan_x_dev(plan, C.byref(xptr)))
                     cache = {}
                     for name, r in reqs.items():
@@ -239,9 +308,12 @@ class PrimalDualSolver(Solver):
             # nsol/primal_dual_solver.py:218-219, 260-261: the observer sees x0 and every iterate
             self._observer.add_x(fetch())
             for _ in range(iters):
-                ctx.check(lib.nsol_pd_plan_iterate(plan, 1, None))
+                iterate(1)
                 self._observer.add_x(fetch())
-        ctx.sync()      # run() returns when the solve is finished (computational time, errors)
+        if slab is not None:
+            slab.check(None)    # synchronises; a timed-out halo wait invalidates the result
+        else:
+            ctx.sync()          # run() returns when the solve is finished (computational time, errors)
         self._set_device_result(fetch)
 
     def run_sweep(self, alphas):

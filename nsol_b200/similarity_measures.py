@@ -6,8 +6,13 @@ both arrays and reduce on the device; called during a solver's probing pass (``_
 they describe themselves, which lets a solver evaluate them per iteration on the device-resident
 iterate instead of copying every iterate to the host.
 
-SSIM (``skimage.measure.compare_ssim``, removed from scikit-image), MI / NMI (histograms) and
-Dice are evaluation-only utilities outside the hot path and are not implemented.
+SSIM, Shannon / joint entropy, MI / NMI and Dice (nsol/similarity_measures.py:135-264) are
+evaluation-only utilities outside the hot path: they are evaluated on the HOST
+with numpy, after the solve, on the iterates the Observer holds.  SSIM restates
+``skimage.measure.compare_ssim(x, x_ref)`` with its defaults (Wang et al. 2004: uniform
+7-sample window, sample covariance, K1 = 0.01, K2 = 0.03) because that function no longer
+exists in scikit-image; its ``data_range`` is taken from the reference image (SURVEY.md 8c:
+SSIM parity is unpinned).
 """
 import ctypes as C
 
@@ -75,11 +80,21 @@ def _measure(kind, x, x_ref):
     return from_stats(kind, st, x.size)
 
 
-def _unavailable(name):
-    def fn(*args, **kwargs):
-        raise NotImplementedError("%s is an evaluation-only measure outside the CUDA hot path (SURVEY.md 2); "
-                                  "it is not implemented in nsol_b200" % name)
-    return fn
+def _host(x):
+    if is_symbol(x):
+        raise TypeError("this measure is evaluated on the host, on stored iterates (use a storing Observer)")
+    return np.asarray(x, dtype=np.float64)
+
+
+def _window_mean(a, win):
+    """Mean over a centred window of ``win`` samples at every position where the window fits."""
+    c = np.concatenate(([0.0], np.cumsum(a)))
+    return (c[win:] - c[:-win]) / float(win)
+
+
+def _entropy(hist):
+    prob = hist[hist > 0] / float(np.sum(hist))
+    return float(-np.sum(prob * np.log(prob)))
 
 
 class SimilarityMeasures(object):
@@ -112,10 +127,53 @@ class SimilarityMeasures(object):
     def normalized_cross_correlation(x, x_ref):
         return _measure("NCC", x, x_ref)
 
-    structural_similarity = staticmethod(_unavailable("SSIM"))
-    mutual_information = staticmethod(_unavailable("MI"))
-    normalized_mutual_information = staticmethod(_unavailable("NMI"))
-    dice_score = staticmethod(_unavailable("Dice"))
+    @staticmethod
+    def structural_similarity(x, x_ref, win=7, K1=0.01, K2=0.03):
+        """Mean structural similarity of the flattened arrays (nsol/similarity_measures.py:135-136), host."""
+        a, r = _host(x).reshape(-1), _host(x_ref).reshape(-1)
+        if a.shape != r.shape:
+            raise ValueError("Input data shapes do not match")
+        if a.size < win:
+            raise ValueError("structural_similarity needs at least %d samples" % win)
+        data_range = float(r.max() - r.min())
+        norm = win / (win - 1.0)
+        ma, mr = _window_mean(a, win), _window_mean(r, win)
+        va = norm * (_window_mean(a * a, win) - ma * ma)
+        vr = norm * (_window_mean(r * r, win) - mr * mr)
+        var = norm * (_window_mean(a * r, win) - ma * mr)
+        c1, c2 = (K1 * data_range) ** 2, (K2 * data_range) ** 2
+        ssim = ((2 * ma * mr + c1) * (2 * var + c2)) / ((ma * ma + mr * mr + c1) * (va + vr + c2))
+        return float(np.mean(ssim))
+
+    @staticmethod
+    def shannon_entropy(x, bins=100):
+        """H(X) = -sum p ln p over a histogram of the flattened array (nsol/similarity_measures.py:154-165), host."""
+        return _entropy(np.histogram(_host(x), bins=bins)[0])
+
+    @staticmethod
+    def joint_entropy(x, x_ref, bins=100):
+        """nsol/similarity_measures.py:183-191, host."""
+        return _entropy(np.histogram2d(_host(x).reshape(-1), _host(x_ref).reshape(-1), bins=bins)[0])
+
+    @staticmethod
+    def mutual_information(x, x_ref, bins=100):
+        """H(X) + H(Y) - H(X,Y)  (nsol/similarity_measures.py:212-216), host."""
+        sm = SimilarityMeasures
+        return sm.shannon_entropy(x, bins) + sm.shannon_entropy(x_ref, bins) - sm.joint_entropy(x, x_ref, bins)
+
+    @staticmethod
+    def normalized_mutual_information(x, x_ref, bins=100):
+        """(H(X) + H(Y)) / H(X,Y)  (nsol/similarity_measures.py:235-239), host."""
+        sm = SimilarityMeasures
+        return (sm.shannon_entropy(x, bins) + sm.shannon_entropy(x_ref, bins)) / sm.joint_entropy(x, x_ref, bins)
+
+    @staticmethod
+    def dice_score(x, x_ref):
+        """2 |A and B| / (|A| + |B|) of two boolean arrays (nsol/similarity_measures.py:255-264), host."""
+        x, x_ref = np.asarray(x), np.asarray(x_ref)
+        if x.dtype != np.bool_ or x_ref.dtype != np.bool_:
+            raise ValueError("x and x_ref need to be of type boolean")
+        return 2.0 * float(np.sum(x & x_ref)) / float(np.sum(x) + np.sum(x_ref))
 
     # nsol/similarity_measures.py:267-277
     similarity_measures = {

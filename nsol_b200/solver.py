@@ -28,11 +28,19 @@ def _scaled_host_copy(x0, x_scale):
     return out
 
 
+def _memory_key(a):
+    """(address, shape, strides, dtype) of an ndarray's buffer, or None."""
+    if not isinstance(a, np.ndarray):
+        return None
+    return (a.__array_interface__["data"][0], a.shape, a.strides, a.dtype.str)
+
+
 class Solver(object):
     __metaclass__ = ABCMeta
 
     def __init__(self, x0, x_scale, verbose):
         self._x_scale = float(x_scale)
+        self._x0_src = _memory_key(x0)      # where the caller's x0 lives (lets a solver see that x0 is its observation)
         self._x0 = _scaled_host_copy(x0, self._x_scale)             # nsol/solver.py:37
         self._x = np.array(self._x0)
         self._x_unscaled = None      # get_x() value produced on the device (x * x_scale)
@@ -54,6 +62,7 @@ class Solver(object):
         return self._verbose
 
     def set_x0(self, x0):
+        self._x0_src = _memory_key(x0)
         self._x0 = _scaled_host_copy(x0, self._x_scale)
         self._x = np.array(self._x0)
         self._x_unscaled = None

@@ -54,16 +54,29 @@ class SolverParameterStudy(ParameterStudy):
         self._observer.clear_x_list()
         self._solver.set_observer(self._observer)
         dist = _dist()
-        writer = dist is None or dist.get_rank() == 0
-        previous = os.path.isfile(self._get_path_to_file_parameters())
-        if not self._append or not previous:
-            if writer:
-                self._create_file_parameters()
-                self._create_files_measures()
-                self._create_file_computational_time()
-            self._append = False
-        else:
-            self._check_that_studies_match()
+        rank = dist.get_rank() if dist else 0
+        # Rank 0 alone looks at the files, decides between "new study" and "append", creates / checks them;
+        # the decision (or its error) is broadcast, so no rank ever reads a file another one is writing.
+        state = [None]
+        if rank == 0:
+            try:
+                previous = os.path.isfile(self._get_path_to_file_parameters())
+                if not self._append or not previous:
+                    self._create_file_parameters()
+                    self._create_files_measures()
+                    self._create_file_computational_time()
+                    state[0] = ("new", None)
+                else:
+                    self._check_that_studies_match()
+                    state[0] = ("append", None)
+            except Exception as e:     # every rank must leave run() together
+                state[0] = ("error", e)
+        if dist:
+            dist.broadcast_object_list(state, src=0)
+        kind, err = state[0]
+        if kind == "error":
+            raise err
+        self._append = kind == "append"
         t0 = time.time()
         self._run()
         self._computational_time = datetime.timedelta(seconds=time.time() - t0)
@@ -76,45 +89,74 @@ class SolverParameterStudy(ParameterStudy):
 
     # ------------------------------------------------------------------ sweep
     def _run(self):
+        import os
         keys = list(self._parameters.keys())
         points = list(itertools.product(*self._parameters.values()))
-        if self._append:
-            reader = ReaderParameterStudy(directory=self._directory, name=self._name)
-            reader.read_study()
-            offset = len(reader.get_parameters_to_line().keys())
-            dic_x = dict(reader.get_reconstructions())
-        else:
-            offset = 0
-            dic_x = {k: v for k, v in self._reconstruction_info.items()}
-
         dist = _dist()
         rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
-        mine = list(range(rank, len(points), world))
-        results = self._run_points(keys, points, mine)       # {index: (params, measures, time, x_last)}
-        # the float16 reconstruction of every run is deflated on the rank that computed it (thread pool)
-        import os
-        threads = max(1, (os.cpu_count() or 1) // world)
-        packed = npz_members({str(i + offset): np.array(results[i][3], dtype=np.float16) for i in sorted(results)}, threads)
-        for i, member in zip(sorted(results), packed):
-            results[i] = results[i][:3] + (member,)
+        offset, members = 0, []
+        if rank == 0:
+            if self._append:       # only the writer reads the study being continued
+                reader = ReaderParameterStudy(directory=self._directory, name=self._name)
+                reader.read_study()
+                offset = len(reader.get_parameters_to_line().keys())
+                dic_x = dict(reader.get_reconstructions())
+            else:
+                dic_x = {k: v for k, v in self._reconstruction_info.items()}
+            members = npz_members(dic_x)     # reconstruction_info / the runs of the study being appended to
         if dist:
-            gathered = [None] * world if rank == 0 else None
-            dist.gather_object(results, gathered, dst=0)
-            if rank != 0:
-                self._solver.set_x0(self._solver.get_x0())
-                return
-            results = {}
-            for part in gathered:
-                results.update(part)
-        members = npz_members(dic_x)          # reconstruction_info / the runs of the study being appended to
-        for i in range(len(points)):
-            params, measures, ctime, member = results[i]
-            for measure, values in measures.items():
-                self._add_to_file_measures(measure, np.asarray(values).reshape(1, -1))
-            self._add_to_file_computational_time(ctime)
-            self._add_to_file_parameters(params)
-            members.append(member)
-        self._write_to_file_reconstructions(members)
+            box = [offset]
+            dist.broadcast_object_list(box, src=0)
+            offset = box[0]
+        threads = max(1, (os.cpu_count() or 1) // world)
+        # Rounds of world x MAX_SWEEP_BATCH points: inside a round the points are dealt round-robin to the ranks
+        # (no data-path communication); after every round the rows of its points are appended to the text files
+        # in index order, as the reference appends them point by point (nsol/solver_parameter_study.py:194-205),
+        # so an interrupted study keeps what it finished.  The reconstructions archive is written once at the
+        # end -- also when a later point fails.
+        per_round = world * MAX_SWEEP_BATCH
+        failure = None
+        try:
+            for r0 in range(0, len(points), per_round):
+                idx = list(range(r0, min(len(points), r0 + per_round)))
+                mine = idx[rank::world]
+                try:
+                    results = self._run_points(keys, points, mine)    # {index: (params, measures, time, x_last)}
+                    # the float16 reconstruction of every run is deflated on the rank that computed it
+                    packed = npz_members({str(i + offset): np.array(results[i][3], dtype=np.float16) for i in sorted(results)}, threads)
+                    for i, member in zip(sorted(results), packed):
+                        results[i] = results[i][:3] + (member,)
+                except Exception as e:
+                    results, failure = {}, e
+                if dist:
+                    gathered = [None] * world if rank == 0 else None
+                    dist.gather_object((results, failure), gathered, dst=0)
+                    flag = [None]
+                    if rank == 0:
+                        results = {}
+                        for part, err in gathered:
+                            results.update(part)
+                            failure = failure or err
+                        flag[0] = failure
+                    dist.broadcast_object_list(flag, src=0)
+                    failure = flag[0]
+                if rank == 0:
+                    for i in idx:
+                        if i not in results:
+                            break              # rows stay contiguous: stop at the first missing point
+                        params, measures, ctime, member = results[i]
+                        for measure, values in measures.items():
+                            self._add_to_file_measures(measure, np.asarray(values).reshape(1, -1))
+                        self._add_to_file_computational_time(ctime)
+                        self._add_to_file_parameters(params)
+                        members.append(member)
+                if failure is not None:
+                    break
+        finally:
+            if rank == 0:
+                self._write_to_file_reconstructions(members)
+        if failure is not None:
+            raise failure
 
     def _apply_point(self, keys, vals):
         params = {}

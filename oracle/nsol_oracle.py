@@ -607,21 +607,22 @@ def admm_shrink_iso(t, ell, dim):
 
 
 def admm_tv(A, A_adj, B, B_adj, b, x0, dim, alpha=0.01, rho=0.5, iterations=10,
-            iter_max=10, x_scale=1.0, keep_iterates=False, norm=None):
-    """``ADMMLinearSolver.run()`` -- nsol/admm_linear_solver.py:165-237 with
-    b_reg = 0: v = B(x0), w = 0; per iteration x <- Tikhonov/LSMR solve with
-    b_reg = v - w and weight rho (x_scale=1, bounds (0, inf)), t = B(x) + w,
-    v = shrink_iso(t, alpha/rho), w = t - v."""
+            iter_max=10, x_scale=1.0, keep_iterates=False, norm=None, b_reg=0):
+    """``ADMMLinearSolver.run()`` -- nsol/admm_linear_solver.py:165-237:
+    v = B(x0) - b_reg, w = 0; per iteration x <- Tikhonov/LSMR solve with
+    b_reg' = v - w + b_reg and weight rho (x_scale=1, bounds (0, inf)), t = B(x) + w - b_reg,
+    v = shrink_iso(t, alpha/rho), w = t - v.  (b_reg is divided by x_scale, :100.)"""
     x_scale = float(x_scale)
     x = np.asarray(x0, dtype=np.float64) / x_scale
     bs = np.asarray(b, dtype=np.float64) / x_scale
-    v = B(x) - 0.0
+    c = b_reg / x_scale
+    v = B(x) - c
     w = np.zeros_like(v)
     iterates = [x * x_scale] if keep_iterates else None
     for _ in range(iterations):
-        x = tikhonov_lsmr(A, A_adj, B, B_adj, bs, x, alpha=rho, b_reg=v - w + 0.0,
+        x = tikhonov_lsmr(A, A_adj, B, B_adj, bs, x, alpha=rho, b_reg=v - w + c,
                           iter_max=iter_max, x_scale=1.0, norm=norm)
-        t = B(x) + w - 0.0
+        t = B(x) + w - c
         v = admm_shrink_iso(t, alpha / rho, dim)
         w = t - v
         if keep_iterates:
