@@ -1,0 +1,323 @@
+"""Round-2 GPU parity tests (``-m gpu``): BASELINE configurations at their FULL size, the
+deconvolution study interface, ADMM with b_reg != 0, study files against the reference's own
+writer, NaN propagation, the sharded-solver API.
+
+Fixtures: tests/golden/r2.npz (+ r2_manifest.json, study_ref/) written by oracle/gen_golden_r2.py
+from the UNMODIFIED reference.  Results of bit-exact float64 paths are pinned by the SHA-256 of the
+reference's result bytes (plus a strided subsample for diagnosis); inputs are regenerated with the
+oracle's bit-identical restatement of nsol/noise.py.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, rel_max
+from oracle import nsol_oracle as orc
+from test_gpu_parity import deconv_callables, make_pd, run_pd
+
+import nsol_b200.admm_linear_solver as admm
+import nsol_b200.primal_dual_solver as pd
+import nsol_b200.tikhonov_linear_solver as tk
+from nsol_b200.deconvolution_solver_parameter_study_interface import (DeconvolutionParameterStudyInterface,
+                                                                      DeconvolutionSolverStudyInterface)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def r2():
+    class R2(object):
+        data = np.load(os.path.join(GOLDEN, "r2.npz"))
+        manifest = json.load(open(os.path.join(GOLDEN, "r2_manifest.json")))
+        inputs = np.load(os.path.join(GOLDEN, "inputs.npz"))
+
+        def check_hash(self, name, x):
+            """bit-exact against the reference's result (hash of its float64 bytes)."""
+            m = self.manifest[name]
+            x = np.ascontiguousarray(x, dtype=np.float64)
+            assert x.size == m["size"]
+            sub = self.data[name]
+            assert np.array_equal(x[::m["stride"]], sub), (name, "subsample differs: max abs %g" % np.max(np.abs(x[::m["stride"]] - sub)))
+            assert hashlib.sha256(x.tobytes()).hexdigest() == m["sha256"], name
+    return R2()
+
+
+# ------------------------------------------------------------------ full-size BASELINE configurations
+@pytest.mark.parametrize("alpha", [0.6, 0.05])
+def test_config2_full_size_bit_exact(r2, alpha):
+    """C2: 2D_Man_1024 + salt & pepper, Huber-L1, 200 iterations, at 1024^2 (alpha 0.6 primary, 0.05 degenerate)."""
+    man = r2.inputs["man_1024"].astype(np.float64)
+    sp = orc.add_salt_and_pepper_noise(man, 0.5, 0.1, seed=1)
+    x = run_pd(sp, reg="HUBER", data="L1", alpha=alpha, L2=8, iterations=200)
+    r2.check_hash("c2_full_alpha%g" % alpha, x)
+    # and against the live oracle (the numpy restatement) on the same input
+    ref = orc.primal_dual_denoise(sp.reshape(-1), sp.shape, reg="HUBER", data="L1", alpha=alpha, L2=8, iterations=200,
+                                  x_scale=float(sp.max()))
+    assert np.array_equal(x, ref)
+
+
+def test_config4_128_cube_100_iterations_bit_exact(r2):
+    """C4 wiring at 128^3 (64^3 Shepp-Logan repeated x2 + Gaussian noise), TV-L2, 100 iterations."""
+    ph = r2.inputs["shepp_logan_64"].astype(np.float64)
+    vol = np.repeat(np.repeat(np.repeat(ph, 2, 0), 2, 1), 2, 2)
+    voln = orc.add_gaussian_noise(vol, 0.05, seed=1)
+    x = run_pd(voln, reg="TV", data="L2", alpha=0.05, L2=8, iterations=100)
+    r2.check_hash("c4_128cube_100it", x)
+    x32 = run_pd(voln, reg="TV", data="L2", alpha=0.05, L2=8, iterations=100, dtype="float32")
+    assert rel_max(x32, x) <= 1e-4
+
+
+def test_config3_full_size_admm_50x10(r2):
+    """C3: 512^2 Lena, blur sigma=1 + noise 0.05, ADMM TV-L2 alpha=0.01 rho=0.1, 50 outer x 10 LSMR iterations."""
+    lena = r2.inputs["lena_512"].astype(np.float64)
+    Ao, _, _, _ = orc.deconvolution_operators(lena.shape, np.eye(2))
+    obs = orc.add_gaussian_noise(Ao(lena.reshape(-1)).reshape(lena.shape), 0.05, seed=1)
+    A, A_adj, D, D_adj = deconv_callables(lena.shape, [1.0, 1.0])
+    xs = float(obs.max())
+    ref = r2.data["c3_full_50x10"]
+    errs = {}
+    for dtype, tol in (("float64", 1e-10), ("float32", 1e-4)):
+        s = admm.ADMMLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=D, B_adj=D_adj, x0=obs.flatten(), dimension=2, alpha=0.01,
+                                  rho=0.1, iterations=50, iter_max=10, x_scale=xs, dtype=dtype)
+        s.run()
+        x = s.get_x()
+        errs[dtype] = rel_max(x, ref)
+        assert errs[dtype] <= tol, errs
+        if dtype == "float32":
+            for f in (orc.psnr, orc.ncc, orc.ssim_1d):
+                assert round(f(x, lena.reshape(-1)), 3) == round(f(ref, lena.reshape(-1)), 3), f.__name__
+        s.release()
+    print("config 3 full size: rel. max-abs vs the reference", errs)
+
+
+@pytest.mark.parametrize("reg", ["TV", "HUBER", "TK1"])
+def test_config5_full_sweep_sampled_bit_exact(r2, reg):
+    """C5: all 64 alpha of np.linspace(0.001, 0.05, 64) batched on 1024^2, 200 iterations; 8 of them per regulariser are
+    pinned against the reference."""
+    man = r2.inputs["man_1024"].astype(np.float64)
+    noisy = orc.add_gaussian_noise(man, 0.05, seed=1)
+    alphas = np.linspace(0.001, 0.05, 64)
+    solver = make_pd(noisy, reg=reg, data="L2", alpha=0.01, L2=8, iterations=200)
+    xs = []
+    for c in range(0, 64, 32):
+        xs.append(np.array(solver.run_sweep(alphas[c:c + 32])))
+    xs = np.concatenate(xs)
+    for i in (0, 9, 18, 27, 36, 45, 54, 63):
+        r2.check_hash("c5_%s_a%02d" % (reg, i), xs[i])
+
+
+# ------------------------------------------------------------------ ADMM with its own b_reg
+@pytest.mark.parametrize("name", ["admm_breg_2d", "admm_breg_2d_scalar", "admm_breg_3d"])
+@pytest.mark.parametrize("path", [1, 2])
+def test_admm_with_b_reg_vs_reference(r2, name, path):
+    m = r2.manifest[name]
+    three = name.endswith("3d")
+    obs = r2.data["in/admm_breg_obs3" if three else "in/admm_breg_obs2"]
+    b_reg = m.get("b_reg", None)
+    if b_reg is None:
+        b_reg = r2.data["in/admm_breg_c3" if three else "in/admm_breg_c2"]
+    A, A_adj, D, D_adj = deconv_callables(obs.shape, m["var"])
+    from nsol_b200 import _lib
+    ctx = _lib.context()
+    ctx.set_tuning("lsmr_path", path)
+    try:
+        s = admm.ADMMLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=D, B_adj=D_adj, x0=obs.flatten(), dimension=obs.ndim,
+                                  b_reg=b_reg, alpha=m["alpha"], rho=m["rho"], iterations=m["iterations"], iter_max=m["iter_max"],
+                                  x_scale=float(obs.max()))
+        s.run()
+        assert rel_max(s.get_x(), r2.data[name]) <= 1e-10
+        s.release()
+    finally:
+        ctx.set_tuning("lsmr_path", 0)
+
+
+# ------------------------------------------------------------------ deconvolution study interface
+def _interface(golden, name, rtype, tv_solver="PD", cls=DeconvolutionSolverStudyInterface, **extra):
+    m = golden.manifest["lsmr"][name]
+    obs = golden("lsmr", "in/" + m["input"])
+    A, A_adj, D, D_adj = deconv_callables(obs.shape, m["var"])
+    xs = float(np.max(obs)) if m.get("x_scale") is None else m["x_scale"]
+    return cls(A=A, A_adj=A_adj, D=D, D_adj=D_adj, b=obs.flatten(), x0=obs.flatten(), alpha=m["alpha"], x_scale=xs,
+               iter_max=m["iter_max"], iterations=m.get("iterations", 10), minimizer="lsmr", measures=["PSNR", "NCC", "SSIM"],
+               reconstruction_type=rtype, dimension=obs.ndim, L2=m.get("L2", 8), rho=m.get("rho", 0.5), tv_solver=tv_solver,
+               x_ref=obs.flatten(), **extra), obs
+
+
+@pytest.mark.parametrize("name,rtype,tv_solver,cls", [
+    ("tk_2d_TK0", "TK0L2", "PD", tk.TikhonovLinearSolver), ("tk_3d_TK1", "TK1L2", "PD", tk.TikhonovLinearSolver),
+    ("pdd_2d_TV", "TVL2", "PD", pd.PrimalDualSolver), ("pdd_2d_HUBER", "HuberL2", "PD", pd.PrimalDualSolver),
+    ("admm_2d", "TVL2", "ADMM", admm.ADMMLinearSolver), ("admm_3d", "TVL2", "ADMM", admm.ADMMLinearSolver)])
+def test_deconvolution_interface_solvers_vs_reference(golden, name, rtype, tv_solver, cls):
+    """nsol/deconvolution_solver_parameter_study_interface.py:217-325: every reconstruction_type x tv_solver gives the
+    solver the reference builds, with the reference's result."""
+    itf, obs = _interface(golden, name, rtype, tv_solver)
+    with pytest.raises(RuntimeError):
+        itf.get_solver()
+    itf.set_up_solver()
+    solver = itf.get_solver()
+    assert isinstance(solver, cls)
+    solver.run()
+    assert rel_max(solver.get_x(), golden("lsmr", name)) <= 1e-10
+    itf.set_up_measures()
+    meas = itf.get_measures()
+    assert sorted(meas) == ["Data", "NCC", "PSNR", "Reg", "SSIM"]
+    x = solver.get_x()
+    vals = {k: float(f(x)) for k, f in meas.items()}
+    assert all(np.isfinite(v) for v in vals.values()), vals
+    # the regulariser / data costs against the oracle's operators
+    Ao, _, Do, _ = orc.deconvolution_operators(obs.shape, np.diag(golden.manifest["lsmr"][name]["var"]))
+    assert abs(vals["Data"] - 0.5 * np.sum((Ao(x) - obs.reshape(-1)) ** 2)) <= 1e-9 * max(1.0, vals["Data"])
+    g = Do(x)
+    expect = {"TK0L2": 0.5 * np.sum(x ** 2), "TK1L2": 0.5 * np.sum(g ** 2)}.get(rtype)
+    if rtype == "TVL2":
+        expect = np.sum(np.sqrt(sum(p ** 2 for p in np.array_split(g, obs.ndim))))
+    if expect is not None:
+        assert abs(vals["Reg"] - expect) <= 1e-9 * max(1.0, abs(expect)), (vals["Reg"], expect)
+    solver.release()
+
+
+def test_deconvolution_parameter_study_interface(golden, tmp_path):
+    """:364-552: solver + measures + the matching *ParameterStudy; run a 3-point alpha sweep with ADMM."""
+    itf, obs = _interface(golden, "admm_2d", "TVL2", "ADMM", cls=DeconvolutionParameterStudyInterface, dir_output=str(tmp_path),
+                          parameters={"alpha": [0.005, 0.01, 0.02]}, name="TVL2", reconstruction_info={"shape": obs_shape(golden, "admm_2d")})
+    itf.set_up_parameter_study()
+    study = itf.get_parameter_study()
+    from nsol_b200.admm_linear_solver_parameter_study import ADMMLinearSolverParameterStudy
+    assert isinstance(study, ADMMLinearSolverParameterStudy)
+    study.run()
+    from nsol_b200.reader_parameter_study import ReaderParameterStudy
+    reader = ReaderParameterStudy(str(tmp_path), "TVL2")
+    reader.read_study()
+    assert reader.get_parameters() == {"alpha": [0.005, 0.01, 0.02]}
+    assert sorted(reader.get_measures()) == ["Data", "NCC", "PSNR", "Reg", "SSIM"]
+    rec = reader.get_reconstructions()
+    # the alpha = 0.01 point is the reference's fixture
+    assert rel_max(rec["1"].astype(np.float64), golden("lsmr", "admm_2d").astype(np.float16).astype(np.float64)) <= 2e-3
+    itf.get_solver().release()
+
+
+def obs_shape(golden, name):
+    m = golden.manifest["lsmr"][name]
+    return golden("lsmr", "in/" + m["input"]).shape
+
+
+# ------------------------------------------------------------------ study files vs the reference's own writer
+def _strip_stamp(line):
+    return line[:line.rindex("(")] if line.startswith("## ") and "(" in line else line
+
+
+def test_study_files_match_reference_writer(tmp_path):
+    """the files a GPU study writes are those the reference's SolverParameterStudy writes
+    (tests/golden/study_ref, produced by nsol/solver_parameter_study.py:229-323 itself) -- text files byte for byte
+    except the time stamp in the header and the measured run times, the reconstructions archive key by key."""
+    from nsol_b200.observer import Observer
+    from nsol_b200.primal_dual_solver_parameter_study import PrimalDualSolverParameterStudy
+    ref_dir = os.path.join(GOLDEN, "study_ref")
+    inp = np.load(os.path.join(ref_dir, "input.npz"))
+    noisy, clean = inp["noisy"], inp["clean"].flatten()
+    solver = make_pd(noisy, reg="TV", data="L2", alpha=0.05, L2=8, iterations=5)
+    obs = Observer()
+    obs.set_measures({"SSD": lambda x: float(np.sum(np.square(x - clean))), "MAXABS": lambda x: float(np.max(np.abs(x)))})
+    study = PrimalDualSolverParameterStudy(solver, obs, dir_output=str(tmp_path), name="RefStudy",
+                                           parameters={"alpha": [0.01, 0.05, 0.2], "alg_type": ["ALG2", "ALG3"]},
+                                           reconstruction_info={"shape": noisy.shape})
+    study.run()
+    for fname in ("RefStudy_parameters.txt", "RefStudy_measure_SSD.txt", "RefStudy_measure_MAXABS.txt"):
+        ours = [_strip_stamp(l) for l in open(os.path.join(str(tmp_path), fname)).read().split("\n")]
+        theirs = [_strip_stamp(l) for l in open(os.path.join(ref_dir, fname)).read().split("\n")]
+        assert ours == theirs, fname
+    ours = open(os.path.join(str(tmp_path), "RefStudy_computational_time.txt")).read().split("\n")
+    theirs = open(os.path.join(ref_dir, "RefStudy_computational_time.txt")).read().split("\n")
+    assert len(ours) == len(theirs) and [_strip_stamp(l) for l in ours[:2]] == [_strip_stamp(l) for l in theirs[:2]]
+    import re
+    assert all(re.match(r"^\d+:\d\d:\d\d(\.\d+)?$", l) for l in ours[2:-1])
+    a = np.load(os.path.join(str(tmp_path), "RefStudy_reconstructions.npz"))
+    b = np.load(os.path.join(ref_dir, "RefStudy_reconstructions.npz"))
+    assert sorted(a.files) == sorted(b.files)
+    for k in b.files:
+        assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
+
+
+# ------------------------------------------------------------------ non-finite data stays visible
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("shape", [(24, 20, 36), (40, 64)])
+def test_nan_and_inf_propagate_like_numpy(shape, dtype):
+    """x / max(1, |x|) of the reference turns NaN into NaN and +-Inf into NaN; the clamp must not hide them."""
+    rng = np.random.RandomState(5)
+    obs = rng.rand(*shape) * 255
+    obs[tuple(s // 2 for s in shape)] = np.nan
+    obs[tuple(s // 3 for s in shape)] = np.inf
+    xs = 255.0
+    with np.errstate(all="ignore"):
+        ref = orc.primal_dual_denoise(obs.reshape(-1), shape, reg="TV", data="L2", alpha=0.05, L2=8, iterations=3, x_scale=xs)
+    x = run_pd(obs, reg="TV", data="L2", alpha=0.05, L2=8, iterations=3, x_scale=xs, dtype=dtype)
+    assert np.array_equal(np.isnan(x), np.isnan(ref))
+    assert np.isnan(x).sum() > 2
+    ok = ~np.isnan(ref)
+    if dtype == "float64":
+        assert np.array_equal(x[ok], ref[ok])
+    else:
+        assert rel_max(x[ok], ref[ok]) <= 1e-4
+
+
+# ------------------------------------------------------------------ e2e upload: x0 is the observation
+def test_x0_is_observation_uploads_once_and_is_bit_exact():
+    rng = np.random.RandomState(9)
+    obs = rng.rand(20, 24, 32) * 200
+    ref = orc.primal_dual_denoise(obs.reshape(-1), obs.shape, reg="TV", data="L2", alpha=0.05, L2=8, iterations=12,
+                                  x_scale=float(obs.max()))
+    s = make_pd(obs, reg="TV", data="L2", alpha=0.05, L2=8, iterations=12)      # b and x0: two different arrays (flatten copies)
+    assert not s._x0_is_observation(s._probe(), np.asarray(s._probe()["b"]))
+    s.run()
+    assert np.array_equal(s.get_x(), ref)
+    # the reference's own wiring: b = x0 = observed.flatten()  (run_denoising.py:95-96)
+    import nsol_b200.linear_operators as lo
+    from nsol_b200.proximal_operators import ProximalOperators as prox
+    b = obs.flatten()
+    xs = float(obs.max())
+    grad, grad_adj = lo.LinearOperators3D().get_gradient_operators()
+    zshape = (3 * obs.shape[0],) + obs.shape[1:]
+    s2 = pd.PrimalDualSolver(prox_f=lambda x, tau: prox.prox_ell2_denoising(x, tau, x0=b, x_scale=xs), prox_g_conj=prox.prox_tv_conj,
+                             B=lambda x: grad(x.reshape(*obs.shape)).flatten(), B_conj=lambda x: grad_adj(x.reshape(*zshape)).flatten(),
+                             L2=8, x0=b, alpha=0.05, iterations=12, x_scale=xs)
+    assert s2._x0_is_observation(s2._probe(), b)
+    s2.run()
+    assert np.array_equal(s2.get_x(), ref)
+    b[0] += 1.0                       # the array changed after construction: the shortcut must not be taken
+    assert not s2._x0_is_observation(s2._probe(), b)
+
+
+# ------------------------------------------------------------------ sharded-solver API (one rank)
+def test_distribute_api_single_rank(tmp_path):
+    """PrimalDualSolver.distribute() / ADMMLinearSolver.distribute() with a world of one rank (gloo plumbing) take the
+    slab drivers and must reproduce the plain solvers; the multi-GPU runs are checked by tools/check_api_multi_gpu.py and
+    by bench.py's `parity` field."""
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", init_method="file://%s" % os.path.join(str(tmp_path), "rdv"), rank=0, world_size=1)
+    try:
+        rng = np.random.RandomState(2)
+        obs = rng.rand(18, 16, 32) * 100
+        s = make_pd(obs, reg="TV", data="L2", alpha=0.05, L2=8, iterations=9)
+        s.run()
+        plain = s.get_x()
+        s.distribute()
+        s.run()
+        assert np.array_equal(s.get_x(), plain)
+        s.release()
+        img = rng.rand(40, 36) * 100
+        A, A_adj, D, D_adj = deconv_callables(img.shape, [1.0, 1.0])
+        kw = dict(A=A, A_adj=A_adj, b=img.flatten(), B=D, B_adj=D_adj, x0=img.flatten(), dimension=2, alpha=0.01, rho=0.1, iterations=4,
+                  iter_max=6, x_scale=float(img.max()))
+        a = admm.ADMMLinearSolver(**kw)
+        a.run()
+        plain = a.get_x()
+        a.distribute()
+        a.run()
+        assert rel_max(a.get_x(), plain) <= 1e-12
+        a.release()
+    finally:
+        dist.destroy_process_group()
