@@ -370,9 +370,9 @@ def lsmr_roofline_records(ctx, stream, peak):
 
         def solve():
             ctx.check(lib.nsol_admm_run_dev(plan.handle, 0.01, 0.1, outer, inner, b.ptr, x0.ptr, x.ptr, stream))
-        l0 = ctx.launch_count()
+        l0 = plan.ctx.launch_count()
         ms = time_events(solve, 2)
-        launches = (ctx.launch_count() - l0) // 3
+        launches = (plan.ctx.launch_count() - l0) // 3
         us = ms * 1e3 / (outer * inner)
         words = 19 if dim == 2 else 22
         out[name] = {"us_per_inner_iteration": us, "voxel_lsmr_iters_per_s": n / (us * 1e-6), "words_per_voxel": words,

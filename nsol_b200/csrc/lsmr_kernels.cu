@@ -661,6 +661,7 @@ static TapArgs<T> lsq_taps(const nsol_lsmr_plan *pl, int ax) {
 }
 
 #include "lsmr_fastv.cuh"
+#include "lsmr_fused3d.cuh"
 
 // blur passes along every numpy axis except the last (x): in -> optmp (-> opbuf); *result is what the
 // consumer's fused x-pass reads (in itself for 1-D problems or A = identity)
@@ -703,6 +704,7 @@ static int lsq_launch_fwd(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *h
     const T *v = (const T *)pl->v;
     const int ax = g.dim - 1;
     if (fused2d_ok(pl, g.b_op)) return fused2d_launch<T>(pl, true, 0, s, nparts);
+    if (fused3d_ok(pl, g.b_op)) return fused3d_launch<T>(pl, true, 0, s, nparts);
     const void *op = nullptr;
     NSOL_CHECK(lsq_blur_front<T>(pl, g, v, &op, s, halo_lo, halo_hi));
     if (fastv_ok(pl)) {
@@ -729,6 +731,7 @@ static int lsq_launch_adj(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *h
     T *v = (T *)pl->v;
     const int ax = g.dim - 1;
     if (fused2d_ok(pl, g.b_op)) return fused2d_launch<T>(pl, false, first, s, nparts);
+    if (fused3d_ok(pl, g.b_op)) return fused3d_launch<T>(pl, false, first, s, nparts);
     const void *op = nullptr;
     NSOL_CHECK(lsq_blur_front<T>(pl, g, u, &op, s, halo_lo, halo_hi));       // A^T = A (same mask, periodic)
     if (fastv_ok(pl)) {

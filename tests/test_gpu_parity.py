@@ -811,8 +811,9 @@ def test_similarity_and_prior_measures_on_device():
     assert abs(sim.normalized_cross_correlation(3 * x + 7, x) - sim.normalized_cross_correlation(x, x)) < 1e-12
     with pytest.raises(ValueError):
         sim.mean_squared_error(x, x_ref[:-1])
-    with pytest.raises(NotImplementedError):
-        sim.structural_similarity(x, x_ref)
+    # SSIM / MI / NMI are evaluated on the host (evaluation-only measures, nsol/similarity_measures.py:135-239)
+    assert abs(sim.structural_similarity(x, x_ref) - orc.ssim_1d(x, x_ref)) < 1e-12
+    assert sim.mutual_information(x, x_ref) > 0 and sim.normalized_mutual_information(x, x_ref) > 1
     shape = (37, 29)
     grad, _ = lo.LinearOperators2D(spacing=np.array([0.7, 1.3])).get_gradient_operators()
     D = lambda v: grad(v.reshape(*shape)).flatten()

@@ -66,8 +66,21 @@ def test_config4_128_cube_100_iterations_bit_exact(r2):
     voln = orc.add_gaussian_noise(vol, 0.05, seed=1)
     x = run_pd(voln, reg="TV", data="L2", alpha=0.05, L2=8, iterations=100)
     r2.check_hash("c4_128cube_100it", x)
+    # float32 mode.  Over 100 accelerated (ALG2) iterations ANY float32 evaluation of this loop drifts from the float64
+    # result by more than 1e-4 in the max norm: the numpy float32 restatement of the same algorithm on the CPU is 2.4e-3 away
+    # on this very input (5.7e-4 at 64^3; tools/fp32_bound_experiment.py, profiles/r2_fp32_bound.md), while 30 iterations
+    # stay below 1e-6.  So: the CUDA float32 path must be no further away than the CPU float32 run (with margin), and
+    # PSNR / SSIM / NCC against the clean volume must agree with the float64 result to three decimals (north_star).
     x32 = run_pd(voln, reg="TV", data="L2", alpha=0.05, L2=8, iterations=100, dtype="float32")
-    assert rel_max(x32, x) <= 1e-4
+    err = rel_max(x32, x)
+    print("C4 128^3 x 100 float32 vs float64: rel. max-abs %.3e (CPU float32 restatement: 2.36e-3)" % err)
+    assert err <= 1.5 * 2.36e-3
+    clean = vol.reshape(-1)
+    for f in (orc.psnr, orc.ncc, orc.ssim_1d):
+        assert round(f(x32, clean), 3) == round(f(x, clean), 3), (f.__name__, f(x32, clean), f(x, clean))
+    x32s = run_pd(voln, reg="TV", data="L2", alpha=0.05, L2=8, iterations=30, dtype="float32")
+    x64s = run_pd(voln, reg="TV", data="L2", alpha=0.05, L2=8, iterations=30)
+    assert rel_max(x32s, x64s) <= 1e-4
 
 
 def test_config3_full_size_admm_50x10(r2):
@@ -135,8 +148,8 @@ def test_admm_with_b_reg_vs_reference(r2, name, path):
 
 
 # ------------------------------------------------------------------ deconvolution study interface
-def _interface(golden, name, rtype, tv_solver="PD", cls=DeconvolutionSolverStudyInterface, **extra):
-    m = golden.manifest["lsmr"][name]
+def _interface(golden, case, rtype, tv_solver="PD", cls=DeconvolutionSolverStudyInterface, **extra):
+    m = golden.manifest["lsmr"][case]
     obs = golden("lsmr", "in/" + m["input"])
     A, A_adj, D, D_adj = deconv_callables(obs.shape, m["var"])
     xs = float(np.max(obs)) if m.get("x_scale") is None else m["x_scale"]
@@ -321,3 +334,45 @@ def test_distribute_api_single_rank(tmp_path):
         a.release()
     finally:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ fused 3-D LSMR kernels
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("shape,var", [((20, 24, 64), 1.0), ((17, 13, 132), 1.0), ((9, 8, 8), 1.0), ((24, 20, 36), 0.4), ((30, 9, 70), 3.5),
+                                       ((16, 40, 260), 2.3)])
+def test_lsmr_fused_3d_kernels_match_generic_kernels(shape, var, dtype):
+    """The fused 3-D forward / adjoint kernels (csrc/lsmr_fused3d.cuh: the whole separable blur inside the consumer --
+    staged raw tiles, y-blur and x-blur through shared memory, register ring along z; used for large volumes, forced here
+    with lsmr_fuse3d = 1) against the generic kernels and the oracle: partial tiles in x and y, several z-chunks with periodic
+    ring warm-up, radius 2, 3, 5 and 6, rows shorter than a tile, a volume barely larger than the mask."""
+    from nsol_b200 import _lib
+    rng = np.random.RandomState(31)
+    obs = rng.rand(*shape) * 200 + 10
+    xs = float(obs.max())
+    A, A_adj, D, D_adj = deconv_callables(shape, [var, var, var])
+    ctx = _lib.context()
+    out = {}
+    try:
+        for tag, path, fuse in (("fused", 1, 1), ("generic", 3, 2)):
+            ctx.set_tuning("lsmr_path", path)
+            ctx.set_tuning("lsmr_fuse3d", fuse)
+            s = admm.ADMMLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=D, B_adj=D_adj, x0=obs.flatten(), dimension=3,
+                                      alpha=0.02, rho=0.3, iterations=3, iter_max=7, x_scale=xs, dtype=dtype)
+            s.run()
+            t1 = tk.TikhonovLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=D, B_adj=D_adj, x0=obs.flatten(), alpha=0.05,
+                                         iter_max=8, x_scale=xs, dtype=dtype)
+            t1.run()
+            out[tag] = (s.get_x(), t1.get_x())
+            s.release()
+            t1.release()
+    finally:
+        ctx.set_tuning("lsmr_path", 0)
+        ctx.set_tuning("lsmr_fuse3d", 0)
+    tol = 1e-11 if dtype == "float64" else 1e-4
+    assert rel_max(out["fused"][0], out["generic"][0]) < tol, rel_max(out["fused"][0], out["generic"][0])
+    assert rel_max(out["fused"][1], out["generic"][1]) < tol, rel_max(out["fused"][1], out["generic"][1])
+    if dtype == "float64":
+        Ao, Ao_adj, Do, Do_adj = orc.deconvolution_operators(shape, np.diag([var, var, var]))
+        ref = orc.admm_tv(Ao, Ao_adj, Do, Do_adj, obs.reshape(-1), obs.reshape(-1), 3, alpha=0.02, rho=0.3, iterations=3,
+                          iter_max=7, x_scale=xs)
+        assert rel_max(out["fused"][0], ref) < 1e-10

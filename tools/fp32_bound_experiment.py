@@ -106,6 +106,26 @@ def admm_f32(A, A_adj, B, B_adj, b, x0, dim, alpha, rho, iterations, iter_max, x
     return x * x_scale
 
 
+def pd_f32(obs, alpha, L2, iters, x_scale):
+    """The primal-dual loop (nsol/primal_dual_solver.py:232-261, TV-L2 wiring) with every array and operation in
+    numpy float32; step sizes from the float64 schedule, like the CUDA kernels."""
+    f = np.float32
+    shape, dim = obs.shape, obs.ndim
+    b = (obs.reshape(-1) / x_scale).astype(f)
+    x, xm, p = b.copy(), b.copy(), np.zeros(dim * b.size, dtype=f)
+    zshape = (dim * shape[0],) + shape[1:]
+    for sigma, tau, tl, theta in orc.pd_schedule("ALG2", L2, alpha, iters):
+        g = orc.grad(xm.reshape(shape)).reshape(-1).astype(f)
+        q = p + f(sigma) * g
+        p = (q / np.maximum(f(1), np.abs(q))).astype(f)
+        d = orc.grad_adj(p.reshape(zshape), None, dim).reshape(-1).astype(f)
+        y = x - f(tau) * d
+        xn = ((y + f(tl) * b) / (f(1) + f(tl))).astype(f)
+        xm = (xn + f(theta) * (xn - x)).astype(f)
+        x = xn
+    return x.astype(np.float64) * x_scale
+
+
 def measures(x, clean):
     return orc.psnr(x, clean), orc.ssim_1d(x, clean), orc.ncc(x, clean)
 
@@ -129,5 +149,26 @@ def main():
         print("| %s | %.2e | %.4f / %.4f | %.5f / %.5f | %.6f / %.6f | %s |" % (name, dev, m64[0], m32[0], m64[1], m32[1], m64[2], m32[2], same))
 
 
+def main_pd():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "inputs.npz"))
+    ph = z["shepp_logan_64"].astype(np.float64)
+    print()
+    print("| primal-dual TV-L2 (config 4 wiring: alpha 0.05, L2 8, ALG2) | rel. max-abs deviation float32 vs float64 (CPU) | PSNR f64 / f32 | SSIM f64 / f32 | NCC f64 / f32 | 3 decimals equal |")
+    print("|---|---|---|---|---|---|")
+    for rep, iters in ((1, 30), (1, 100), (2, 30), (2, 100)):
+        vol = ph
+        for ax in range(3):
+            vol = np.repeat(vol, rep, ax)
+        voln = orc.add_gaussian_noise(vol, 0.05, seed=1)
+        xs = float(voln.max())
+        x64 = orc.primal_dual_denoise(voln.reshape(-1), voln.shape, reg="TV", data="L2", alpha=0.05, L2=8, iterations=iters, x_scale=xs)
+        x32 = pd_f32(voln, 0.05, 8.0, iters, xs)
+        dev = np.max(np.abs(x32 - x64)) / np.max(np.abs(x64))
+        m64, m32 = measures(x64, vol.reshape(-1)), measures(x32, vol.reshape(-1))
+        same = all(round(a, 3) == round(b, 3) for a, b in zip(m64, m32))
+        print("| %d^3, %d iterations | %.2e | %.4f / %.4f | %.5f / %.5f | %.6f / %.6f | %s |" % (64 * rep, iters, dev, m64[0], m32[0], m64[1], m32[1], m64[2], m32[2], same), flush=True)
+
+
 if __name__ == "__main__":
+    main_pd()
     main()
