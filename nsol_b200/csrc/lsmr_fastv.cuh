@@ -741,8 +741,10 @@ static int fused2d_launch(nsol_lsmr_plan *pl, bool forward, int first, cudaStrea
 // u = [b; sqrt_alpha * b_reg], partial ||u||^2.  nvec = n / VEC vectors per block of u.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(LSMR_THREADS) fastv_rhs_kernel(long long nvec, int rows_b, const T *__restrict__ b, const T *__restrict__ breg,
-                                                                 T sqrt_alpha, T *__restrict__ u, double *__restrict__ part) {
+                                                                 T sqrt_alpha, T *__restrict__ u, double *__restrict__ part,
+                                                                 const double *__restrict__ sa_dev = nullptr) {
     using V = Vec<T, VEC>;
+    if (sa_dev) sqrt_alpha = (T)*sa_dev;      // weight computed on the device (graph-replayed primal-dual deconvolution)
     const long long total = nvec * (1 + rows_b);
     double acc = 0.0;
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (long long)gridDim.x * blockDim.x) {
@@ -888,8 +890,11 @@ __global__ void __launch_bounds__(FAST_TH) fastv_shrink_kernel(FastvGeom<T> g, c
 // =====================================================================================================
 // p <- prox_g*(p + sigma grad(xbar))   (primal_dual_solver.py:242-243; proximal_operators.py:139-140, 157-159)
 template <typename T, int VEC>
-__global__ void __launch_bounds__(FAST_TH) fastv_pdd_dual_kernel(FastvGeom<T> g, const T *__restrict__ xbar, T *__restrict__ p, T sigma, T den, int reg) {
+__global__ void __launch_bounds__(FAST_TH) fastv_pdd_dual_kernel(FastvGeom<T> g, const T *__restrict__ xbar, T *__restrict__ p,
+                                                                 const double *__restrict__ sched, const int *__restrict__ it, int reg) {
     using V = Vec<T, VEC>;
+    const double *srow = sched + (long long)(*it) * 8;      // step sizes of the current iteration (device table)
+    const T sigma = (T)srow[0], den = (T)srow[4];
     const int x0 = (int)(blockIdx.x * FAST_TH + threadIdx.x) * VEC;
     if (x0 >= g.nx) return;
     const int y = (int)blockIdx.y, z = (int)blockIdx.z;
@@ -935,9 +940,11 @@ __global__ void __launch_bounds__(FAST_TH) fastv_pdd_dual_kernel(FastvGeom<T> g,
 
 // b_reg <- (x - tau grad_adj(p)) / prox_scale   (primal_dual_solver.py:246; tikhonov b_reg / x_scale)
 template <typename T, int VEC>
-__global__ void __launch_bounds__(FAST_TH) fastv_pdd_arg_kernel(FastvGeom<T> g, const T *__restrict__ x, const T *__restrict__ p, T tau, T prox_scale,
+__global__ void __launch_bounds__(FAST_TH) fastv_pdd_arg_kernel(FastvGeom<T> g, const T *__restrict__ x, const T *__restrict__ p,
+                                                                const double *__restrict__ sched, const int *__restrict__ it, T prox_scale,
                                                                 T *__restrict__ breg) {
     using V = Vec<T, VEC>;
+    const T tau = (T)sched[(long long)(*it) * 8 + 1];
     const int x0 = (int)(blockIdx.x * FAST_TH + threadIdx.x) * VEC;
     if (x0 >= g.nx) return;
     const int y = (int)blockIdx.y, z = (int)blockIdx.z;
@@ -979,9 +986,11 @@ __global__ void __launch_bounds__(FAST_TH) fastv_pdd_arg_kernel(FastvGeom<T> g, 
 
 // x+ = y * prox_scale ; xbar = x+ + theta (x+ - x) ; x = x+   (solver.py:117-118; primal_dual_solver.py:253)
 template <typename T, int VEC>
-__global__ void __launch_bounds__(LSMR_THREADS) fastv_pdd_relax_kernel(long long nvec, const T *__restrict__ yv, T prox_scale, T theta, T *__restrict__ x,
+__global__ void __launch_bounds__(LSMR_THREADS) fastv_pdd_relax_kernel(long long nvec, const T *__restrict__ yv, T prox_scale,
+                                                                       const double *__restrict__ sched, const int *__restrict__ it, T *__restrict__ x,
                                                                        T *__restrict__ xbar) {
     using V = Vec<T, VEC>;
+    const T theta = (T)sched[(long long)(*it) * 8 + 3];
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nvec; j += (long long)gridDim.x * blockDim.x) {
         const V a = vec_load<T, VEC>(yv + j * VEC), xo = vec_load<T, VEC>(x + j * VEC);
         V xn, xb;

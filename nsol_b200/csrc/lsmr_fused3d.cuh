@@ -62,6 +62,21 @@ __device__ __forceinline__ void f3_wait() { asm volatile("cp.async.wait_group %0
 __device__ __forceinline__ double f3_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
 __device__ __forceinline__ float f3_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 
+// sum over a (32, F3_TY) block; result valid in thread (0, 0).  (block_sum of lsmr_kernels.cu assumes a 1-D block.)
+__device__ __forceinline__ double f3_block_sum(double v) {
+    __shared__ double warp_part[F3_TY];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) warp_part[threadIdx.y] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+#pragma unroll
+        for (int w = 0; w < F3_TY; ++w) r += warp_part[w];      // fixed order: deterministic
+    }
+    return r;
+}
+
 __device__ __forceinline__ int f3_mod(int v, int n) {
     v %= n;
     return v < 0 ? v + n : v;
@@ -298,7 +313,7 @@ __global__ void __launch_bounds__(32 * F3_TY, 2) fused3d_kernel(F3Geom g, T wx, 
         }
     }
     f3_wait<0>();
-    acc = block_sum(acc);
+    acc = f3_block_sum(acc);
     if (threadIdx.x == 0 && threadIdx.y == 0) part[((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = acc;
 }
 

@@ -215,7 +215,9 @@ __device__ __forceinline__ void scal_tests(LsmrScalars *S, double ss) {
     if (istop > 0) S->done = 1;
 }
 
-__global__ void lsmr_scalar_init_beta(LsmrScalars *S, const double *part, int count, double sqrt_alpha, int maxiter) {
+__global__ void lsmr_scalar_init_beta(LsmrScalars *S, const double *part, int count, double sqrt_alpha, int maxiter,
+                                      const double *sa_dev = nullptr) {
+    if (sa_dev) sqrt_alpha = *sa_dev;
     const double ss = reduce_partials(part, count);
     if (threadIdx.x == 0) scal_init_beta(S, ss, sqrt_alpha, maxiter);
 }
@@ -283,7 +285,8 @@ __device__ __forceinline__ void lsq_decode(const LsqGeom<T> &g, long long r, int
 // u = [b; sqrt_alpha * b_reg], partial ||u||^2
 template <typename T>
 __global__ void lsmr_rhs_kernel(LsqGeom<T> g, int rows_b, const T *__restrict__ b, const T *__restrict__ breg, double sqrt_alpha,
-                                T *__restrict__ u, double *__restrict__ part) {
+                                T *__restrict__ u, double *__restrict__ part, const double *__restrict__ sa_dev = nullptr) {
+    if (sa_dev) sqrt_alpha = *sa_dev;       // weight computed on the device (graph-replayed primal-dual deconvolution)
     const long long total = g.n * (1 + rows_b);
     double acc = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -778,15 +781,16 @@ static int lsq_flat_blocks(const nsol_lsmr_plan *pl, long long nvec) {
 }
 
 template <typename T>
-static int lsq_launch_rhs(nsol_lsmr_plan *pl, const LsqGeom<T> &g, int rows_b, const void *b, const void *breg, double sa, cudaStream_t s, int *nparts) {
+static int lsq_launch_rhs(nsol_lsmr_plan *pl, const LsqGeom<T> &g, int rows_b, const void *b, const void *breg, double sa, cudaStream_t s, int *nparts,
+                          const double *sa_dev = nullptr) {
     constexpr int VEC = FastvCfg<T>::VEC;
     if (fastv_ok(pl)) {
         const long long nvec = g.n / VEC;
         const int nb = lsq_flat_blocks(pl, nvec * (1 + rows_b));
-        fastv_rhs_kernel<T, VEC><<<nb, LSMR_THREADS, 0, s>>>(nvec, rows_b, (const T *)b, (const T *)breg, (T)sa, (T *)pl->u, pl->part);
+        fastv_rhs_kernel<T, VEC><<<nb, LSMR_THREADS, 0, s>>>(nvec, rows_b, (const T *)b, (const T *)breg, (T)sa, (T *)pl->u, pl->part, sa_dev);
         *nparts = nb;
     } else {
-        lsmr_rhs_kernel<T><<<pl->nblocks, LSMR_THREADS, 0, s>>>(g, rows_b, (const T *)b, (const T *)breg, sa, (T *)pl->u, pl->part);
+        lsmr_rhs_kernel<T><<<pl->nblocks, LSMR_THREADS, 0, s>>>(g, rows_b, (const T *)b, (const T *)breg, sa, (T *)pl->u, pl->part, sa_dev);
         *nparts = pl->nblocks;
     }
     NSOL_LAUNCH_CHECK(pl->ctx);
@@ -830,7 +834,7 @@ static int lsq_launch_shrink(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void
 
 template <typename T>
 static int lsmr_solve_t(nsol_lsmr_plan *pl, double alpha, const void *b_dev, const void *breg_dev, int maxiter, double lo, double hi,
-                        void *x_out, cudaStream_t s) {
+                        void *x_out, cudaStream_t s, const double *sa_dev = nullptr) {
     nsol_ctx *ctx = pl->ctx;
     const LsqGeom<T> g = make_geom<T>(pl);
     // alpha <= EPS: plain system A x = b (tikhonov_linear_solver.py:241-248)
@@ -842,8 +846,8 @@ static int lsmr_solve_t(nsol_lsmr_plan *pl, double alpha, const void *b_dev, con
     double *part = pl->part;
 
     int rhs_parts = 0;
-    NSOL_CHECK(lsq_launch_rhs<T>(pl, ge, rows_b, b_dev, breg_dev, sa, s, &rhs_parts));
-    lsmr_scalar_init_beta<<<1, 1024, 0, s>>>(pl->S, part, rhs_parts, sa, maxiter);
+    NSOL_CHECK(lsq_launch_rhs<T>(pl, ge, rows_b, b_dev, breg_dev, sa, s, &rhs_parts, sa_dev));
+    lsmr_scalar_init_beta<<<1, 1024, 0, s>>>(pl->S, part, rhs_parts, sa, maxiter, sa_dev);
     NSOL_LAUNCH_CHECK(ctx);
     if (g.ny > 65535 || g.nz > 65535)
         return nsol_fail(ctx, NSOL_EINVAL, "lsmr (multi-kernel path): more than 65535 rows along y or z are not supported");
@@ -1413,8 +1417,14 @@ extern "C" int nsol_lsmr_plan_status(nsol_lsmr_plan *pl, int *itn_out, int *isto
 // primal-dual deconvolution: prox_f = prox_linear_least_squares (one LSMR solve per PD iteration)
 // ---------------------------------------------------------------------------
 // p <- prox_g*(p + sigma grad(xbar))   (primal_dual_solver.py:242-243; proximal_operators.py:139-140, 157-159)
+// Step sizes: row *it of the device table sched[iterations][8] = (sigma, tau, tau*lambda, theta, den_g, den_f, 0, 0)
+// (pd_schedule_rows, float64 host arithmetic in the reference's order) -- read on the device so that ONE captured CUDA graph
+// of a primal-dual iteration can be replayed for every iteration.
 template <typename T>
-__global__ void pdd_dual_kernel(LsqGeom<T> g, const T *__restrict__ xbar, T *__restrict__ p, T sigma, T den, int reg) {
+__global__ void pdd_dual_kernel(LsqGeom<T> g, const T *__restrict__ xbar, T *__restrict__ p, const double *__restrict__ sched,
+                                const int *__restrict__ it, int reg) {
+    const double *row = sched + (long long)(*it) * 8;
+    const T sigma = (T)row[0], den = (T)row[4];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += (long long)gridDim.x * blockDim.x) {
         int idx[3];
         lsq_decode(g, i, idx);
@@ -1432,7 +1442,9 @@ __global__ void pdd_dual_kernel(LsqGeom<T> g, const T *__restrict__ xbar, T *__r
 
 // b_reg <- (x - tau grad_adj(p)) / prox_scale   (primal_dual_solver.py:246; tikhonov b_reg / x_scale)
 template <typename T>
-__global__ void pdd_arg_kernel(LsqGeom<T> g, const T *__restrict__ x, const T *__restrict__ p, T tau, T prox_scale, T *__restrict__ breg) {
+__global__ void pdd_arg_kernel(LsqGeom<T> g, const T *__restrict__ x, const T *__restrict__ p, const double *__restrict__ sched,
+                               const int *__restrict__ it, T prox_scale, T *__restrict__ breg) {
+    const T tau = (T)sched[(long long)(*it) * 8 + 1];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += (long long)gridDim.x * blockDim.x) {
         int idx[3];
         lsq_decode(g, i, idx);
@@ -1449,7 +1461,9 @@ __global__ void pdd_arg_kernel(LsqGeom<T> g, const T *__restrict__ x, const T *_
 
 // x+ = y * prox_scale ; xbar = x+ + theta (x+ - x) ; x = x+   (solver.py:117-118; primal_dual_solver.py:253)
 template <typename T>
-__global__ void pdd_relax_kernel(long long n, const T *__restrict__ y, T prox_scale, T theta, T *__restrict__ x, T *__restrict__ xbar) {
+__global__ void pdd_relax_kernel(long long n, const T *__restrict__ y, T prox_scale, const double *__restrict__ sched,
+                                 const int *__restrict__ it, T *__restrict__ x, T *__restrict__ xbar) {
+    const T theta = (T)sched[(long long)(*it) * 8 + 3];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const T xn = y[i] * prox_scale;
         const T xo = x[i];
@@ -1457,6 +1471,13 @@ __global__ void pdd_relax_kernel(long long n, const T *__restrict__ y, T prox_sc
         x[i] = xn;
     }
 }
+
+// device-side bookkeeping of the graph-replayed iteration: sa = sqrt(1 / (tau * lambda)) of the current row (the weight of
+// the identity rows of the prox's Tikhonov system, proximal_operators.py:58-75) before the solve; ++it after the relaxation
+__global__ void pdd_prepare_kernel(const double *__restrict__ sched, const int *__restrict__ it, double *__restrict__ sa) {
+    sa[0] = sqrt(1.0 / sched[(long long)(*it) * 8 + 2]);
+}
+__global__ void pdd_advance_kernel(int *it) { it[0] += 1; }
 
 template <typename T>
 static int pd_deconv_t(nsol_lsmr_plan *pl, const nsol_pd_desc *pd, int iterations, int iter_max, double prox_scale, double *x_host,
@@ -1469,7 +1490,7 @@ static int pd_deconv_t(nsol_lsmr_plan *pl, const nsol_pd_desc *pd, int iteration
     const bool vec = fastv_ok(pl) && g.ny <= 65535 && g.nz <= 65535;      // row-mapped 128-bit kernels (csrc/lsmr_fastv.cuh)
     const FastvGeom<T> fg = make_fastv_geom<T>(g);
     const dim3 vgrid((g.nx / VEC + FAST_TH - 1) / FAST_TH, g.ny, g.nz);
-    // state: x = pl->xbuf, xbar = pl->h reuse is not possible (LSMR owns h) -> admm_v holds [xbar | y | spare], admm_w holds p
+    // state: x = pl->xbuf; admm_v holds [xbar | y | spare], admm_w holds p (the LSMR solve owns u, v, h, hbar, x)
     T *x = (T *)pl->xbuf, *xbar = (T *)pl->admm_v, *p = (T *)pl->admm_w, *breg = (T *)pl->breg;
     T *y = (pl->gv.dim >= 2) ? xbar + n : nullptr;
     void *ybuf = y;
@@ -1478,42 +1499,112 @@ static int pd_deconv_t(nsol_lsmr_plan *pl, const nsol_pd_desc *pd, int iteration
         NSOL_CUDA(ctx, cudaMalloc(&ybuf, n * sizeof(T)));
         own_y = true;
     }
-    std::vector<double> rows((size_t)(iterations > 0 ? iterations : 1) * 8);
+    // step-size table on the device: [iterations][8] doubles, then sa (1 double) and the iteration counter
+    const int rows_n = iterations > 0 ? iterations : 1;
+    std::vector<double> rows((size_t)rows_n * 8);
     pd_schedule_rows(*pd, pd->alpha[0], iterations, rows.data());
-    NSOL_CUDA(ctx, cudaMemcpyAsync(xbar, x, n * sizeof(T), cudaMemcpyDeviceToDevice, s));
-    NSOL_CUDA(ctx, cudaMemsetAsync(p, 0, n * pl->gv.dim * sizeof(T), s));
+    for (int i = 0; i < iterations; ++i)
+        if (!(1.0 / rows[(size_t)i * 8 + 2] > 1e-10)) {
+            if (own_y) cudaFree(ybuf);
+            return nsol_fail(ctx, NSOL_EINVAL, "pd deconvolution: tau * lambda = %g is too large for the Tikhonov weight", rows[(size_t)i * 8 + 2]);
+        }
+    char *tab = nullptr;
+    const size_t tab_bytes = rows.size() * sizeof(double) + 2 * sizeof(double);
+    cudaError_t e0 = cudaMalloc((void **)&tab, tab_bytes);
+    if (e0 != cudaSuccess) {
+        if (own_y) cudaFree(ybuf);
+        return nsol_fail(ctx, NSOL_ENOMEM, "pd deconvolution: cudaMalloc(%zu) -> %s", tab_bytes, cudaGetErrorString(e0));
+    }
+    double *sched = (double *)tab, *sa_dev = sched + rows.size();
+    int *it_dev = (int *)(sa_dev + 1);
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(s);
+        cudaFree(tab);
+        if (own_y) cudaFree(ybuf);
+    };
     int rc = NSOL_OK;
-    if (iterates_host) rc = lsq_download(pl, x, pd->x_scale, iterates_host, s);
-    for (int it = 0; it < iterations && rc == NSOL_OK; ++it) {
-        const double *r = &rows[(size_t)it * 8];
+    {
+        cudaError_t e = cudaMemcpyAsync(sched, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(sa_dev, 0, 2 * sizeof(double), s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(xbar, x, n * sizeof(T), cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(p, 0, n * pl->gv.dim * sizeof(T), s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);       // `rows` is a host temporary
+        if (e != cudaSuccess) rc = nsol_fail(ctx, NSOL_ECUDA, "pd deconvolution: %s", cudaGetErrorString(e));
+    }
+    if (rc == NSOL_OK && iterates_host) rc = lsq_download(pl, x, pd->x_scale, iterates_host, s);
+    const int coop = rc == NSOL_OK ? lsmr_use_coop(pl) : 0;
+    if (coop < 0) rc = coop;
+    const int reg = pd->reg;
+
+    // one primal-dual iteration (primal_dual_solver.py:242-253); every kernel takes its step sizes from row *it_dev
+    auto iteration = [&](cudaStream_t st, double alpha_host) -> int {
         if (vec) {
-            fastv_pdd_dual_kernel<T, VEC><<<vgrid, FAST_TH, 0, s>>>(fg, xbar, p, (T)r[0], (T)r[4], pd->reg);
-            ctx->launches++;
-            fastv_pdd_arg_kernel<T, VEC><<<vgrid, FAST_TH, 0, s>>>(fg, x, p, (T)r[1], (T)prox_scale, breg);
-            ctx->launches++;
+            fastv_pdd_dual_kernel<T, VEC><<<vgrid, FAST_TH, 0, st>>>(fg, xbar, p, sched, it_dev, reg);
+            NSOL_LAUNCH_CHECK(ctx);
+            fastv_pdd_arg_kernel<T, VEC><<<vgrid, FAST_TH, 0, st>>>(fg, x, p, sched, it_dev, (T)prox_scale, breg);
+            NSOL_LAUNCH_CHECK(ctx);
         } else {
-            pdd_dual_kernel<T><<<nb, th, 0, s>>>(g, xbar, p, (T)r[0], (T)r[4], pd->reg);
-            ctx->launches++;
-            pdd_arg_kernel<T><<<nb, th, 0, s>>>(g, x, p, (T)r[1], (T)prox_scale, breg);
-            ctx->launches++;
+            pdd_dual_kernel<T><<<nb, th, 0, st>>>(g, xbar, p, sched, it_dev, reg);
+            NSOL_LAUNCH_CHECK(ctx);
+            pdd_arg_kernel<T><<<nb, th, 0, st>>>(g, x, p, sched, it_dev, (T)prox_scale, breg);
+            NSOL_LAUNCH_CHECK(ctx);
         }
         // tikhonov: alpha = 1 / (tau * lambda), b_reg = y / prox_scale, B = I  (proximal_operators.py:58-75)
-        rc = lsmr_solve_any(pl, 1.0 / r[2], pl->bbuf, breg, iter_max, 0.0, INFINITY, ybuf, s);
-        if (rc != NSOL_OK) break;
-        if (vec) fastv_pdd_relax_kernel<T, VEC><<<lsq_flat_blocks(pl, (long long)n / VEC), th, 0, s>>>((long long)n / VEC, (const T *)ybuf, (T)prox_scale, (T)r[3], x, xbar);
-        else pdd_relax_kernel<T><<<nb, th, 0, s>>>((long long)n, (const T *)ybuf, (T)prox_scale, (T)r[3], x, xbar);
-        ctx->launches++;
-        if (iterates_host) rc = lsq_download(pl, x, pd->x_scale, iterates_host + (size_t)(it + 1) * n, s);
+        if (coop) {
+            NSOL_CHECK(lsmr_solve_coop<T>(pl, alpha_host, pl->bbuf, breg, iter_max, 0.0, INFINITY, ybuf, 0, 0.0, st));
+        } else {
+            pdd_prepare_kernel<<<1, 1, 0, st>>>(sched, it_dev, sa_dev);
+            NSOL_LAUNCH_CHECK(ctx);
+            NSOL_CHECK(lsmr_solve_t<T>(pl, 1.0, pl->bbuf, breg, iter_max, 0.0, INFINITY, ybuf, st, sa_dev));
+        }
+        if (vec) fastv_pdd_relax_kernel<T, VEC><<<lsq_flat_blocks(pl, (long long)n / VEC), th, 0, st>>>((long long)n / VEC, (const T *)ybuf, (T)prox_scale, sched, it_dev, x, xbar);
+        else pdd_relax_kernel<T><<<nb, th, 0, st>>>((long long)n, (const T *)ybuf, (T)prox_scale, sched, it_dev, x, xbar);
+        NSOL_LAUNCH_CHECK(ctx);
+        pdd_advance_kernel<<<1, 1, 0, st>>>(it_dev);
+        NSOL_LAUNCH_CHECK(ctx);
+        return NSOL_OK;
+    };
+
+    if (rc == NSOL_OK && !coop && !iterates_host && iterations >= 2) {
+        // The launch sequence of an iteration is fixed and all its parameters live on the device: capture it once,
+        // replay it `iterations` times (~90 kernels per iteration stop paying individual launch latency).
+        const int64_t l0 = ctx->launches;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+        if (ce == cudaSuccess) {
+            rc = iteration(s, 0.0);
+            ce = cudaStreamEndCapture(s, &graph);
+        }
+        if (rc == NSOL_OK && ce != cudaSuccess) rc = nsol_fail(ctx, NSOL_ECUDA, "pd deconvolution: graph capture failed: %s", cudaGetErrorString(ce));
+        const int64_t per_iteration = ctx->launches - l0;
+        if (rc == NSOL_OK) {
+            ce = cudaGraphInstantiate(&exec, graph, 0);
+            if (ce != cudaSuccess) rc = nsol_fail(ctx, NSOL_ECUDA, "pd deconvolution: graph instantiation failed: %s", cudaGetErrorString(ce));
+        }
+        if (graph) cudaGraphDestroy(graph);
+        for (int it = 0; rc == NSOL_OK && it < iterations; ++it) {
+            ce = cudaGraphLaunch(exec, s);
+            if (ce != cudaSuccess) rc = nsol_fail(ctx, NSOL_ECUDA, "pd deconvolution: graph launch failed: %s", cudaGetErrorString(ce));
+        }
+        ctx->launches += per_iteration * (iterations - 1);
+        if (exec) {
+            cudaError_t se = cudaStreamSynchronize(s);       // the executable graph must outlive its launches
+            cudaGraphExecDestroy(exec);
+            if (rc == NSOL_OK && se != cudaSuccess) rc = nsol_fail(ctx, NSOL_ECUDA, "pd deconvolution: %s", cudaGetErrorString(se));
+        }
+    } else {
+        for (int it = 0; it < iterations && rc == NSOL_OK; ++it) {
+            rc = iteration(s, 1.0 / rows[(size_t)it * 8 + 2]);
+            if (rc == NSOL_OK && iterates_host) rc = lsq_download(pl, x, pd->x_scale, iterates_host + (size_t)(it + 1) * n, s);
+        }
     }
     if (rc == NSOL_OK) {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = nsol_fail(ctx, NSOL_ECUDA, "pd deconvolution: %s", cudaGetErrorString(e));
     }
     if (rc == NSOL_OK) rc = lsq_download(pl, x, pd->x_scale, x_host, s);
-    if (own_y) {
-        cudaStreamSynchronize(s);
-        cudaFree(ybuf);
-    }
+    cleanup();
     return rc;
 }
 
