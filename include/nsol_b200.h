@@ -83,7 +83,7 @@ int nsol_create(int device, nsol_ctx **out);
 void nsol_destroy(nsol_ctx *ctx);
 /* ctx may be NULL: returns the calling thread's last creation error. */
 const char *nsol_last_error(const nsol_ctx *ctx);
-/* tuning knobs ("pd_zc", "pd_ty", "pd_variant", "lsmr_blocks", "lsmr_path", "lsmr_fuse2d", "lsmr_fuse3d", "link_timeout_ms"); value <= 0 restores the default */
+/* tuning knobs ("pd_zc", "pd_ty", "pd_variant", "pd_persist", "lsmr_blocks", "lsmr_path", "lsmr_fuse2d", "lsmr_fuse3d", "link_timeout_ms"); value <= 0 restores the default */
 int nsol_set_tuning(nsol_ctx *ctx, const char *key, int value);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t nsol_launch_count(const nsol_ctx *ctx);

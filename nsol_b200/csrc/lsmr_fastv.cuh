@@ -61,16 +61,18 @@ static FastvGeom<T> make_fastv_geom(const LsqGeom<T> &g) {
 // Every thread produces FASTV_ROWS consecutive outputs of its line from one sweep over FASTV_ROWS + 2R inputs
 // (all loads issued up front): (ROWS + 2R) / ROWS loads per output instead of 2R + 1.
 #define FASTV_ROWS 8
+// (bx, by, bz): block index of the row-mapped grid -- the kernel's blockIdx, or a virtual index in the persistent
+// cooperative solve (lsmr_coopv_kernel)
 template <typename T, int R, int VEC>
-__global__ void __launch_bounds__(FAST_TH) fastv_blur_pass_kernel(FastvGeom<T> g, TapsR<T, R> tp, int kaxis, const T *__restrict__ in,
-                                                                  T *__restrict__ out, const T *__restrict__ halo_lo,
-                                                                  const T *__restrict__ halo_hi) {
+__device__ __forceinline__ void fastv_blur_pass_body(const FastvGeom<T> &g, const TapsR<T, R> &tp, int kaxis, const T *__restrict__ in,
+                                                     T *__restrict__ out, const T *__restrict__ halo_lo, const T *__restrict__ halo_hi,
+                                                     unsigned bx, unsigned by, unsigned bz) {
     using V = Vec<T, VEC>;
-    const int x = (int)(blockIdx.x * FAST_TH + threadIdx.x) * VEC;
+    const int x = (int)(bx * FAST_TH + threadIdx.x) * VEC;
     if (x >= g.nx) return;
     // the grid axis of the blurred direction counts groups of FASTV_ROWS positions
-    const int y = kaxis == 1 ? 0 : (int)blockIdx.y, z = kaxis == 2 ? 0 : (int)blockIdx.z;
-    const int pos0 = (kaxis == 1 ? (int)blockIdx.y : (int)blockIdx.z) * FASTV_ROWS;
+    const int y = kaxis == 1 ? 0 : (int)by, z = kaxis == 2 ? 0 : (int)bz;
+    const int pos0 = (kaxis == 1 ? (int)by : (int)bz) * FASTV_ROWS;
     const long long plane = (long long)g.nx * g.ny;
     const long long st = kaxis == 1 ? (long long)g.nx : plane;
     const int ext = kaxis == 1 ? g.ny : g.nz;
@@ -110,6 +112,13 @@ __global__ void __launch_bounds__(FAST_TH) fastv_blur_pass_kernel(FastvGeom<T> g
     }
 }
 
+template <typename T, int R, int VEC>
+__global__ void __launch_bounds__(FAST_TH) fastv_blur_pass_kernel(FastvGeom<T> g, TapsR<T, R> tp, int kaxis, const T *__restrict__ in,
+                                                                  T *__restrict__ out, const T *__restrict__ halo_lo,
+                                                                  const T *__restrict__ halo_hi) {
+    fastv_blur_pass_body<T, R, VEC>(g, tp, kaxis, in, out, halo_lo, halo_hi, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
 // x-blur of VEC consecutive outputs of one row (periodic): reads the aligned 128-bit vectors covering
 // [x - R, x + VEC - 1 + R]; tap order as fast_blur_line
 template <typename T, int R, int VEC>
@@ -147,14 +156,12 @@ __device__ __forceinline__ Vec<T, VEC> fastv_blur_x(const TapsR<T, R> &tp, const
 
 // u <- (u * inv_beta) * (-alpha) + [A v; sqrt_alpha B v], v = vhat * inv_alpha, partial ||u||^2   (lsmr.py:336-338)
 template <typename T, int R, int VEC>
-__global__ void __launch_bounds__(FAST_TH) fastv_fwd_kernel(FastvGeom<T> g, const LsmrScalars *__restrict__ S, TapsR<T, R> tx,
-                                                            const T *__restrict__ src, const T *__restrict__ vhat, T *__restrict__ u,
-                                                            double *__restrict__ part, const T *__restrict__ v_hi) {
+__device__ __forceinline__ void fastv_fwd_body(const FastvGeom<T> &g, const LsmrScalars *S, const TapsR<T, R> &tx, const T *__restrict__ src,
+                                               const T *__restrict__ vhat, T *__restrict__ u, const T *__restrict__ v_hi, unsigned bx,
+                                               unsigned by, unsigned bz, double &acc) {
     using V = Vec<T, VEC>;
-    if (S->done) return;
-    const int x = (int)(blockIdx.x * FAST_TH + threadIdx.x) * VEC;
-    const int y = (int)blockIdx.y, z = (int)blockIdx.z;
-    double acc = 0.0;
+    const int x = (int)(bx * FAST_TH + threadIdx.x) * VEC;
+    const int y = (int)by, z = (int)bz;
     if (x < g.nx) {
         const T inv_alpha = (T)S->inv_alpha, inv_beta = (T)S->inv_beta, malpha = (T)(-S->alpha), sa = (T)S->sqrt_alpha;
         const long long plane = (long long)g.nx * g.ny;
@@ -237,20 +244,27 @@ __global__ void __launch_bounds__(FAST_TH) fastv_fwd_kernel(FastvGeom<T> g, cons
             vec_store<T, VEC>(uk + i, uv);
         }
     }
+}
+
+template <typename T, int R, int VEC>
+__global__ void __launch_bounds__(FAST_TH) fastv_fwd_kernel(FastvGeom<T> g, const LsmrScalars *__restrict__ S, TapsR<T, R> tx,
+                                                            const T *__restrict__ src, const T *__restrict__ vhat, T *__restrict__ u,
+                                                            double *__restrict__ part, const T *__restrict__ v_hi) {
+    if (S->done) return;
+    double acc = 0.0;
+    fastv_fwd_body<T, R, VEC>(g, S, tx, src, vhat, u, v_hi, blockIdx.x, blockIdx.y, blockIdx.z, acc);
     acc = block_sum(acc);
     if (threadIdx.x == 0) part[((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = acc;
 }
 
 // vhat <- (vhat * inv_alpha) * (-beta) + (A^T u0 + sqrt_alpha B^T u1..), u = uhat * inv_beta, partial ||v||^2 (lsmr.py:342-344)
 template <typename T, int R, int VEC>
-__global__ void __launch_bounds__(FAST_TH) fastv_adj_kernel(FastvGeom<T> g, const LsmrScalars *__restrict__ S, TapsR<T, R> tx,
-                                                            const T *__restrict__ src, const T *__restrict__ u, T *__restrict__ vhat,
-                                                            double *__restrict__ part, int first, const T *__restrict__ uz_lo) {
+__device__ __forceinline__ void fastv_adj_body(const FastvGeom<T> &g, const LsmrScalars *S, const TapsR<T, R> &tx, const T *__restrict__ src,
+                                               const T *__restrict__ u, T *__restrict__ vhat, int first, const T *__restrict__ uz_lo,
+                                               unsigned bx, unsigned by, unsigned bz, double &acc) {
     using V = Vec<T, VEC>;
-    if (S->done) return;
-    const int x = (int)(blockIdx.x * FAST_TH + threadIdx.x) * VEC;
-    const int y = (int)blockIdx.y, z = (int)blockIdx.z;
-    double acc = 0.0;
+    const int x = (int)(bx * FAST_TH + threadIdx.x) * VEC;
+    const int y = (int)by, z = (int)bz;
     if (x < g.nx) {
         const T inv_alpha = (T)S->inv_alpha, inv_beta = (T)S->inv_beta, mbeta = (T)(-S->beta), sa = (T)S->sqrt_alpha;
         const long long plane = (long long)g.nx * g.ny;
@@ -316,6 +330,15 @@ __global__ void __launch_bounds__(FAST_TH) fastv_adj_kernel(FastvGeom<T> g, cons
         }
         vec_store<T, VEC>(vhat + i, vv);
     }
+}
+
+template <typename T, int R, int VEC>
+__global__ void __launch_bounds__(FAST_TH) fastv_adj_kernel(FastvGeom<T> g, const LsmrScalars *__restrict__ S, TapsR<T, R> tx,
+                                                            const T *__restrict__ src, const T *__restrict__ u, T *__restrict__ vhat,
+                                                            double *__restrict__ part, int first, const T *__restrict__ uz_lo) {
+    if (S->done) return;
+    double acc = 0.0;
+    fastv_adj_body<T, R, VEC>(g, S, tx, src, u, vhat, first, uz_lo, blockIdx.x, blockIdx.y, blockIdx.z, acc);
     acc = block_sum(acc);
     if (threadIdx.x == 0) part[((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = acc;
 }

@@ -553,13 +553,15 @@ struct nsol_lsmr_plan {
     int tap_off[3] = {0, 0, 0};
     double *coop_part = nullptr;   // [3][coop_blocks]
     int coop_blocks = 0;           // 0: not initialised, -1: unavailable
+    double *coopv_part = nullptr;  // persistent vector solve (lsmr_coopv.cuh): [3][coopv_blocks]
+    int coopv_blocks = 0;
 };
 
 extern "C" void nsol_lsmr_plan_destroy(nsol_lsmr_plan *pl) {
     if (!pl) return;
     if (pl->ctx) nsol_bind_device(pl->ctx);
     void *ptrs[] = {pl->u, pl->v, pl->h, pl->hbar, pl->x, pl->opbuf, pl->optmp, pl->breg, pl->admm_v, pl->admm_w, pl->admm_c,
-                    pl->bbuf, pl->xbuf, pl->stage, pl->part, pl->S, pl->taps_dev, pl->coop_part,
+                    pl->bbuf, pl->xbuf, pl->stage, pl->part, pl->S, pl->taps_dev, pl->coop_part, pl->coopv_part,
                     pl->halo_v_lo, pl->halo_v_hi, pl->halo_u_lo, pl->halo_u_hi, pl->halo_uz_lo, pl->halo_x_hi, pl->ssbuf};
     for (void *p : ptrs) cudaFree(p);
     if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
@@ -872,6 +874,7 @@ static int lsmr_solve_t(nsol_lsmr_plan *pl, double alpha, const void *b_dev, con
 }
 
 #include "lsmr_coop.cuh"
+#include "lsmr_coopv.cuh"
 
 // one-time setup of the cooperative path: taps on the device, co-resident grid size, partial sums
 template <typename T>
@@ -969,6 +972,11 @@ static int lsmr_use_coop(nsol_lsmr_plan *pl) {
 
 static int lsmr_solve_any(nsol_lsmr_plan *pl, double alpha, const void *b_dev, const void *breg_dev, int maxiter, double lo, double hi,
                           void *x_out, cudaStream_t s) {
+    if (coopv_ok(pl)) {      // small / mid-size problem: the whole solve as one persistent vector launch
+        const int rc = pl->gv.dtype == NSOL_F32 ? lsmr_solve_coopv<float>(pl, alpha, b_dev, breg_dev, maxiter, lo, hi, x_out, s)
+                                                : lsmr_solve_coopv<double>(pl, alpha, b_dev, breg_dev, maxiter, lo, hi, x_out, s);
+        if (rc != NSOL_ESTATE) return rc;
+    }
     const int coop = lsmr_use_coop(pl);
     if (coop < 0) return coop;
     if (coop) {
@@ -1074,6 +1082,14 @@ static int admm_iterations_t(nsol_lsmr_plan *pl, double alpha, double rho, int i
         NSOL_CHECK(lsq_launch_shrink<T>(pl, g, x_dev, w, alpha / rho, v, w, breg, nullptr, 0, st));
         return NSOL_OK;
     };
+    if (coopv_ok(pl)) {
+        // persistent vector solve: two launches per outer iteration (solve, shrink) -- nothing left for a graph to save
+        for (int it = 0; it < iterations; ++it) {
+            NSOL_CHECK(outer_iteration(s));
+            if (iterates_host) NSOL_CHECK(lsq_download(pl, x_dev, x_scale, iterates_host + (size_t)(it + 1) * n, s));
+        }
+        return NSOL_OK;
+    }
     const int coop = lsmr_use_coop(pl);
     if (coop < 0) return coop;
     if (coop && iterations > 0) {
@@ -1532,7 +1548,8 @@ static int pd_deconv_t(nsol_lsmr_plan *pl, const nsol_pd_desc *pd, int iteration
         if (e != cudaSuccess) rc = nsol_fail(ctx, NSOL_ECUDA, "pd deconvolution: %s", cudaGetErrorString(e));
     }
     if (rc == NSOL_OK && iterates_host) rc = lsq_download(pl, x, pd->x_scale, iterates_host, s);
-    const int coop = rc == NSOL_OK ? lsmr_use_coop(pl) : 0;
+    const bool coopv = coopv_ok(pl);
+    const int coop = (rc == NSOL_OK && !coopv) ? lsmr_use_coop(pl) : 0;
     if (coop < 0) rc = coop;
     const int reg = pd->reg;
 
@@ -1550,7 +1567,9 @@ static int pd_deconv_t(nsol_lsmr_plan *pl, const nsol_pd_desc *pd, int iteration
             NSOL_LAUNCH_CHECK(ctx);
         }
         // tikhonov: alpha = 1 / (tau * lambda), b_reg = y / prox_scale, B = I  (proximal_operators.py:58-75)
-        if (coop) {
+        if (coopv) {
+            NSOL_CHECK(lsmr_solve_any(pl, alpha_host, pl->bbuf, breg, iter_max, 0.0, INFINITY, ybuf, st));
+        } else if (coop) {
             NSOL_CHECK(lsmr_solve_coop<T>(pl, alpha_host, pl->bbuf, breg, iter_max, 0.0, INFINITY, ybuf, 0, 0.0, st));
         } else {
             pdd_prepare_kernel<<<1, 1, 0, st>>>(sched, it_dev, sa_dev);
@@ -1565,7 +1584,7 @@ static int pd_deconv_t(nsol_lsmr_plan *pl, const nsol_pd_desc *pd, int iteration
         return NSOL_OK;
     };
 
-    if (rc == NSOL_OK && !coop && !iterates_host && iterations >= 2) {
+    if (rc == NSOL_OK && !coop && !coopv && !iterates_host && iterations >= 2) {
         // The launch sequence of an iteration is fixed and all its parameters live on the device: capture it once,
         // replay it `iterations` times (~90 kernels per iteration stop paying individual launch latency).
         const int64_t l0 = ctx->launches;

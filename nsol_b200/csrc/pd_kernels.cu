@@ -259,8 +259,10 @@ struct PdStep {
 #ifndef NSOL_PD_MINB_F32
 #define NSOL_PD_MINB_F32 2
 #endif
+// One CTA's share of an iteration: tile (bx, by), z-chunk / batch member bzi.  Called by pd_iter_kernel with its block
+// index and by the persistent cooperative kernel (small problems) with virtual block indices.
 template <typename T, int VEC, bool HAS_Y, int REG, int DATA, bool LINK, bool UNIT>
-__global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : (HAS_Y ? NSOL_PD_MINB_F64 : NSOL_PD_MINB_F64_2D)) pd_iter_kernel(const PdArgs<T> a) {
+__device__ __forceinline__ void pd_iter_body(const PdArgs<T> &a, const unsigned bx, const unsigned by, const unsigned bzi) {
     using V = Vec<T, VEC>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -268,12 +270,12 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : (HAS_
     const int TY = HAS_Y ? (int)blockDim.y : 1;
     const int ty = HAS_Y ? (int)threadIdx.y : 0;
     const int tile_w = (int)blockDim.x * VEC;
-    const int x0 = (int)blockIdx.x * tile_w + (int)threadIdx.x * VEC;
-    const int y0 = HAS_Y ? (int)blockIdx.y * TY : 0;
+    const int x0 = (int)bx * tile_w + (int)threadIdx.x * VEC;
+    const int y0 = HAS_Y ? (int)by * TY : 0;
     const int y = y0 + ty;
-    int chunk = a.chunk_first + (int)(blockIdx.z % (unsigned)a.nsel) * a.chunk_stride;
+    int chunk = a.chunk_first + (int)(bzi % (unsigned)a.nsel) * a.chunk_stride;
     if (LINK && a.front_chunks) chunk = chunk == 0 ? 0 : (chunk == 1 ? a.nchunks - 1 : chunk - 1);
-    const int bz = (int)(blockIdx.z / (unsigned)a.nsel);
+    const int bz = (int)(bzi / (unsigned)a.nsel);
     const int z0 = chunk * a.zc;
     const int z1 = min(a.nz, z0 + a.zc);
     const bool xin = x0 < a.nx;
@@ -450,6 +452,38 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : (HAS_
         if (z + 1 < z1) plane_step(z + 1, alt, cur);
     }
     if (LINK) pd_link_finish<T, VEC>(a, z0, z1, hrow, active);
+}
+
+template <typename T, int VEC, bool HAS_Y, int REG, int DATA, bool LINK, bool UNIT>
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : (HAS_Y ? NSOL_PD_MINB_F64 : NSOL_PD_MINB_F64_2D)) pd_iter_kernel(const PdArgs<T> a) {
+    pd_iter_body<T, VEC, HAS_Y, REG, DATA, LINK, UNIT>(a, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// ---- persistent variant for small 2-D / 1-D problems (BASELINE configs 1 and 2: one 256^2 / 1024^2 image) --------------
+// The whole state (x, xbar, b, p: 2.5 MB at 256^2, 42 MB at 1024^2 in float64) lives in L2, so an iteration costs a few
+// microseconds of work and as much again in launch latency.  Here ONE cooperative launch runs all n iterations: every CTA
+// loops over its share of the virtual blocks of an iteration (same tiles, same arithmetic as pd_iter_kernel -- bit-identical),
+// then the grid synchronises and the ping-pong buffers swap.  Step sizes come from the same device table.
+#include <cooperative_groups.h>
+template <typename T, int VEC, int REG, int DATA, bool UNIT>
+__global__ void __launch_bounds__(128) pd_iter_persist_kernel(PdArgs<T> a, int iterations, unsigned vgx, unsigned vgz) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const unsigned total = vgx * vgz;
+    for (int i = 0; i < iterations; ++i) {
+        for (unsigned vb = blockIdx.x; vb < total; vb += gridDim.x) pd_iter_body<T, VEC, false, REG, DATA, false, UNIT>(a, vb % vgx, 0u, vb / vgx);
+        // the state this iteration wrote becomes the input of the next one
+        const T *xb = a.xbar_in;
+        a.xbar_in = a.xbar_out;
+        a.xbar_out = const_cast<T *>(xb);
+        const T *t0 = a.px_in;
+        a.px_in = a.px_out;
+        a.px_out = const_cast<T *>(t0);
+        const T *t1 = a.pz_in;
+        a.pz_in = a.pz_out;
+        a.pz_out = const_cast<T *>(t1);
+        a.it += 1;
+        if (i + 1 < iterations) grid.sync();
+    }
 }
 
 #include "pd_bulk_kernel.cuh"
@@ -997,6 +1031,46 @@ static int pd_launch_bulk(const nsol_pd_plan *pl, const PdArgs<T> &a, dim3 grid,
     return NSOL_EINVAL;
 }
 
+// persistent cooperative launch of n iterations (2-D / 1-D vector path, no z-slab neighbours)
+template <typename T, int VEC, int R, int D, bool UNIT>
+static int pd_launch_persist_one(nsol_pd_plan *pl, PdArgs<T> a, dim3 grid, dim3 block, int n, cudaStream_t s) {
+    nsol_ctx *ctx = pl->ctx;
+    static int per_sm[64] = {0};      // co-resident CTAs per SM of this instantiation, per device
+    const int dev = ctx->device & 63;
+    if (per_sm[dev] == 0) {
+        int v = 0;
+        NSOL_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, pd_iter_persist_kernel<T, VEC, R, D, UNIT>, (int)block.x, 0));
+        per_sm[dev] = v > 0 ? v : -1;
+    }
+    if (per_sm[dev] < 0) return NSOL_ESTATE;
+    unsigned vgx = grid.x, vgz = grid.z;
+    const long long total = (long long)vgx * vgz;
+    long long cap = (long long)per_sm[dev] * ctx->sm_count;
+    const unsigned blocks = (unsigned)(total < cap ? total : cap);
+    void *params[] = {(void *)&a, (void *)&n, (void *)&vgx, (void *)&vgz};
+    NSOL_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)pd_iter_persist_kernel<T, VEC, R, D, UNIT>, dim3(blocks), block, params, 0, s));
+    ctx->launches++;
+    return NSOL_OK;
+}
+
+template <typename T, int VEC>
+static int pd_launch_persist(nsol_pd_plan *pl, const PdArgs<T> &a, dim3 grid, dim3 block, int n, cudaStream_t s) {
+    const int reg = pl->desc.reg, data = pl->desc.data;
+    const bool unit = a.wx == T(1) && (!a.has_z || a.wz == T(1));
+#define NSOL_PD_CASE(R, D)                                                                           \
+    if (reg == R && data == D)                                                                       \
+        return unit ? pd_launch_persist_one<T, VEC, R, D, true>(pl, a, grid, block, n, s)            \
+                    : pd_launch_persist_one<T, VEC, R, D, false>(pl, a, grid, block, n, s);
+    NSOL_PD_CASE(NSOL_REG_TV, NSOL_DATA_L2)
+    NSOL_PD_CASE(NSOL_REG_TV, NSOL_DATA_L1)
+    NSOL_PD_CASE(NSOL_REG_HUBER, NSOL_DATA_L2)
+    NSOL_PD_CASE(NSOL_REG_HUBER, NSOL_DATA_L1)
+    NSOL_PD_CASE(NSOL_REG_TK1, NSOL_DATA_L2)
+    NSOL_PD_CASE(NSOL_REG_TK1, NSOL_DATA_L1)
+#undef NSOL_PD_CASE
+    return NSOL_EINVAL;
+}
+
 // rows per CTA (3-D only) and planes per z-chunk
 static void pd_tiling(const nsol_ctx *ctx, const GridView &gv, int vecw, int *ty_out, int *zc_out, bool link = false) {
     const bool has_y = gv.comp_y >= 0;
@@ -1031,7 +1105,7 @@ static void pd_tiling(const nsol_ctx *ctx, const GridView &gv, int vecw, int *ty
 // part: 0 = whole iteration; 1 = only the first and last z-chunk (the planes a z-slab neighbour
 // needs), no state advance; 2 = the remaining interior chunks, then advance.
 template <typename T, int VECW>
-static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0) {
+static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, int persist_n = 0) {
     nsol_ctx *ctx = pl->ctx;
     const GridView &gv = pl->gv;
     const int cur = pl->cur, nxt = cur ^ 1;
@@ -1128,6 +1202,18 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0) {
     const long long gz = (long long)a.nsel * gv.batch;
     if (gz > 65535) return nsol_fail(ctx, NSOL_EINVAL, "pd: nchunks*batch = %lld exceeds the grid limit; raise pd_zc", gz);
     grid.z = (unsigned)gz;
+    if (persist_n > 1) {
+        // small 2-D / 1-D problem (the caller checked): all persist_n iterations in one cooperative launch
+        if constexpr (VECW > 1) {
+            int rc = pd_launch_persist<T, VECW>(pl, a, grid, block, persist_n, s);
+            if (rc == NSOL_OK) {
+                pl->cur = (persist_n & 1) ? nxt : cur;
+                pl->it += persist_n;
+            }
+            return rc;
+        }
+        return NSOL_ESTATE;
+    }
     // kernel variant: 1 = register-pipelined loads (LDG), 2 = TMA bulk-async staged tiles;
     // default: bulk for float64 3-D volumes (issue-bound with LDG), LDG otherwise
     int variant = ctx->pd_variant;
@@ -1161,6 +1247,14 @@ extern "C" int nsol_pd_plan_iterate(nsol_pd_plan *pl, int n, nsol_stream s) {
     const int vecw = gv.dtype == NSOL_F32 ? 4 : 2;
     const bool vec_ok = (gv.nx % vecw) == 0;
     if (pl->link_on && !pl->link_fresh) NSOL_CHECK(pd_link_publish(pl, st));   // also for n == 0 (publish only)
+    // Small 2-D / 1-D problems whose state is L2-resident (BASELINE configs 1, 2): one persistent cooperative launch for all n
+    // iterations instead of n launches ("pd_persist" tuning knob: 0 auto, 1 whenever possible, 2 never).
+    if (n >= 2 && gv.comp_y < 0 && vec_ok && !pl->link_on && !pl->halo_above && !pl->halo_below && ctx->pd_persist != 2 &&
+        (ctx->pd_persist == 1 || pl->bytes <= ((size_t)96 << 20))) {
+        int rc = gv.dtype == NSOL_F32 ? pd_launch_iteration<float, 4>(pl, st, 0, n) : pd_launch_iteration<double, 2>(pl, st, 0, n);
+        if (rc == NSOL_OK) return NSOL_OK;
+        if (rc != NSOL_ESTATE) return rc;      // NSOL_ESTATE: cooperative launch unavailable -> one launch per iteration
+    }
     for (int i = 0; i < n; ++i) {
         int rc;
         if (gv.dtype == NSOL_F32) rc = vec_ok ? pd_launch_iteration<float, 4>(pl, st) : pd_launch_iteration<float, 1>(pl, st);

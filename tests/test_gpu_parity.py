@@ -671,7 +671,7 @@ def test_standalone_prox_linear_least_squares(golden):
     assert rel_max(got, ref) < F64_LSMR_TOL
 
 
-@pytest.mark.parametrize("path", [1, 2, 3])
+@pytest.mark.parametrize("path", [1, 2, 3, 4])
 def test_lsmr_multi_kernel_and_cooperative_paths(golden, path):
     """Both LSMR implementations (1 = one kernel per phase + CUDA graph for ADMM, 2 = a single
     cooperative launch with grid.sync between phases) against the reference fixtures."""
