@@ -41,6 +41,7 @@ extern "C" int nsol_create(int device, nsol_ctx **out) {
     if (const char *v = getenv("NSOL_LSMR_FUSE2D")) ctx->lsmr_fuse2d = atoi(v);
     if (const char *v = getenv("NSOL_LSMR_FUSE3D")) ctx->lsmr_fuse3d = atoi(v);
     if (const char *v = getenv("NSOL_PD_PERSIST")) ctx->pd_persist = atoi(v);
+    if (const char *v = getenv("NSOL_PD_PERSIST_BLOCKS")) ctx->pd_persist_blocks = atoi(v);
     *out = ctx;
     return NSOL_OK;
 }
@@ -63,6 +64,7 @@ extern "C" int nsol_set_tuning(nsol_ctx *ctx, const char *key, int value) {
     else if (!strcmp(key, "lsmr_fuse2d")) ctx->lsmr_fuse2d = value;
     else if (!strcmp(key, "lsmr_fuse3d")) ctx->lsmr_fuse3d = value;
     else if (!strcmp(key, "pd_persist")) ctx->pd_persist = value;
+    else if (!strcmp(key, "pd_persist_blocks")) ctx->pd_persist_blocks = value;
     else return nsol_fail(ctx, NSOL_EINVAL, "nsol_set_tuning: unknown key '%s'", key);
     return NSOL_OK;
 }

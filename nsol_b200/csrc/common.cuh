@@ -18,6 +18,7 @@ struct nsol_ctx {
     int pd_zc = 0;
     int pd_ty = 0;
     int pd_variant = 0;
+    int pd_persist_blocks = 0;   // persistent primal-dual kernel: cap on the number of CTAs (0: one per SM)
     int pd_persist = 0;     // persistent cooperative primal-dual kernel for small 2-D / 1-D problems: 0 auto, 1 whenever possible, 2 never
     int lsmr_blocks = 0;
     int lsmr_path = 0;      // 0 auto, 1 multi-kernel (vector kernels where they apply), 2 cooperative single launch (generic phases),

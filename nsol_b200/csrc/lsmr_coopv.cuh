@@ -264,9 +264,10 @@ static int lsmr_solve_coopv_r(nsol_lsmr_plan *pl, double alpha, const void *b_de
     a.vgx = (unsigned)((pl->gv.nx / VEC + FAST_TH - 1) / FAST_TH);
     // grid: one CTA per row-mapped virtual block up to what is co-resident; grid.sync() cost grows with the block count
     long long want = (long long)a.vgx * pl->gv.ny * pl->gv.nz;
-    int cap_per_sm = per_sm[dev] > 4 ? 4 : per_sm[dev];
-    long long cap = (long long)cap_per_sm * ctx->sm_count;
-    if (ctx->lsmr_blocks > 0 && ctx->lsmr_blocks < cap) cap = ctx->lsmr_blocks;
+    // (one same-address atomic per CTA: ~6 us per sync with 4 CTAs per SM) -> one CTA per SM unless "lsmr_blocks" says otherwise
+    long long cap = (long long)per_sm[dev] * ctx->sm_count;
+    const long long lim = ctx->lsmr_blocks > 0 ? ctx->lsmr_blocks : ctx->sm_count;
+    if (lim < cap) cap = lim;
     const int blocks = (int)(want < cap ? (want > 0 ? want : 1) : cap);
     if (pl->coopv_blocks < blocks) {
         if (pl->coopv_part) {

@@ -1045,7 +1045,11 @@ static int pd_launch_persist_one(nsol_pd_plan *pl, PdArgs<T> a, dim3 grid, dim3 
     if (per_sm[dev] < 0) return NSOL_ESTATE;
     unsigned vgx = grid.x, vgz = grid.z;
     const long long total = (long long)vgx * vgz;
+    // grid.sync() is one same-address atomic per CTA: its cost grows with the CTA count (~6 us with 4 CTAs per SM, measured
+    // with the LSMR solves), so the default is one CTA per SM
     long long cap = (long long)per_sm[dev] * ctx->sm_count;
+    const long long want = ctx->pd_persist_blocks > 0 ? ctx->pd_persist_blocks : ctx->sm_count;
+    if (want < cap) cap = want;
     const unsigned blocks = (unsigned)(total < cap ? total : cap);
     void *params[] = {(void *)&a, (void *)&n, (void *)&vgx, (void *)&vgz};
     NSOL_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)pd_iter_persist_kernel<T, VEC, R, D, UNIT>, dim3(blocks), block, params, 0, s));
