@@ -374,10 +374,17 @@ def lsmr_roofline_records(ctx, stream, peak):
         ms = time_events(solve, 2)
         launches = (plan.ctx.launch_count() - l0) // 3
         us = ms * 1e3 / (outer * inner)
-        words = 19 if dim == 2 else 22                   # SURVEY.md 8d
+        # 19 (2-D) / 22 (3-D) words per voxel and inner iteration, plus per OUTER iteration (1 + 3d) words for the
+        # shrink / w update (K7) and ~12 words of LSMR start-up (right-hand side, first adjoint, start vectors, clip)
+        words = 19 if dim == 2 else 22
+        words_outer = (1 + 3 * dim) + 12
+        words_all = words + words_outer / float(inner)
         out[name] = {"us_per_inner_iteration": us, "voxel_lsmr_iters_per_s": n / (us * 1e-6), "words_per_voxel": words,
                      "achieved_gbs": words * esz * n / (us * 1e-6) / 1e9, "hbm_frac_of_measured": words * esz * n / (us * 1e-6) / 1e9 / peak,
-                     "launches_per_solve": launches, "outer_x_inner": "%dx%d" % (outer, inner), "dtype": dtype}
+                     "words_per_voxel_incl_outer_iteration": words_all,
+                     "hbm_frac_of_measured_incl_outer_iteration": words_all * esz * n / (us * 1e-6) / 1e9 / peak,
+                     "launches_per_solve": launches, "outer_x_inner": "%dx%d" % (outer, inner), "dtype": dtype,
+                     "note": "the time includes the per-outer-iteration kernels; 'words_per_voxel' counts the inner iteration only"}
         for buf in (b, x0, x):
             buf.free()
         plan.close()

@@ -207,10 +207,13 @@ __global__ void __launch_bounds__(FAST_TH) lsmr_coopv_kernel(const CoopvArgs<T, 
 }
 
 // The persistent vector solve applies when the vector kernels do, every blurred axis has the same radius (or A is the
-// identity) and the problem is small enough to be latency-bound: <= 2^20 elements by default ("lsmr_path": 0 auto,
-// 4 = whenever possible; 1, 2, 3 select the other paths).
+// identity) and the problem is small: <= 2^18 elements by default ("lsmr_path": 0 auto, 4 = whenever possible; 1, 2, 3
+// select the other paths).  Measured on B200 (profiles/r2_latency_configs.md): 256^2 23.9 us per inner iteration against
+// 25.2 us for the graph-replayed multi-kernel path, 512^2 29.0 vs 28.4, 1024^2 54 vs 50 -- a dependent phase costs ~4.8 us
+// whether it ends in a grid.sync() or in a kernel boundary inside a CUDA graph, so the persistent form only wins where the
+// launch train cannot be graphed (primal-dual deconvolution: 377 vs 404 us per PD iteration at 512^2) or is very short.
 #ifndef NSOL_COOPV_MAX_ELEMENTS
-#define NSOL_COOPV_MAX_ELEMENTS (1ll << 20)
+#define NSOL_COOPV_MAX_ELEMENTS (1ll << 18)
 #endif
 static int coopv_radius(const nsol_lsmr_plan *pl) {
     if (pl->desc.a_op != NSOL_A_BLUR) return 0;
@@ -264,10 +267,11 @@ static int lsmr_solve_coopv_r(nsol_lsmr_plan *pl, double alpha, const void *b_de
     a.vgx = (unsigned)((pl->gv.nx / VEC + FAST_TH - 1) / FAST_TH);
     // grid: one CTA per row-mapped virtual block up to what is co-resident; grid.sync() cost grows with the block count
     long long want = (long long)a.vgx * pl->gv.ny * pl->gv.nz;
-    // (one same-address atomic per CTA: ~6 us per sync with 4 CTAs per SM) -> one CTA per SM unless "lsmr_blocks" says otherwise
-    long long cap = (long long)per_sm[dev] * ctx->sm_count;
-    const long long lim = ctx->lsmr_blocks > 0 ? ctx->lsmr_blocks : ctx->sm_count;
-    if (lim < cap) cap = lim;
+    // measured (profiles/r2_latency_configs.md): flat from 2 CTAs per SM on, slower below (the phases are bound by the latency
+    // of their dependent L2 accesses, which more CTAs overlap -- not by grid.sync())
+    int cap_per_sm = per_sm[dev] > 4 ? 4 : per_sm[dev];
+    long long cap = (long long)cap_per_sm * ctx->sm_count;
+    if (ctx->lsmr_blocks > 0 && ctx->lsmr_blocks < cap) cap = ctx->lsmr_blocks;
     const int blocks = (int)(want < cap ? (want > 0 ? want : 1) : cap);
     if (pl->coopv_blocks < blocks) {
         if (pl->coopv_part) {

@@ -714,7 +714,7 @@ static bool fused2d_ok(const nsol_lsmr_plan *pl, int b_op) {
     const int rz = pl->desc.radius[0], rx = pl->desc.radius[1];
     if (rz != rx || rz < 1) return false;                    // instantiated for isotropic masks only
     if (gv.nz < 2 * rz + 1) return false;
-    if (pl->ctx->lsmr_fuse2d == 1) return true;
+    if (pl->ctx->lsmr_fuse2d == 1 || pl->ctx->lsmr_fuse2d == 3) return true;      // 3: forced, first-generation kernels
     // from 16 MB per vector (1536^2 float64: 86.9 vs 107.7 us per iteration; 1024^2 float32: 42.5 vs 39.3 us): below,
     // the row-mapped kernels have more threads in flight
     return gv.n * (long long)pl->esz >= (1ll << 24);
@@ -726,7 +726,7 @@ static int fused2d_rows_per_chunk(const nsol_lsmr_plan *pl, int vec) {
     // aim at >= 2 blocks of 128 threads per SM and warp-strip; never fewer than 16 rows per chunk
     int zc = 64;
     while (zc > 16 && (long long)strips * ((gv.nz + zc - 1) / zc) < (long long)pl->ctx->sm_count * 8) zc /= 2;
-    if (pl->ctx->lsmr_fuse2d == 1 && gv.nz < 64) zc = gv.nz < 8 ? gv.nz : 8;     // tests: several chunks on small images
+    if ((pl->ctx->lsmr_fuse2d == 1 || pl->ctx->lsmr_fuse2d == 3) && gv.nz < 64) zc = gv.nz < 8 ? gv.nz : 8;     // tests: several chunks on small images
     return zc;
 }
 

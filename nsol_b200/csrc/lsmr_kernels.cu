@@ -667,6 +667,7 @@ static TapArgs<T> lsq_taps(const nsol_lsmr_plan *pl, int ax) {
 
 #include "lsmr_fastv.cuh"
 #include "lsmr_fused3d.cuh"
+#include "lsmr_fused2d_v2.cuh"
 
 // blur passes along every numpy axis except the last (x): in -> optmp (-> opbuf); *result is what the
 // consumer's fused x-pass reads (in itself for 1-D problems or A = identity)
@@ -708,7 +709,7 @@ static int lsq_launch_fwd(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *h
     T *u = (T *)pl->u;
     const T *v = (const T *)pl->v;
     const int ax = g.dim - 1;
-    if (fused2d_ok(pl, g.b_op)) return fused2d_launch<T>(pl, true, 0, s, nparts);
+    if (fused2d_ok(pl, g.b_op)) return pl->ctx->lsmr_fuse2d == 3 ? fused2d_launch<T>(pl, true, 0, s, nparts) : fused2d_v2_launch<T>(pl, true, 0, s, nparts);
     if (fused3d_ok(pl, g.b_op)) return fused3d_launch<T>(pl, true, 0, s, nparts);
     const void *op = nullptr;
     NSOL_CHECK(lsq_blur_front<T>(pl, g, v, &op, s, halo_lo, halo_hi));
@@ -735,7 +736,7 @@ static int lsq_launch_adj(nsol_lsmr_plan *pl, const LsqGeom<T> &g, const void *h
     const T *u = (const T *)pl->u;
     T *v = (T *)pl->v;
     const int ax = g.dim - 1;
-    if (fused2d_ok(pl, g.b_op)) return fused2d_launch<T>(pl, false, first, s, nparts);
+    if (fused2d_ok(pl, g.b_op)) return pl->ctx->lsmr_fuse2d == 3 ? fused2d_launch<T>(pl, false, first, s, nparts) : fused2d_v2_launch<T>(pl, false, first, s, nparts);
     if (fused3d_ok(pl, g.b_op)) return fused3d_launch<T>(pl, false, first, s, nparts);
     const void *op = nullptr;
     NSOL_CHECK(lsq_blur_front<T>(pl, g, u, &op, s, halo_lo, halo_hi));       // A^T = A (same mask, periodic)

@@ -1045,11 +1045,11 @@ static int pd_launch_persist_one(nsol_pd_plan *pl, PdArgs<T> a, dim3 grid, dim3 
     if (per_sm[dev] < 0) return NSOL_ESTATE;
     unsigned vgx = grid.x, vgz = grid.z;
     const long long total = (long long)vgx * vgz;
-    // grid.sync() is one same-address atomic per CTA: its cost grows with the CTA count (~6 us with 4 CTAs per SM, measured
-    // with the LSMR solves), so the default is one CTA per SM
+    // as many CTAs as are co-resident: measured on B200 (profiles/r2_latency_configs.md) the iteration time falls with the CTA
+    // count until every virtual block has its own CTA (256^2: flat from 74 CTAs at 4.9 us; 1024^2: 27 us with 148 CTAs, 11.7 us
+    // with 592) -- the phases are bound by the latency of their dependent L2 accesses, not by the cost of grid.sync()
     long long cap = (long long)per_sm[dev] * ctx->sm_count;
-    const long long want = ctx->pd_persist_blocks > 0 ? ctx->pd_persist_blocks : ctx->sm_count;
-    if (want < cap) cap = want;
+    if (ctx->pd_persist_blocks > 0 && ctx->pd_persist_blocks < cap) cap = ctx->pd_persist_blocks;
     const unsigned blocks = (unsigned)(total < cap ? total : cap);
     void *params[] = {(void *)&a, (void *)&n, (void *)&vgx, (void *)&vgz};
     NSOL_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)pd_iter_persist_kernel<T, VEC, R, D, UNIT>, dim3(blocks), block, params, 0, s));

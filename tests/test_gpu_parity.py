@@ -766,7 +766,7 @@ def test_lsmr_fused_2d_kernels_match_generic_kernels(shape, var, dtype):
     ctx = _lib.context()
     out = {}
     try:
-        for tag, path, fuse in (("fused", 1, 1), ("generic", 3, 2)):
+        for tag, path, fuse in (("fused", 1, 1), ("fused_gen1", 1, 3), ("generic", 3, 2)):
             ctx.set_tuning("lsmr_path", path)
             ctx.set_tuning("lsmr_fuse2d", fuse)
             s = admm.ADMMLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=D, B_adj=D_adj, x0=obs.flatten(), dimension=2,
@@ -782,6 +782,7 @@ def test_lsmr_fused_2d_kernels_match_generic_kernels(shape, var, dtype):
     tol = 1e-11 if dtype == "float64" else F32_TOL
     assert rel_max(out["fused"][0], out["generic"][0]) < tol, rel_max(out["fused"][0], out["generic"][0])
     assert rel_max(out["fused"][1], out["generic"][1]) < tol
+    assert rel_max(out["fused_gen1"][0], out["generic"][0]) < tol and rel_max(out["fused_gen1"][1], out["generic"][1]) < tol
     if dtype == "float64":
         Ao, Ao_adj, Do, Do_adj = orc.deconvolution_operators(shape, np.diag([var, var]))
         ref = orc.admm_tv(Ao, Ao_adj, Do, Do_adj, obs.reshape(-1), obs.reshape(-1), 2, alpha=0.02, rho=0.3, iterations=3,
