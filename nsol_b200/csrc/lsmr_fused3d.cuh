@@ -50,6 +50,10 @@ struct F3 {
 struct F3Geom {
     int nx, ny, nz, zc;
     long long n;
+    // z-slab decomposition (nsol_lsmr_plan_slab): planes below 0 / above nz - 1 of the blurred array come from the halo
+    // buffers filled by the neighbour exchange (ring: periodic blur) instead of the in-volume wrap; the gradient has a
+    // neighbour below / above or the zero boundary at the global ends
+    int slab, grad_lo, grad_hi, ghost;
 };
 
 __device__ __forceinline__ void f3_cp16(void *smem, const void *gmem) {
@@ -85,7 +89,9 @@ __device__ __forceinline__ int f3_mod(int v, int n) {
 template <typename T, int R, int VEC, bool FWD>
 __global__ void __launch_bounds__(32 * F3_TY, 2) fused3d_kernel(F3Geom g, T wx, T wy, T wz, const LsmrScalars *__restrict__ S, TapsR<T, R> tx,
                                                                 TapsR<T, R> ty_, TapsR<T, R> tz, const T *__restrict__ blur_in, T *__restrict__ u,
-                                                                T *__restrict__ vhat, double *__restrict__ part, int first) {
+                                                                T *__restrict__ vhat, double *__restrict__ part, int first,
+                                                                const T *__restrict__ halo_lo, const T *__restrict__ halo_hi,
+                                                                const T *__restrict__ uz_lo) {
     using V = Vec<T, VEC>;
     using L = F3<T, VEC, R>;
     extern __shared__ __align__(16) unsigned char f3_smem[];
@@ -122,9 +128,14 @@ __global__ void __launch_bounds__(32 * F3_TY, 2) fused3d_kernel(F3Geom g, T wx, 
 
     auto issue_raw = [&](int j) {        // raw plane of ring index j: volume plane z0 - R + j (periodic)
         int zi = z0 - R + j;
-        zi += zi < 0 ? g.nz : 0;
-        zi -= zi >= g.nz ? g.nz : 0;
-        const T *src = blur_in + (long long)zi * plane;
+        const T *src;
+        if (g.slab) {            // planes beyond the slab: the neighbours' planes in the halo buffers
+            src = zi < 0 ? halo_lo + (long long)(zi + g.ghost) * plane : (zi >= g.nz ? halo_hi + (long long)(zi - g.nz) * plane : blur_in + (long long)zi * plane);
+        } else {
+            zi += zi < 0 ? g.nz : 0;
+            zi -= zi >= g.nz ? g.nz : 0;
+            src = blur_in + (long long)zi * plane;
+        }
         T *st = s_raw + (j % L::S) * L::RAW;
 #pragma unroll
         for (int q = 0; q < NR; ++q) {
@@ -163,6 +174,7 @@ __global__ void __launch_bounds__(32 * F3_TY, 2) fused3d_kernel(F3Geom g, T wx, 
     for (int i = 0; i <= 2 * R; ++i) ring[i] = vec_zero<T, VEC>();
     V u3_prev = vec_zero<T, VEC>();                          // adjoint: u3 of plane z - 1 (zero below the first plane)
     if (!FWD && active && z0 > 0) u3_prev = vec_load<T, VEC>(u3 + (long long)(z0 - 1) * plane + (long long)y * g.nx + x);
+    if (!FWD && active && z0 == 0 && g.slab && g.grad_lo) u3_prev = vec_load<T, VEC>(uz_lo + (long long)y * g.nx + x);   // lower neighbour's last u_z plane
     double acc = 0.0;
 
     // ---- prologue: planes 0 .. P-1 (one group each) -----------------------------------------------------------
@@ -252,7 +264,7 @@ __global__ void __launch_bounds__(32 * F3_TY, 2) fused3d_kernel(F3Geom g, T wx, 
                 const T right = (x + VEC < g.nx) ? rz[VEC] : T(0);                                  // zero boundary, not the periodic halo
                 V vup = vec_zero<T, VEC>(), vz = vec_zero<T, VEC>();
                 if (y + 1 < g.ny) vup = vec_load<T, VEC>(rz + L::LEN);
-                if (z + 1 < g.nz) vz = vec_load<T, VEC>(rz1);
+                if (z + 1 < g.nz || (g.slab && g.grad_hi)) vz = vec_load<T, VEC>(rz1);      // (slab: the staged plane nz is the upper neighbour's first plane)
                 V a0 = vec_load<T, VEC>(op + (0 * F3_TY + ty) * L::W + lane * VEC);
                 V a1 = vec_load<T, VEC>(op + (1 * F3_TY + ty) * L::W + lane * VEC);
                 V a2 = vec_load<T, VEC>(op + (2 * F3_TY + ty) * L::W + lane * VEC);
@@ -322,7 +334,7 @@ __global__ void __launch_bounds__(32 * F3_TY, 2) fused3d_kernel(F3Geom g, T wx, 
 // possible, 2 never
 static bool fused3d_ok(const nsol_lsmr_plan *pl, int b_op) {
     const GridView &gv = pl->gv;
-    if (gv.dim != 3 || pl->slab || pl->desc.a_op != NSOL_A_BLUR || b_op != NSOL_B_GRAD || !fastv_ok(pl)) return false;
+    if (gv.dim != 3 || pl->desc.a_op != NSOL_A_BLUR || b_op != NSOL_B_GRAD || !fastv_ok(pl)) return false;
     if (pl->ctx->lsmr_fuse3d == 2) return false;
     const int r = pl->desc.radius[0];
     if (r < 1 || r != pl->desc.radius[1] || r != pl->desc.radius[2]) return false;
@@ -354,6 +366,10 @@ static int fused3d_launch_r(nsol_lsmr_plan *pl, int first, cudaStream_t s, int *
     g.nz = gv.nz;
     g.n = gv.n;
     g.zc = fused3d_planes_per_chunk(pl, VEC);
+    g.slab = pl->slab ? 1 : 0;
+    g.grad_lo = pl->grad_lo;
+    g.grad_hi = pl->grad_hi;
+    g.ghost = pl->ghost;
     const dim3 grid((gv.nx + L::W - 1) / L::W, (gv.ny + F3_TY - 1) / F3_TY, (gv.nz + g.zc - 1) / g.zc);
     const dim3 block(32, F3_TY, 1);
     const size_t smem = L::smem(FWD);
@@ -367,7 +383,8 @@ static int fused3d_launch_r(nsol_lsmr_plan *pl, int first, cudaStream_t s, int *
     // numpy axis 0 = z, 1 = y, 2 = x; derivative component k acts on axis 2 - k
     fused3d_kernel<T, R, VEC, FWD><<<grid, block, smem, s>>>(g, (T)gv.w[0], (T)gv.w[1], (T)gv.w[2], pl->S, lsq_taps_r<T, R>(pl, 2), lsq_taps_r<T, R>(pl, 1),
                                                             lsq_taps_r<T, R>(pl, 0), FWD ? (const T *)pl->v : (const T *)pl->u, (T *)pl->u,
-                                                            (T *)pl->v, pl->part, first);
+                                                            (T *)pl->v, pl->part, first, (const T *)(FWD ? pl->halo_v_lo : pl->halo_u_lo),
+                                                            (const T *)(FWD ? pl->halo_v_hi : pl->halo_u_hi), (const T *)pl->halo_uz_lo);
     *nparts = (int)(grid.x * grid.y * grid.z);
     NSOL_LAUNCH_CHECK(pl->ctx);
     return NSOL_OK;

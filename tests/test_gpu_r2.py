@@ -376,3 +376,46 @@ def test_lsmr_fused_3d_kernels_match_generic_kernels(shape, var, dtype):
         ref = orc.admm_tv(Ao, Ao_adj, Do, Do_adj, obs.reshape(-1), obs.reshape(-1), 3, alpha=0.02, rho=0.3, iterations=3,
                           iter_max=7, x_scale=xs)
         assert rel_max(out["fused"][0], ref) < 1e-10
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("shape,nslabs", [((18, 10, 20), 2), ((24, 9, 68), 3), ((9, 12, 16), 1)])
+def test_admm_zslab_emulation_with_fused_3d_kernels(shape, nslabs, dtype):
+    """The fused 3-D LSMR kernels in z-slab mode: planes beyond the slab are read from the halo buffers (ring exchange of
+    the periodic blur halos, neighbour planes for the gradient / its adjoint) instead of the in-volume wrap.  Same
+    single-process emulation of S slabs as test_admm_zslab_emulation_matches_unsharded, forced onto the fused kernels."""
+    from nsol_b200 import _lib
+    from nsol_b200.distributed import SlabLsq, slab_admm_program, run_slab_admm_emulated, slab_bounds
+    from nsol_b200.linear_solver import probe_least_squares
+    rng = np.random.RandomState(19)
+    obs = rng.rand(*shape) * 200 + 20
+    alpha, rho, iterations, iter_max = 0.02, 0.2, 3, 6
+    xs = float(obs.max())
+    A, A_adj, D, D_adj = deconv_callables(shape, [1.0, 1.0, 1.0])
+    ctx = _lib.context()
+    ctx.set_tuning("lsmr_fuse3d", 2)
+    ctx.set_tuning("lsmr_path", 1)
+    slabs = []
+    try:
+        ref_solver = admm.ADMMLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=D, B_adj=D_adj, x0=obs.flatten(), dimension=3, alpha=alpha,
+                                           rho=rho, iterations=iterations, iter_max=iter_max, x_scale=xs, dtype=dtype)
+        ref_solver.run()
+        ref = ref_solver.get_x()
+        ref_solver.release()
+        ctx.set_tuning("lsmr_fuse3d", 1)
+        info = probe_least_squares(A, A_adj, D, D_adj, obs.size)
+        for r in range(nslabs):
+            z_lo, z_hi = slab_bounds(shape[0], r, nslabs)
+            sl = SlabLsq(ctx, dict(info, shape=(z_hi - z_lo,) + tuple(shape[1:])), dtype, r, nslabs)
+            part = np.ascontiguousarray(obs[z_lo:z_hi]).reshape(-1) / xs
+            sl.upload(part, part)
+            slabs.append(sl)
+        run_slab_admm_emulated(slabs, slab_admm_program(iterations, iter_max, alpha, rho))
+        out = np.concatenate([sl.download(xs) for sl in slabs])
+    finally:
+        for sl in slabs:
+            sl.close()
+        ctx.set_tuning("lsmr_fuse3d", 0)
+        ctx.set_tuning("lsmr_path", 0)
+    tol = 1e-9 if dtype == "float64" else 1e-4
+    assert rel_max(out, ref) < tol, rel_max(out, ref)
