@@ -83,11 +83,16 @@ int nsol_create(int device, nsol_ctx **out);
 void nsol_destroy(nsol_ctx *ctx);
 /* ctx may be NULL: returns the calling thread's last creation error. */
 const char *nsol_last_error(const nsol_ctx *ctx);
-/* tuning knobs ("pd_zc", "pd_ty", "pd_variant", "pd_persist", "lsmr_blocks", "lsmr_path", "lsmr_fuse2d", "lsmr_fuse3d", "link_timeout_ms"); value <= 0 restores the default */
+/* tuning knobs ("pd_zc", "pd_ty", "pd_variant", "pd_persist", "lsmr_blocks", "lsmr_path", "lsmr_fuse2d", "lsmr_fuse3d", "link_timeout_ms", "debug_guard"); value <= 0 restores the default */
 int nsol_set_tuning(nsol_ctx *ctx, const char *key, int value);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t nsol_launch_count(const nsol_ctx *ctx);
 int nsol_device_sm_count(const nsol_ctx *ctx);
+/* Debug aid (the pool's compute-sanitizer is closed): after nsol_set_tuning(ctx, "debug_guard", 1) the arrays of every plan
+ * created on this context sit between two 64 KiB guard bands filled with NaN bit patterns -- an out-of-bounds read drags NaN
+ * into the result, an out-of-bounds write is counted here.  Synchronises the device.  violations_out: guard bytes overwritten
+ * so far; arrays_out (may be NULL): guarded arrays currently alive. */
+int nsol_debug_guard_check(nsol_ctx *ctx, int64_t *violations_out, int *arrays_out);
 
 /* ---- memory / stream helpers (plumbing for hosts without a CUDA binding) - */
 int nsol_device_alloc(nsol_ctx *ctx, size_t bytes, void **dev);

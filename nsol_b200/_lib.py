@@ -55,6 +55,7 @@ SIGNATURES = {
     "nsol_set_tuning": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "nsol_launch_count": (C.c_int64, [C.c_void_p]),
     "nsol_device_sm_count": (C.c_int, [C.c_void_p]),
+    "nsol_debug_guard_check": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "nsol_device_alloc": (C.c_int, [C.c_void_p, C.c_size_t, c_void_pp]),
     "nsol_device_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nsol_host_alloc": (C.c_int, [C.c_void_p, C.c_size_t, c_void_pp]),
@@ -180,6 +181,12 @@ class Context(object):
 
     def sm_count(self):
         return int(self.lib.nsol_device_sm_count(self.handle))
+
+    def guard_check(self):
+        """(guard bytes overwritten so far, guarded arrays alive) -- see the "debug_guard" tuning knob."""
+        bad, n = C.c_int64(), C.c_int()
+        self.check(self.lib.nsol_debug_guard_check(self.handle, C.byref(bad), C.byref(n)))
+        return int(bad.value), int(n.value)
 
     # ---- memory
     def device_alloc(self, nbytes):

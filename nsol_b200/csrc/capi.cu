@@ -63,9 +63,71 @@ extern "C" int nsol_set_tuning(nsol_ctx *ctx, const char *key, int value) {
     else if (!strcmp(key, "link_timeout_ms")) ctx->link_timeout_ms = value;
     else if (!strcmp(key, "lsmr_fuse2d")) ctx->lsmr_fuse2d = value;
     else if (!strcmp(key, "lsmr_fuse3d")) ctx->lsmr_fuse3d = value;
+    else if (!strcmp(key, "debug_guard")) ctx->debug_guard = value;
     else if (!strcmp(key, "pd_persist")) ctx->pd_persist = value;
     else if (!strcmp(key, "pd_persist_blocks")) ctx->pd_persist_blocks = value;
     else return nsol_fail(ctx, NSOL_EINVAL, "nsol_set_tuning: unknown key '%s'", key);
+    return NSOL_OK;
+}
+
+// ---- guarded plan arrays (debug_guard) -------------------------------------------------------------------------
+cudaError_t nsol_plan_alloc(nsol_ctx *ctx, void **ptr, size_t bytes) {
+    if (!ctx->debug_guard) return cudaMalloc(ptr, bytes);
+    const size_t user = (bytes + 255) / 256 * 256;
+    char *base = nullptr;
+    cudaError_t e = cudaMalloc((void **)&base, user + 2 * NSOL_GUARD_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(base, 0xFF, user + 2 * NSOL_GUARD_BYTES);      // all-ones words are NaN in float32 and float64
+    if (e != cudaSuccess) {
+        cudaFree(base);
+        return e;
+    }
+    *ptr = base + NSOL_GUARD_BYTES;
+    ctx->guarded[*ptr] = std::make_pair((void *)base, bytes);
+    return cudaSuccess;
+}
+
+void nsol_plan_free(nsol_ctx *ctx, void *ptr) {
+    if (!ptr) return;
+    if (ctx) {
+        auto it = ctx->guarded.find(ptr);
+        if (it != ctx->guarded.end()) {
+            cudaFree(it->second.first);
+            ctx->guarded.erase(it);
+            return;
+        }
+    }
+    cudaFree(ptr);
+}
+
+__global__ void guard_check_kernel(const unsigned char *lo, size_t lo_len, const unsigned char *hi, size_t hi_len, unsigned long long *bad) {
+    unsigned long long n = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = t; i < lo_len; i += stride) n += lo[i] != 0xFF;
+    for (size_t i = t; i < hi_len; i += stride) n += hi[i] != 0xFF;
+    if (n) atomicAdd(bad, n);
+}
+
+// Number of guard-band bytes any kernel has overwritten so far (synchronises the device).  arrays_out: guarded arrays alive.
+extern "C" int nsol_debug_guard_check(nsol_ctx *ctx, int64_t *violations_out, int *arrays_out) {
+    if (!ctx || !violations_out) return NSOL_EINVAL;
+    NSOL_CHECK(nsol_bind_device(ctx));
+    unsigned long long *bad = nullptr;
+    NSOL_CUDA(ctx, cudaMalloc((void **)&bad, sizeof(unsigned long long)));
+    NSOL_CUDA(ctx, cudaMemset(bad, 0, sizeof(unsigned long long)));
+    NSOL_CUDA(ctx, cudaDeviceSynchronize());
+    for (auto &kv : ctx->guarded) {
+        const unsigned char *base = (const unsigned char *)kv.second.first;
+        const size_t bytes = kv.second.second, user = (bytes + 255) / 256 * 256;
+        // below: the whole band; above: from the end of the user bytes (the padding up to the 256-byte boundary counts too)
+        guard_check_kernel<<<64, 256>>>(base, NSOL_GUARD_BYTES, base + NSOL_GUARD_BYTES + bytes, (user - bytes) + NSOL_GUARD_BYTES, bad);
+    }
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpy(&h, bad, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(bad);
+    if (e != cudaSuccess) return nsol_fail(ctx, NSOL_ECUDA, "guard check: %s", cudaGetErrorString(e));
+    *violations_out = (int64_t)h;
+    if (arrays_out) *arrays_out = (int)ctx->guarded.size();
     return NSOL_OK;
 }
 

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
 #include <string>
 
 #include "nsol_b200.h"
@@ -27,8 +28,18 @@ struct nsol_ctx {
                             // 3 whenever possible with the first-generation kernels (lsmr_fastv.cuh; kept for comparison)
     int lsmr_fuse3d = 0;    // fused 3-D forward / adjoint LSMR kernels (csrc/lsmr_fused3d.cuh): same values
     int link_timeout_ms = 0; // in-kernel halo exchange: give up waiting for a neighbour after this long (0 = 5000)
+    // "debug_guard" = 1: the arrays of every plan created afterwards sit between two NaN-filled guard bands; an out-of-bounds
+    // read drags NaN into the result, an out-of-bounds write is found by nsol_debug_guard_check (the pool's compute-sanitizer
+    // is closed -- this is the bounds check the parity tests run instead)
+    int debug_guard = 0;
+    std::map<void *, std::pair<void *, size_t>> guarded;   // user pointer -> (base pointer, user bytes)
     std::string err;
 };
+
+#define NSOL_GUARD_BYTES ((size_t)1 << 16)
+// cudaMalloc / cudaFree of a plan array, guarded when ctx->debug_guard is set (capi.cu)
+cudaError_t nsol_plan_alloc(nsol_ctx *ctx, void **ptr, size_t bytes);
+void nsol_plan_free(nsol_ctx *ctx, void *ptr);
 
 extern thread_local std::string g_nsol_create_error;
 

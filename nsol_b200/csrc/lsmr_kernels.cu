@@ -563,7 +563,7 @@ extern "C" void nsol_lsmr_plan_destroy(nsol_lsmr_plan *pl) {
     void *ptrs[] = {pl->u, pl->v, pl->h, pl->hbar, pl->x, pl->opbuf, pl->optmp, pl->breg, pl->admm_v, pl->admm_w, pl->admm_c,
                     pl->bbuf, pl->xbuf, pl->stage, pl->part, pl->S, pl->taps_dev, pl->coop_part, pl->coopv_part,
                     pl->halo_v_lo, pl->halo_v_hi, pl->halo_u_lo, pl->halo_u_hi, pl->halo_uz_lo, pl->halo_x_hi, pl->ssbuf};
-    for (void *p : ptrs) cudaFree(p);
+    for (void *p : ptrs) nsol_plan_free(pl->ctx, p);
     if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
     delete pl;
 }
@@ -601,7 +601,7 @@ extern "C" int nsol_lsmr_plan_create(nsol_ctx *ctx, const nsol_lsq_desc *desc, n
     pl->row_blocks = ((gv.nx + FAST_TH - 1) / FAST_TH) * gv.ny * gv.nz;
     const size_t nb = (size_t)gv.n * pl->esz;
     auto alloc = [&](void **ptr, size_t bytes) -> bool {
-        cudaError_t e = cudaMalloc(ptr, bytes ? bytes : 8);
+        cudaError_t e = nsol_plan_alloc(ctx, ptr, bytes ? bytes : 8);
         if (e != cudaSuccess) {
             nsol_fail(ctx, NSOL_ENOMEM, "lsmr plan: cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e));
             return false;
@@ -1282,7 +1282,7 @@ extern "C" int nsol_lsmr_plan_slab(nsol_lsmr_plan *pl, int has_below, int has_ab
         void **bufs[] = {&pl->halo_v_lo, &pl->halo_v_hi, &pl->halo_u_lo, &pl->halo_u_hi, &pl->halo_uz_lo, &pl->halo_x_hi};
         const size_t sizes[] = {plane * ghost, plane * ghost, plane * ghost, plane * ghost, plane, plane};
         for (int i = 0; i < 6; ++i) {
-            NSOL_CUDA(ctx, cudaMalloc(bufs[i], sizes[i]));
+            NSOL_CUDA(ctx, nsol_plan_alloc(ctx, bufs[i], sizes[i]));
             NSOL_CUDA(ctx, cudaMemset(*bufs[i], 0, sizes[i]));
             pl->bytes += sizes[i];
         }

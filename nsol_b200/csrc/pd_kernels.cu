@@ -611,11 +611,11 @@ static int pd_ensure_schedule(nsol_pd_plan *pl, int upto) {
 extern "C" void nsol_pd_plan_destroy(nsol_pd_plan *pl) {
     if (!pl) return;
     if (pl->ctx) nsol_bind_device(pl->ctx);
-    cudaFree(pl->x);
-    cudaFree(pl->b);
+    nsol_plan_free(pl->ctx, pl->x);
+    nsol_plan_free(pl->ctx, pl->b);
     for (int i = 0; i < 2; ++i) {
-        cudaFree(pl->xbar[i]);
-        for (int k = 0; k < 3; ++k) cudaFree(pl->p[i][k]);
+        nsol_plan_free(pl->ctx, pl->xbar[i]);
+        for (int k = 0; k < 3; ++k) nsol_plan_free(pl->ctx, pl->p[i][k]);
     }
     cudaFree(pl->stage);
     cudaFree(pl->sched);
@@ -646,7 +646,7 @@ extern "C" int nsol_pd_plan_create(nsol_ctx *ctx, const nsol_pd_desc *desc, nsol
     const size_t vol_bytes = (size_t)gv.n * gv.batch * pl->esz;
     const size_t b_bytes = (size_t)gv.n * (desc->b_batched ? gv.batch : 1) * pl->esz;
     auto alloc = [&](void **ptr, size_t bytes) -> bool {
-        cudaError_t e = cudaMalloc(ptr, bytes);
+        cudaError_t e = nsol_plan_alloc(ctx, ptr, bytes);
         if (e != cudaSuccess) {
             nsol_fail(ctx, NSOL_ENOMEM, "pd plan: cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e));
             return false;

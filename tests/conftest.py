@@ -45,3 +45,20 @@ def rel_max(a, b):
     a = np.asarray(a, dtype=np.float64).reshape(-1)
     b = np.asarray(b, dtype=np.float64).reshape(-1)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+# ---- bounds checking of the CUDA kernels (stands in for compute-sanitizer memcheck, which is closed on the GPU pool) ----------
+# NSOL_DEBUG_GUARD=1 python -m pytest tests -m gpu : every plan array of every GPU test sits between two NaN-filled 64 KiB guard
+# bands (nsol_set_tuning "debug_guard").  An out-of-bounds READ drags NaN into a result the parity assertions look at; an
+# out-of-bounds WRITE is counted by nsol_debug_guard_check after each test.
+@pytest.fixture(autouse=True)
+def _guard_bands(request):
+    if os.environ.get("NSOL_DEBUG_GUARD", "0") != "1" or request.node.get_closest_marker("gpu") is None:
+        yield
+        return
+    from nsol_b200 import _lib
+    ctx = _lib.context()
+    ctx.set_tuning("debug_guard", 1)
+    yield
+    bad, _ = ctx.guard_check()
+    assert bad == 0, "%s: %d guard bytes overwritten (out-of-bounds write)" % (request.node.name, bad)

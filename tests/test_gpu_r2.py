@@ -419,3 +419,43 @@ def test_admm_zslab_emulation_with_fused_3d_kernels(shape, nslabs, dtype):
         ctx.set_tuning("lsmr_path", 0)
     tol = 1e-9 if dtype == "float64" else 1e-4
     assert rel_max(out, ref) < tol, rel_max(out, ref)
+
+
+# ------------------------------------------------------------------ guard bands (bounds checking without compute-sanitizer)
+def test_debug_guard_finds_out_of_bounds_write_and_read():
+    """The guard-band mode of the library (tuning knob "debug_guard") must see a write one word before / after a plan array, and a
+    read beyond an array must bring NaN into the result."""
+    import ctypes as C
+
+    from nsol_b200 import _lib
+    ctx = _lib.context()
+    ctx.set_tuning("debug_guard", 1)
+    try:
+        bad0, n0 = ctx.guard_check()
+        rng = np.random.RandomState(3)
+        b = rng.rand(24, 20, 28)
+        solver = make_pd(b, reg="TV", data="L2", alpha=0.05, L2=8, iterations=3)
+        solver.run()
+        x = solver.get_x()
+        assert np.all(np.isfinite(x))
+        bad1, n1 = ctx.guard_check()
+        assert bad1 == bad0 and n1 >= n0 + 9            # x, b, 2 x xbar, 2 x 3 p: all guarded, none overrun
+        plan = solver._plan
+        xd = C.c_void_p()
+        ctx.check(ctx.lib.nsol_pd_plan_x_dev(plan, C.byref(xd)))
+        # a write of one word just below and just above the array
+        ctx.check(ctx.lib.nsol_memset_dev(ctx.handle, C.c_void_p(xd.value - 8), 0, 8, None))
+        ctx.check(ctx.lib.nsol_memset_dev(ctx.handle, C.c_void_p(xd.value + b.size * 8), 0, 8, None))
+        bad2, _ = ctx.guard_check()
+        assert bad2 - bad1 == 16
+        # a read of the word after the array sees NaN
+        word = np.zeros(1)
+        ctx.check(ctx.lib.nsol_memcpy_d2h(ctx.handle, word.ctypes.data_as(C.c_void_p), C.c_void_p(xd.value + b.size * 8 + 8), 8, None))
+        ctx.check(ctx.lib.nsol_stream_sync(ctx.handle, None))
+        assert np.isnan(word[0])
+        # repair the bands so that later checks start clean
+        ctx.check(ctx.lib.nsol_memset_dev(ctx.handle, C.c_void_p(xd.value - 8), 0xFF, 8, None))
+        ctx.check(ctx.lib.nsol_memset_dev(ctx.handle, C.c_void_p(xd.value + b.size * 8), 0xFF, 8, None))
+        assert ctx.guard_check()[0] == bad1
+    finally:
+        ctx.set_tuning("debug_guard", 0)
