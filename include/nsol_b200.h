@@ -83,7 +83,7 @@ int nsol_create(int device, nsol_ctx **out);
 void nsol_destroy(nsol_ctx *ctx);
 /* ctx may be NULL: returns the calling thread's last creation error. */
 const char *nsol_last_error(const nsol_ctx *ctx);
-/* tuning knobs ("pd_zc", "pd_ty", "pd_variant", "pd_persist", "lsmr_blocks", "lsmr_path", "lsmr_fuse2d", "lsmr_fuse3d", "link_timeout_ms", "debug_guard"); value <= 0 restores the default */
+/* tuning knobs ("pd_zc", "pd_ty", "pd_variant", "pd_persist", "pd_pipe", "pd_pipe_depth", "pd_pipe_planes", "lsmr_blocks", "lsmr_path", "lsmr_fuse2d", "lsmr_fuse3d", "link_timeout_ms", "debug_guard"); value <= 0 restores the default */
 int nsol_set_tuning(nsol_ctx *ctx, const char *key, int value);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t nsol_launch_count(const nsol_ctx *ctx);
@@ -204,6 +204,15 @@ int nsol_pd_plan_x_dev(nsol_pd_plan *plan, const void **x_dev);
 int nsol_pd_plan_get_x_host(nsol_pd_plan *plan, double *x_host, nsol_stream s);
 /* device-resident variant of the same: x * x_scale into a device array of dtype_out */
 int nsol_pd_plan_get_x_dev(nsol_pd_plan *plan, int dtype_out, void *out_dev, nsol_stream s);
+/* One whole solve of an existing plan from / to host float64 buffers: reset with (b_host, x0_host; x0_host NULL = b_host),
+ * `iterations` iterations, x_host = x * x_scale.  Replaces PrimalDualSolver.run() + get_x() without an Observer
+ * (nsol/primal_dual_solver.py:215-263, nsol/solver.py:117-118).  For a large single volume with page-locked host buffers the
+ * upload / download are cut into groups of z-planes that overlap a wavefront of iterations (tuning knobs "pd_pipe",
+ * "pd_pipe_depth", "pd_pipe_planes"); otherwise it is reset_host + iterate + get_x_host.  Same kernels, same bits.  Synchronous. */
+int nsol_pd_plan_solve_host(nsol_pd_plan *plan, const double *b_host, const double *x0_host, int iterations, double *x_host,
+                            nsol_stream s);
+/* transfer groups / wavefront depth used by the last nsol_pd_plan_solve_host (0 groups: the plain sequence) */
+int nsol_pd_plan_solve_info(const nsol_pd_plan *plan, int *groups_out, int *depth_out);
 /* one call = PrimalDualSolver.run() + get_x() with host float64 buffers
  * (H2D, iterations, D2H).  iterates_host, if not NULL, receives the
  * (iterations+1) arrays the Observer would see (:218-219, :260-261). */

@@ -21,6 +21,10 @@ struct nsol_ctx {
     int pd_variant = 0;
     int pd_persist_blocks = 0;   // persistent primal-dual kernel: cap on the number of CTAs (0: one per SM)
     int pd_persist = 0;     // persistent cooperative primal-dual kernel for small 2-D / 1-D problems: 0 auto, 1 whenever possible, 2 never
+    // pipelined host solve (nsol_pd_plan_solve_host): the z-ordered upload / download of a large volume overlaps a wavefront of
+    // iterations.  pd_pipe: 0 auto (volumes >= 64 MiB, pinned host buffers), 1 whenever possible, 2 never; pd_pipe_depth: iterations
+    // the first group runs ahead of the last one (0 = 10); pd_pipe_planes: z-planes per transfer group (0 = 16)
+    int pd_pipe = 0, pd_pipe_depth = 0, pd_pipe_planes = 0;
     int lsmr_blocks = 0;
     int lsmr_path = 0;      // 0 auto, 1 multi-kernel (vector kernels where they apply), 2 cooperative single launch (generic phases),
                             // 3 multi-kernel with the generic kernels, 4 persistent cooperative solve built from the vector phases

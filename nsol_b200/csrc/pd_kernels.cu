@@ -21,6 +21,7 @@
 //
 // Arithmetic keeps the reference's operation order and is compiled without FMA
 // contraction (-fmad=false), so the float64 path is bit-identical to numpy.
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -525,6 +526,11 @@ struct nsol_pd_plan {
     bool link_on = false;
     bool link_fresh = false;          // the neighbours hold the halos of the current state
     unsigned link_pub = 0;            // generations published so far (= index of the next one)
+    // pipelined host solve (nsol_pd_plan_solve_host): copy streams and one event per transfer group
+    cudaStream_t pipe_up = nullptr, pipe_dn = nullptr;
+    cudaEvent_t pipe_fork = nullptr;
+    std::vector<cudaEvent_t> pipe_ev_up, pipe_ev_x, pipe_ev_dn;
+    int pipe_groups_last = 0, pipe_depth_last = 0;   // what the last solve did (0 groups: plain sequence)
 };
 
 // layout of a link block (all offsets 256-byte aligned)
@@ -619,6 +625,11 @@ extern "C" void nsol_pd_plan_destroy(nsol_pd_plan *pl) {
     }
     cudaFree(pl->stage);
     cudaFree(pl->sched);
+    for (auto *v : {&pl->pipe_ev_up, &pl->pipe_ev_x, &pl->pipe_ev_dn})
+        for (cudaEvent_t e : *v) cudaEventDestroy(e);
+    if (pl->pipe_fork) cudaEventDestroy(pl->pipe_fork);
+    if (pl->pipe_up) cudaStreamDestroy(pl->pipe_up);
+    if (pl->pipe_dn) cudaStreamDestroy(pl->pipe_dn);
     if (pl->peer_below && pl->peer_below_ipc) cudaIpcCloseMemHandle(pl->peer_below);
     if (pl->peer_above && pl->peer_above_ipc) cudaIpcCloseMemHandle(pl->peer_above);
     cudaFree(pl->link_block);
@@ -1108,11 +1119,18 @@ static void pd_tiling(const nsol_ctx *ctx, const GridView &gv, int vecw, int *ty
 
 // part: 0 = whole iteration; 1 = only the first and last z-chunk (the planes a z-slab neighbour
 // needs), no state advance; 2 = the remaining interior chunks, then advance.
+// rg (pipelined solve, nsol_pd_plan_solve_host): iteration rg->it (0-based) on the z-chunks [rg->c0, rg->c1) only, reading the
+// buffers of parity it & 1; the plan's own counters do not move.
+struct PdRange {
+    int c0, c1, it;
+};
+
 template <typename T, int VECW>
-static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, int persist_n = 0) {
+static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, int persist_n = 0, const PdRange *rg = nullptr) {
     nsol_ctx *ctx = pl->ctx;
     const GridView &gv = pl->gv;
-    const int cur = pl->cur, nxt = cur ^ 1;
+    if (rg && (pl->link_on || part != 0 || persist_n > 1)) return nsol_fail(ctx, NSOL_ESTATE, "pd: chunk-range launch in link / split / persistent mode");
+    const int cur = rg ? (rg->it & 1) : pl->cur, nxt = cur ^ 1;
     PdArgs<T> a;
     a.xbar_in = (const T *)pl->xbar[cur];
     a.xbar_out = (T *)pl->xbar[nxt];
@@ -1170,7 +1188,7 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, i
     a.wx = (T)gv.w[gv.comp_x];
     a.wy = gv.comp_y >= 0 ? (T)gv.w[gv.comp_y] : T(0);
     a.wz = gv.comp_z >= 0 ? (T)gv.w[gv.comp_z] : T(0);
-    a.it = pl->it;
+    a.it = rg ? rg->it : pl->it;
     a.batch = gv.batch;
 
     const bool has_y = gv.comp_y >= 0;
@@ -1202,6 +1220,11 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, i
             a.chunk_first = 1;
         }
     }
+    if (rg) {
+        if (rg->c0 < 0 || rg->c1 > a.nchunks || rg->c0 >= rg->c1) return nsol_fail(ctx, NSOL_EINVAL, "pd: bad chunk range [%d, %d) of %d", rg->c0, rg->c1, a.nchunks);
+        a.chunk_first = rg->c0;
+        a.nsel = rg->c1 - rg->c0;
+    }
     a.front_chunks = (pl->link_on && a.nchunks >= 3) ? 1 : 0;
     const long long gz = (long long)a.nsel * gv.batch;
     if (gz > 65535) return nsol_fail(ctx, NSOL_EINVAL, "pd: nchunks*batch = %lld exceeds the grid limit; raise pd_zc", gz);
@@ -1231,7 +1254,7 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, i
         pd_launch_rd<T, VECW, false>(pl, a, grid, block, smem, s);
     }
     NSOL_LAUNCH_CHECK(ctx);
-    if (part != 1) {
+    if (part != 1 && !rg) {
         pl->cur = nxt;
         pl->it += 1;
         if (pl->link_on) pl->link_pub += 1;
@@ -1323,6 +1346,186 @@ extern "C" int nsol_pd_plan_get_x_host(nsol_pd_plan *pl, double *x_host, nsol_st
     NSOL_CUDA(ctx, cudaMemcpyAsync(x_host, pl->stage, nv * sizeof(double), cudaMemcpyDeviceToHost, st));
     NSOL_CUDA(ctx, cudaStreamSynchronize(st));
     if (pl->link_on) NSOL_CHECK(nsol_pd_plan_link_status(pl, s));
+    return NSOL_OK;
+}
+
+// ---- pipelined host solve --------------------------------------------------------------------------------------------
+// reset of the planes of one transfer group from the float64 staging copy of the observation (and of x0 when it is a different
+// array): b' = b / b_scale, x = xbar = x0 / x0_scale, p = 0 -- the same IEEE operations as pd_reset_common, one pass.
+template <typename T>
+__global__ void pd_reset_range_kernel(long long n, const double *sb, const double *sx, double b_scale, double x0_scale,
+                                      T *b, T *x, T *xbar, T *p0, T *p1, T *p2) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const double vb = sb[i], vx = sx[i];
+        b[i] = (T)(vb / b_scale);
+        const T v = (T)(vx / x0_scale);
+        x[i] = v;
+        xbar[i] = v;
+        p0[i] = T(0);
+        if (p1) p1[i] = T(0);
+        if (p2) p2[i] = T(0);
+    }
+}
+
+static bool pd_host_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+template <typename T>
+static int pd_launch_range(nsol_pd_plan *pl, cudaStream_t st, int c0, int c1, int it) {
+    const PdRange rg = {c0, c1, it};
+    const int vecw = sizeof(T) == 4 ? 4 : 2;
+    if ((pl->gv.nx % vecw) == 0) {
+        if (sizeof(T) == 4) return pd_launch_iteration<float, 4>(pl, st, 0, 0, &rg);
+        return pd_launch_iteration<double, 2>(pl, st, 0, 0, &rg);
+    }
+    if (sizeof(T) == 4) return pd_launch_iteration<float, 1>(pl, st, 0, 0, &rg);
+    return pd_launch_iteration<double, 1>(pl, st, 0, 0, &rg);
+}
+
+// One whole solve from / to host memory: x_host = x_scale * PD_iterations(b_host, x0_host).  For a large single volume with
+// page-locked host buffers the transfers are cut into groups of z-planes and overlap the iterations (DESIGN.md 3.1 "pipelined
+// solve"): group j is uploaded on a copy stream while the groups below it advance on a wavefront -- iteration i of group c
+// needs iteration i - 1 of groups c - 1, c, c + 1 only, so when group j lands, groups j-1, j-2, ..., j-D run iterations
+// 0, 1, ..., D-1; after the last upload the volume is brought to D iterations everywhere, iterations D ... n-D'-1 are whole-volume
+// launches, and the mirror image at the end lets group 0 finish first and go back to the host while the groups above it catch up.
+// The kernels, the chunk geometry and therefore every bit of the result are those of nsol_pd_plan_iterate.
+template <typename T>
+static int pd_solve_pipelined(nsol_pd_plan *pl, const double *b_host, const double *x0_host, int iterations, double *x_host,
+                              cudaStream_t st, int planes, int depth) {
+    nsol_ctx *ctx = pl->ctx;
+    const GridView &gv = pl->gv;
+    const int vecw = sizeof(T) == 4 ? 4 : 2;
+    int ty, zc;
+    pd_tiling(ctx, gv, (gv.nx % vecw) == 0 ? vecw : 1, &ty, &zc, false);
+    const int nchunks = (gv.nz + zc - 1) / zc;
+    const int gch = planes / zc > 0 ? planes / zc : 1;              // z-chunks per transfer group
+    const int ng = (nchunks + gch - 1) / gch;
+    const long long plane = (long long)gv.nx * gv.ny;
+    const bool same = (x0_host == nullptr) || (x0_host == b_host);
+    const size_t nv = (size_t)gv.n;
+    NSOL_CHECK(pd_ensure_stage(pl, (same ? 1 : 2) * nv * sizeof(double)));
+    NSOL_CHECK(pd_ensure_schedule(pl, iterations));
+    if (!pl->pipe_up) {
+        NSOL_CUDA(ctx, cudaStreamCreateWithFlags(&pl->pipe_up, cudaStreamNonBlocking));
+        NSOL_CUDA(ctx, cudaStreamCreateWithFlags(&pl->pipe_dn, cudaStreamNonBlocking));
+        NSOL_CUDA(ctx, cudaEventCreateWithFlags(&pl->pipe_fork, cudaEventDisableTiming));
+    }
+    for (auto *v : {&pl->pipe_ev_up, &pl->pipe_ev_x, &pl->pipe_ev_dn})
+        while ((int)v->size() < ng) {
+            cudaEvent_t e;
+            NSOL_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            v->push_back(e);
+        }
+    double *sb = (double *)pl->stage, *sx = same ? sb : sb + nv;
+    auto g_lo = [&](int g) { return (long long)std::min(g * gch * zc, gv.nz) * plane; };     // first voxel of group g
+    const int d_up = std::min(depth, iterations / 2), d_dn = std::min(depth, iterations - d_up);
+    std::vector<int> done(ng, -1);                                   // -1: not yet on the device
+    auto advance = [&](int c) -> int {
+        // the wavefront rule: both neighbours hold the state this iteration reads
+        if (done[c] < 0 || (c > 0 && done[c - 1] < done[c]) || (c + 1 < ng && done[c + 1] < done[c]))
+            return nsol_fail(ctx, NSOL_ESTATE, "pd pipelined solve: wavefront order violated at group %d", c);
+        NSOL_CHECK(pd_launch_range<T>(pl, st, c * gch, std::min((c + 1) * gch, nchunks), done[c]));
+        done[c] += 1;
+        return NSOL_OK;
+    };
+    // ---- uploads, all queued on the copy stream behind whatever the caller's stream holds
+    NSOL_CUDA(ctx, cudaEventRecord(pl->pipe_fork, st));
+    NSOL_CUDA(ctx, cudaStreamWaitEvent(pl->pipe_up, pl->pipe_fork, 0));
+    for (int g = 0; g < ng; ++g) {
+        const long long lo = g_lo(g), cnt = g_lo(g + 1) - lo;
+        NSOL_CUDA(ctx, cudaMemcpyAsync(sb + lo, b_host + lo, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, pl->pipe_up));
+        if (!same) NSOL_CUDA(ctx, cudaMemcpyAsync(sx + lo, x0_host + lo, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, pl->pipe_up));
+        NSOL_CUDA(ctx, cudaEventRecord(pl->pipe_ev_up[g], pl->pipe_up));
+    }
+    // ---- arrival phase: group j lands -> reset it, groups j-1 ... j-D advance one iteration each (newest first)
+    for (int j = 0; j < ng + d_up; ++j) {
+        if (j < ng) {
+            const long long lo = g_lo(j), cnt = g_lo(j + 1) - lo;
+            NSOL_CUDA(ctx, cudaStreamWaitEvent(st, pl->pipe_ev_up[j], 0));
+            const int threads = 256;
+            const long long want = (cnt + threads - 1) / threads;
+            const int blocks = (int)std::min<long long>(std::max<long long>(want, 1), (long long)ctx->sm_count * 16);
+            T *p1 = gv.dim > 1 ? (T *)pl->p[0][1] + lo : nullptr, *p2 = gv.dim > 2 ? (T *)pl->p[0][2] + lo : nullptr;
+            pd_reset_range_kernel<T><<<blocks, threads, 0, st>>>(cnt, sb + lo, sx + lo, pl->desc.b_scale, pl->desc.x0_scale, (T *)pl->b + lo,
+                                                                (T *)pl->x + lo, (T *)pl->xbar[0] + lo, (T *)pl->p[0][0] + lo, p1, p2);
+            NSOL_LAUNCH_CHECK(ctx);
+            done[j] = 0;
+        }
+        for (int c = std::min(j - 1, ng - 1); c >= std::max(0, j - d_up); --c) NSOL_CHECK(advance(c));
+    }
+    // ---- whole-volume iterations d_up ... iterations - d_dn - 1
+    pl->cur = d_up & 1;
+    pl->it = d_up;
+    pl->ready = true;
+    pl->link_fresh = false;
+    for (int i = d_up; i < iterations - d_dn; ++i) {
+        if (sizeof(T) == 4) NSOL_CHECK(((gv.nx % 4) == 0 ? pd_launch_iteration<float, 4>(pl, st) : pd_launch_iteration<float, 1>(pl, st)));
+        else NSOL_CHECK(((gv.nx % 2) == 0 ? pd_launch_iteration<double, 2>(pl, st) : pd_launch_iteration<double, 1>(pl, st)));
+    }
+    for (int c = 0; c < ng; ++c) done[c] = iterations - d_dn;
+    // ---- ramp: round t advances the groups [0, d_dn - t] (one launch, they are at the same iteration) -> group c is c iterations
+    // short of the end
+    for (int t = 1; t <= d_dn; ++t) {
+        const int top = std::min(d_dn - t, ng - 1);
+        NSOL_CHECK(pd_launch_range<T>(pl, st, 0, std::min((top + 1) * gch, nchunks), iterations - d_dn + t - 1));
+        for (int c = 0; c <= top; ++c) done[c] += 1;
+    }
+    // ---- departure phase: step j finishes group j (farthest group first), converts it and sends it home on the copy stream
+    for (int j = 0; j < ng; ++j) {
+        for (int c = std::min(j + d_dn - 1, ng - 1); c >= j; --c)
+            if (done[c] < iterations && (c + 1 >= ng || done[c + 1] >= done[c])) NSOL_CHECK(advance(c));
+        if (done[j] != iterations) return nsol_fail(ctx, NSOL_ESTATE, "pd pipelined solve: group %d stopped at iteration %d", j, done[j]);
+        const long long lo = g_lo(j), cnt = g_lo(j + 1) - lo;
+        NSOL_CHECK(nsol_scale_convert(ctx, cnt, gv.dtype, (const T *)pl->x + lo, NSOL_F64, sb + lo, pl->desc.x_scale, 0, (nsol_stream)st));
+        NSOL_CUDA(ctx, cudaEventRecord(pl->pipe_ev_x[j], st));
+        NSOL_CUDA(ctx, cudaStreamWaitEvent(pl->pipe_dn, pl->pipe_ev_x[j], 0));
+        NSOL_CUDA(ctx, cudaMemcpyAsync(x_host + lo, sb + lo, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, pl->pipe_dn));
+    }
+    NSOL_CUDA(ctx, cudaEventRecord(pl->pipe_ev_dn[0], pl->pipe_dn));
+    NSOL_CUDA(ctx, cudaStreamWaitEvent(st, pl->pipe_ev_dn[0], 0));
+    pl->cur = iterations & 1;
+    pl->it = iterations;
+    pl->pipe_groups_last = ng;
+    pl->pipe_depth_last = d_up;
+    NSOL_CUDA(ctx, cudaStreamSynchronize(st));
+    return NSOL_OK;
+}
+
+extern "C" int nsol_pd_plan_solve_host(nsol_pd_plan *pl, const double *b_host, const double *x0_host, int iterations,
+                                       double *x_host, nsol_stream s) {
+    if (!pl) return NSOL_EINVAL;
+    nsol_ctx *ctx = pl->ctx;
+    if (!b_host || !x_host) return nsol_fail(ctx, NSOL_EINVAL, "pd solve: b or x is NULL");
+    if (iterations < 0) return nsol_fail(ctx, NSOL_EINVAL, "pd solve: iterations must be >= 0");
+    NSOL_CHECK(nsol_bind_device(ctx));
+    const GridView &gv = pl->gv;
+    pl->pipe_groups_last = 0;
+    const bool possible = gv.comp_z >= 0 && gv.batch == 1 && !pl->link_on && !pl->halo_above && !pl->halo_below && ctx->pd_pipe != 2;
+    if (possible && (ctx->pd_pipe == 1 || ((size_t)gv.n * sizeof(double) >= ((size_t)64 << 20) && pd_host_pinned(b_host) &&
+                                           pd_host_pinned(x_host) && (!x0_host || x0_host == b_host || pd_host_pinned(x0_host))))) {
+        const int planes = ctx->pd_pipe_planes > 0 ? ctx->pd_pipe_planes : 16;
+        const int depth = ctx->pd_pipe_depth > 0 ? ctx->pd_pipe_depth : 10;
+        if (gv.dtype == NSOL_F32) return pd_solve_pipelined<float>(pl, b_host, x0_host, iterations, x_host, (cudaStream_t)s, planes, depth);
+        return pd_solve_pipelined<double>(pl, b_host, x0_host, iterations, x_host, (cudaStream_t)s, planes, depth);
+    }
+    NSOL_CHECK(nsol_pd_plan_reset_host(pl, b_host, x0_host, s));
+    NSOL_CHECK(nsol_pd_plan_iterate(pl, iterations, s));
+    return nsol_pd_plan_get_x_host(pl, x_host, s);
+}
+
+// transfer groups and wavefront depth of the last nsol_pd_plan_solve_host (0 groups: the plain upload / iterate / download sequence)
+extern "C" int nsol_pd_plan_solve_info(const nsol_pd_plan *pl, int *groups_out, int *depth_out) {
+    if (!pl) return NSOL_EINVAL;
+    if (groups_out) *groups_out = pl->pipe_groups_last;
+    if (depth_out) *depth_out = pl->pipe_depth_last;
     return NSOL_OK;
 }
 

@@ -252,6 +252,26 @@ class PrimalDualSolver(Solver):
             raise ValueError("iterations must be >= 0")
         plan = self._acquire_plan(ctx, cfg, desc)
         slab = getattr(self, "_slab", None)
+
+        def fetch():
+            out = ctx.result_empty(n, np.float64)
+            ctx.check(lib.nsol_pd_plan_get_x_host(plan, out.ctypes.data, None))
+            return out
+
+        if slab is None and self._observer is None:
+            # No Observer: the whole solve is ONE library call that also brings the result back -- for a large volume the upload,
+            # the iterations and the download overlap (nsol_pd_plan_solve_host).  The first get_x() hands that array out, later
+            # calls download a fresh copy like the reference returns a fresh array (nsol/solver.py:117-118).
+            first = [ctx.result_empty(n, np.float64)]
+            ctx.check(lib.nsol_pd_plan_solve_host(plan, b.ctypes.data, x0.ctypes.data if x0 is not None else None, iters,
+                                                  first[0].ctypes.data, None))
+
+            def fetch_first():
+                if first:
+                    return first.pop()
+                return fetch()
+            self._set_device_result(fetch_first)
+            return
         ctx.check(lib.nsol_pd_plan_reset_host(plan, b.ctypes.data, x0.ctypes.data if x0 is not None else None, None))
         if slab is not None:
             slab._halo_fresh = False
@@ -261,11 +281,6 @@ class PrimalDualSolver(Solver):
                 slab.iterate(k, None)
             else:
                 ctx.check(lib.nsol_pd_plan_iterate(plan, k, None))
-
-        def fetch():
-            out = ctx.result_empty(n, np.float64)
-            ctx.check(lib.nsol_pd_plan_get_x_host(plan, out.ctypes.data, None))
-            return out
 
         reqs = None
         if self._observer is not None and not getattr(self._observer, "get_store_iterates", lambda: True)():

@@ -459,3 +459,95 @@ def test_debug_guard_finds_out_of_bounds_write_and_read():
         assert ctx.guard_check()[0] == bad1
     finally:
         ctx.set_tuning("debug_guard", 0)
+
+
+# ------------------------------------------------------------------ pipelined host solve (upload / wavefront / download overlap)
+def _solve_info(solver):
+    import ctypes as C
+
+    from nsol_b200 import _lib
+    ctx = _lib.context()
+    g, d = C.c_int(), C.c_int()
+    ctx.check(ctx.lib.nsol_pd_plan_solve_info(solver._plan, C.byref(g), C.byref(d)))
+    return g.value, d.value
+
+
+@pytest.mark.parametrize("shape,iterations,planes,depth,dtype", [
+    ((40, 24, 32), 30, 4, 10, None),        # 10 groups, full depth
+    ((37, 20, 30), 25, 8, 4, None),         # ragged last group (37 planes), shallow wavefront
+    ((16, 24, 32), 7, 4, 10, None),         # depth clipped by the iteration count (3 up, 4 down)
+    ((12, 16, 32), 1, 4, 10, None),         # one iteration: nothing to skew on the way in
+    ((12, 16, 32), 0, 4, 10, None),         # zero iterations: reset + download only
+    ((9, 16, 32), 40, 64, 10, None),        # a single group
+    ((40, 24, 32), 30, 4, 10, "float32"),
+    ((64, 48), 30, 8, 6, None),             # 2-D image, rows are the marching axis
+    ((33, 18, 26), 21, 4, 10, None),        # nx not a multiple of the vector width -> scalar kernel
+])
+def test_pipelined_host_solve_is_bit_identical_to_plain_solve(shape, iterations, planes, depth, dtype):
+    """nsol_pd_plan_solve_host with transfer groups + wavefront (forced by "pd_pipe" = 1 on small volumes) must return exactly
+    what the plain upload / iterate / download sequence returns (and, in float64, what the reference computes)."""
+    from nsol_b200 import _lib
+    ctx = _lib.context()
+    rng = np.random.RandomState(sum(shape) + iterations)
+    obs = rng.rand(*shape) * 150 + 1
+    reg, data = ("HUBER", "L1") if len(shape) == 2 else ("TV", "L2")
+    kw = dict(reg=reg, data=data, alpha=0.08, L2=8, iterations=iterations, dtype=dtype)
+    try:
+        ctx.set_tuning("pd_pipe", 2)
+        plain = make_pd(obs, **kw)
+        plain.run()
+        assert _solve_info(plain) == (0, 0)
+        x_plain = plain.get_x()
+        ctx.set_tuning("pd_pipe", 1)
+        ctx.set_tuning("pd_pipe_planes", planes)
+        ctx.set_tuning("pd_pipe_depth", depth)
+        piped = make_pd(obs, **kw)
+        piped.run()
+        groups, d_up = _solve_info(piped)
+        assert groups >= 1 and d_up == min(depth, iterations // 2)
+        x1 = piped.get_x()
+        x2 = piped.get_x()              # second call: a fresh download of the resident state
+        assert np.array_equal(x1, x_plain) and np.array_equal(x2, x_plain) and x1 is not x2
+        piped.run()                     # the plan is reused: a second solve gives the same bits
+        assert np.array_equal(piped.get_x(), x_plain)
+    finally:
+        for k in ("pd_pipe", "pd_pipe_planes", "pd_pipe_depth"):
+            ctx.set_tuning(k, 0)
+    if dtype is None:
+        ref = orc.primal_dual_denoise(obs.reshape(-1), obs.shape, reg=reg, data=data, alpha=0.08, L2=8, iterations=iterations,
+                                      x_scale=float(obs.max()))
+        assert np.array_equal(x_plain, ref)
+
+
+def test_pipelined_host_solve_with_the_reference_wiring_and_pinned_buffers():
+    """b = x0 = one page-locked array (bench.py's e2e wiring): one upload per group, auto mode picks the pipeline from 64 MiB."""
+    import nsol_b200.linear_operators as lo
+    from nsol_b200 import _lib
+    from nsol_b200.proximal_operators import ProximalOperators as prox
+    ctx = _lib.context()
+    shape = (144, 256, 256)                 # 72 MiB in float64
+    rng = np.random.RandomState(5)
+    b = ctx.pinned_empty((int(np.prod(shape)),), np.float64)
+    b[:] = rng.rand(b.size) * 255
+    xs = float(b.max())
+    grad, grad_adj = lo.LinearOperators3D().get_gradient_operators()
+    zshape = (3 * shape[0],) + shape[1:]
+
+    def solver():
+        return pd.PrimalDualSolver(prox_f=lambda x, tau: prox.prox_ell2_denoising(x, tau, x0=b, x_scale=xs), prox_g_conj=prox.prox_tv_conj,
+                                   B=lambda x: grad(x.reshape(*shape)).flatten(), B_conj=lambda x: grad_adj(x.reshape(*zshape)).flatten(),
+                                   L2=8, x0=b, alpha=0.05, iterations=24, x_scale=xs)
+    s = solver()
+    assert s._x0_is_observation(s._probe(), np.asarray(b))
+    s.run()
+    groups, d_up = _solve_info(s)
+    assert groups == 9 and d_up == 10       # 144 planes in groups of 16, default depth
+    x = s.get_x()
+    try:
+        ctx.set_tuning("pd_pipe", 2)
+        s2 = solver()
+        s2.run()
+        assert _solve_info(s2) == (0, 0)
+        assert np.array_equal(s2.get_x(), x)
+    finally:
+        ctx.set_tuning("pd_pipe", 0)
