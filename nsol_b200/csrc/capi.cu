@@ -42,6 +42,9 @@ extern "C" int nsol_create(int device, nsol_ctx **out) {
     if (const char *v = getenv("NSOL_LSMR_FUSE3D")) ctx->lsmr_fuse3d = atoi(v);
     if (const char *v = getenv("NSOL_PD_PERSIST")) ctx->pd_persist = atoi(v);
     if (const char *v = getenv("NSOL_PD_PERSIST_BLOCKS")) ctx->pd_persist_blocks = atoi(v);
+    if (const char *v = getenv("NSOL_PD_TB")) ctx->pd_tb = atoi(v);
+    if (const char *v = getenv("NSOL_PD_TB_K")) ctx->pd_tb_k = atoi(v);
+    if (const char *v = getenv("NSOL_PD_TB_NR")) ctx->pd_tb_nr = atoi(v);
     if (const char *v = getenv("NSOL_PD_PIPE")) ctx->pd_pipe = atoi(v);
     if (const char *v = getenv("NSOL_PD_PIPE_DEPTH")) ctx->pd_pipe_depth = atoi(v);
     if (const char *v = getenv("NSOL_PD_PIPE_PLANES")) ctx->pd_pipe_planes = atoi(v);
@@ -69,6 +72,9 @@ extern "C" int nsol_set_tuning(nsol_ctx *ctx, const char *key, int value) {
     else if (!strcmp(key, "debug_guard")) ctx->debug_guard = value;
     else if (!strcmp(key, "pd_persist")) ctx->pd_persist = value;
     else if (!strcmp(key, "pd_persist_blocks")) ctx->pd_persist_blocks = value;
+    else if (!strcmp(key, "pd_tb")) ctx->pd_tb = value;
+    else if (!strcmp(key, "pd_tb_k")) ctx->pd_tb_k = value;
+    else if (!strcmp(key, "pd_tb_nr")) ctx->pd_tb_nr = value;
     else if (!strcmp(key, "pd_pipe")) ctx->pd_pipe = value;
     else if (!strcmp(key, "pd_pipe_depth")) ctx->pd_pipe_depth = value;
     else if (!strcmp(key, "pd_pipe_planes")) ctx->pd_pipe_planes = value;

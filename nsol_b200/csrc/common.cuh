@@ -25,6 +25,10 @@ struct nsol_ctx {
     // iterations.  pd_pipe: 0 auto (volumes >= 64 MiB, pinned host buffers), 1 whenever possible, 2 never; pd_pipe_depth: iterations
     // the first group runs ahead of the last one (0 = 10); pd_pipe_planes: z-planes per transfer group (0 = 16)
     int pd_pipe = 0, pd_pipe_depth = 0, pd_pipe_planes = 0;
+    // 2-D temporal blocking (csrc/pd_tb2d.cuh): pd_tb 0 auto (2-D problems, >= 2 iterations), 1 whenever possible, 2 never;
+    // pd_tb_k iterations per pass (0 = 4); pd_tb_nr rows per thread = region height 16 / 32 / 32 for 1 / 2 / 4 (0 = chosen from the
+    // problem size)
+    int pd_tb = 0, pd_tb_k = 0, pd_tb_nr = 0;
     int lsmr_blocks = 0;
     int lsmr_path = 0;      // 0 auto, 1 multi-kernel (vector kernels where they apply), 2 cooperative single launch (generic phases),
                             // 3 multi-kernel with the generic kernels, 4 persistent cooperative solve built from the vector phases
@@ -165,6 +169,8 @@ __device__ __forceinline__ void vec_store(T *p, const Vec<T, VEC> &x) {
 
 __device__ __forceinline__ double shfl_down_t(double x, int d) { return __shfl_down_sync(0xffffffffu, x, d); }
 __device__ __forceinline__ float shfl_down_t(float x, int d) { return __shfl_down_sync(0xffffffffu, x, d); }
+__device__ __forceinline__ double shfl_t(double x, int lane) { return __shfl_sync(0xffffffffu, x, lane); }
+__device__ __forceinline__ float shfl_t(float x, int lane) { return __shfl_sync(0xffffffffu, x, lane); }
 __device__ __forceinline__ double shfl_up_t(double x, int d) { return __shfl_up_sync(0xffffffffu, x, d); }
 __device__ __forceinline__ float shfl_up_t(float x, int d) { return __shfl_up_sync(0xffffffffu, x, d); }
 

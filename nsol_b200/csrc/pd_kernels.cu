@@ -488,6 +488,7 @@ __global__ void __launch_bounds__(128) pd_iter_persist_kernel(PdArgs<T> a, int i
 }
 
 #include "pd_bulk_kernel.cuh"
+#include "pd_tb2d.cuh"
 
 #ifndef NSOL_PD_DEFAULT_VARIANT_F64
 #define NSOL_PD_DEFAULT_VARIANT_F64 2
@@ -507,6 +508,7 @@ struct nsol_pd_plan {
     size_t esz = 8;
     // device state
     void *x = nullptr, *b = nullptr;
+    void *x_alt = nullptr;        // second x array of the 2-D temporal-blocking kernel (x ping-pongs between passes there)
     void *xbar[2] = {nullptr, nullptr};
     void *p[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     void *stage = nullptr;        // float64 staging for host transfers
@@ -618,6 +620,7 @@ extern "C" void nsol_pd_plan_destroy(nsol_pd_plan *pl) {
     if (!pl) return;
     if (pl->ctx) nsol_bind_device(pl->ctx);
     nsol_plan_free(pl->ctx, pl->x);
+    nsol_plan_free(pl->ctx, pl->x_alt);
     nsol_plan_free(pl->ctx, pl->b);
     for (int i = 0; i < 2; ++i) {
         nsol_plan_free(pl->ctx, pl->xbar[i]);
@@ -1262,6 +1265,69 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, i
     return NSOL_OK;
 }
 
+// n iterations of a 2-D problem with the temporal-blocking kernel: ceil(n / K) launches.  NSOL_ESTATE: not applicable here.
+template <typename T>
+static int pd_iterate_tb2d(nsol_pd_plan *pl, int n, cudaStream_t st) {
+    nsol_ctx *ctx = pl->ctx;
+    const GridView &gv = pl->gv;
+    // region: 64 columns x 32 rows (512 threads, two rows per thread); "pd_tb_nr" = 1: 64 x 16, 4: 64 x 32 with 256 threads
+    const long long pixels = (long long)gv.nx * gv.nz * gv.batch;
+    const bool small = pixels < (long long)ctx->sm_count * 4 * 56 * 24;
+    const int nr = ctx->pd_tb_nr > 0 ? ctx->pd_tb_nr : 2;
+    const int rows = pd_tb2d_rows(nr);
+    if (rows == 0) return nsol_fail(ctx, NSOL_EINVAL, "pd_tb_nr must be 1, 2 or 4");
+    // iterations per pass, measured on B200 (profiles/r2_tb2d.md): 4 where the kernel is bound by its arithmetic (the recomputed
+    // rings grow with K), 8 for a small single image, which is bound by launches and dependent L2 round trips
+    int K = ctx->pd_tb_k > 0 ? ctx->pd_tb_k : (small ? 8 : 4);
+    K = std::min(K, (rows - 2) / 2);
+    const int tw = 64 - 2 * K, th = rows - 2 * K;
+    const long long tiles_z = (gv.nz + th - 1) / th;
+    if (tiles_z > 65535 || gv.batch > 65535) return NSOL_ESTATE;
+    if (!pl->x_alt) {
+        cudaError_t e = nsol_plan_alloc(ctx, &pl->x_alt, (size_t)gv.n * gv.batch * pl->esz);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return NSOL_ESTATE;      // no room for the second x array: one pass per iteration
+        }
+        pl->bytes += (size_t)gv.n * gv.batch * pl->esz;
+    }
+    PdTbArgs<T> a;
+    a.b = (const T *)pl->b;
+    a.sched = pl->sched;
+    a.n = gv.n;
+    a.b_stride = pl->desc.b_batched ? gv.n : 0;
+    a.nx = gv.nx;
+    a.nz = gv.nz;
+    a.batch = gv.batch;
+    a.halo = K;
+    a.tw = tw;
+    a.th = th;
+    a.wx = (T)gv.w[gv.comp_x];
+    a.wz = (T)gv.w[gv.comp_z];
+    const dim3 grid((gv.nx + tw - 1) / tw, (unsigned)tiles_z, gv.batch);
+    for (int done = 0; done < n;) {
+        const int k = std::min(K, n - done);
+        const int cur = pl->cur, nxt = cur ^ 1;
+        a.xbar_in = (const T *)pl->xbar[cur];
+        a.xbar_out = (T *)pl->xbar[nxt];
+        a.px_in = (const T *)pl->p[cur][gv.comp_x];
+        a.px_out = (T *)pl->p[nxt][gv.comp_x];
+        a.pz_in = (const T *)pl->p[cur][gv.comp_z];
+        a.pz_out = (T *)pl->p[nxt][gv.comp_z];
+        a.x_in = (const T *)pl->x;
+        a.x_out = (T *)pl->x_alt;
+        a.it = pl->it;
+        a.ksub = k;
+        NSOL_CHECK(pd_tb2d_launch<T>(ctx, pl->desc.reg, pl->desc.data, nr, a, grid, st));
+        NSOL_LAUNCH_CHECK(ctx);
+        std::swap(pl->x, pl->x_alt);
+        pl->cur = nxt;
+        pl->it += k;
+        done += k;
+    }
+    return NSOL_OK;
+}
+
 extern "C" int nsol_pd_plan_iterate(nsol_pd_plan *pl, int n, nsol_stream s) {
     if (!pl) return NSOL_EINVAL;
     nsol_ctx *ctx = pl->ctx;
@@ -1274,6 +1340,14 @@ extern "C" int nsol_pd_plan_iterate(nsol_pd_plan *pl, int n, nsol_stream s) {
     const int vecw = gv.dtype == NSOL_F32 ? 4 : 2;
     const bool vec_ok = (gv.nx % vecw) == 0;
     if (pl->link_on && !pl->link_fresh) NSOL_CHECK(pd_link_publish(pl, st));   // also for n == 0 (publish only)
+    // 2-D problems: K iterations per pass over the state in shared-memory tiles (csrc/pd_tb2d.cuh; "pd_tb" tuning knob: 0 auto,
+    // 1 whenever possible, 2 never).  Single images (BASELINE configs 1, 2) lose 1 - 1/K of their dependent L2 round trips and
+    // launches, batched sweeps (config 5) 1 - 1/K of their HBM traffic.
+    if (gv.dim == 2 && gv.comp_z >= 0 && gv.comp_y < 0 && !pl->link_on && !pl->halo_above && !pl->halo_below && ctx->pd_tb != 2 &&
+        (n >= 2 || ctx->pd_tb == 1) && n >= 1) {
+        int rc = gv.dtype == NSOL_F32 ? pd_iterate_tb2d<float>(pl, n, st) : pd_iterate_tb2d<double>(pl, n, st);
+        if (rc != NSOL_ESTATE) return rc;
+    }
     // Small 2-D / 1-D problems whose state is L2-resident (BASELINE configs 1, 2): one persistent cooperative launch for all n
     // iterations instead of n launches ("pd_persist" tuning knob: 0 auto, 1 whenever possible, 2 never).
     if (n >= 2 && gv.comp_y < 0 && vec_ok && !pl->link_on && !pl->halo_above && !pl->halo_below && ctx->pd_persist != 2 &&

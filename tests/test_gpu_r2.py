@@ -551,3 +551,71 @@ def test_pipelined_host_solve_with_the_reference_wiring_and_pinned_buffers():
         assert np.array_equal(s2.get_x(), x)
     finally:
         ctx.set_tuning("pd_pipe", 0)
+
+
+# ------------------------------------------------------------------ 2-D temporal blocking (K iterations per pass, csrc/pd_tb2d.cuh)
+@pytest.mark.parametrize("shape,reg,data,alg,spacing,iterations", [
+    ((256, 256), "TV", "L2", "ALG2", None, 100),            # BASELINE config 1's shape of work
+    ((75, 131), "HUBER", "L1", "ALG2", None, 23),           # ragged, iterations not a multiple of K
+    ((40, 36), "TK1", "L2", "ALG3", None, 9),
+    ((90, 70), "TV", "L1", "ALG2_AHMOD", (0.7, 1.3), 14),   # non-unit spacing
+    ((33, 300), "HUBER", "L2", "ALG2", None, 5),
+    ((300, 17), "TV", "L2", "ALG2", None, 6),               # narrower than one tile, odd width
+])
+def test_temporal_blocking_2d_is_bit_identical(shape, reg, data, alg, spacing, iterations):
+    """The tile kernel that runs K iterations per pass must reproduce the one-pass-per-iteration kernels bit for bit (float64;
+    1e-6 in float32) for every K / region height, and the oracle."""
+    from nsol_b200 import _lib
+    ctx = _lib.context()
+    rng = np.random.RandomState(shape[0] + iterations)
+    obs = rng.rand(*shape) * 200
+    kw = dict(reg=reg, data=data, alpha=0.3 if data == "L1" else 0.04, L2=8, iterations=iterations, alg_type=alg, spacing=spacing)
+    try:
+        ctx.set_tuning("pd_tb", 2)
+        plain = run_pd(obs, **kw)
+        plain32 = run_pd(obs, dtype="float32", **kw)
+        for k, nr in ((0, 0), (1, 1), (3, 2), (7, 1), (12, 4), (2, 4), (15, 2), (5, 1)):
+            ctx.set_tuning("pd_tb", 1)
+            ctx.set_tuning("pd_tb_k", k)
+            ctx.set_tuning("pd_tb_nr", nr)
+            assert np.array_equal(run_pd(obs, **kw), plain), (k, nr)
+            assert rel_max(run_pd(obs, dtype="float32", **kw), plain32) < 1e-6, (k, nr)
+    finally:
+        for key in ("pd_tb", "pd_tb_k", "pd_tb_nr"):
+            ctx.set_tuning(key, 0)
+    sp = None if spacing is None else np.asarray(spacing, dtype=float)
+    ref = orc.primal_dual_denoise(obs.reshape(-1), obs.shape, reg=reg, data=data, alpha=kw["alpha"], L2=8, iterations=iterations,
+                                  x_scale=float(obs.max()), alg_type=alg, spacing=sp)
+    assert np.array_equal(plain, ref)
+
+
+def test_temporal_blocking_2d_batched_sweep_and_observer():
+    """Batched alpha sweep (config 5's shape of work) through the tile kernel, and an Observer run (one iteration per call)
+    continuing on a plan whose x arrays have been swapped by the tile kernel."""
+    from nsol_b200 import _lib
+    from nsol_b200.observer import Observer
+    ctx = _lib.context()
+    rng = np.random.RandomState(2)
+    obs = rng.rand(120, 88) * 90
+    alphas = np.linspace(0.002, 0.08, 5)
+    try:
+        ctx.set_tuning("pd_tb", 2)
+        ref = make_pd(obs, reg="HUBER", data="L2", alpha=0.01, L2=8, iterations=31).run_sweep(alphas)
+        ctx.set_tuning("pd_tb", 0)
+        got = make_pd(obs, reg="HUBER", data="L2", alpha=0.01, L2=8, iterations=31).run_sweep(alphas)
+        assert np.array_equal(got, ref)
+        s = make_pd(obs, reg="TV", data="L2", alpha=0.03, L2=8, iterations=7)
+        s.run()                                  # 7 iterations: two passes, x lives in the second array now
+        x7 = s.get_x()
+        o = Observer()
+        s.set_observer(o)
+        s.run()                                  # the same plan, one iteration per call, iterates stored
+        its = o.get_x_list()
+        assert len(its) == 8 and np.array_equal(its[-1], x7)
+        ctx.set_tuning("pd_tb", 1)               # single iterations through the tile kernel as well
+        o2 = Observer()
+        s.set_observer(o2)
+        s.run()
+        assert all(np.array_equal(u, v) for u, v in zip(o2.get_x_list(), its))
+    finally:
+        ctx.set_tuning("pd_tb", 0)
