@@ -211,6 +211,9 @@ int nsol_pd_plan_get_x_dev(nsol_pd_plan *plan, int dtype_out, void *out_dev, nso
  * "pd_pipe_depth", "pd_pipe_planes"); otherwise it is reset_host + iterate + get_x_host.  Same kernels, same bits.  Synchronous. */
 int nsol_pd_plan_solve_host(nsol_pd_plan *plan, const double *b_host, const double *x0_host, int iterations, double *x_host,
                             nsol_stream s);
+/* linked z-slabs (nsol_pd_plan_link_*): direction of the transfer groups of nsol_pd_plan_solve_host, +1 bottom-up (default),
+ * -1 top-down; neighbouring slabs must alternate (rank parity) so that the wavefront continues through the slab boundaries */
+int nsol_pd_plan_set_pipe_direction(nsol_pd_plan *plan, int direction);
 /* transfer groups / wavefront depth used by the last nsol_pd_plan_solve_host (0 groups: the plain sequence) */
 int nsol_pd_plan_solve_info(const nsol_pd_plan *plan, int *groups_out, int *depth_out);
 /* one call = PrimalDualSolver.run() + get_x() with host float64 buffers

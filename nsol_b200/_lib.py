@@ -91,6 +91,7 @@ SIGNATURES = {
     "nsol_pd_plan_get_x_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsol_pd_plan_get_x_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "nsol_pd_plan_solve_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "nsol_pd_plan_set_pipe_direction": (C.c_int, [C.c_void_p, C.c_int]),
     "nsol_pd_plan_solve_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "nsol_pd_run_host": (C.c_int, [C.c_void_p, C.POINTER(PdDesc), C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),

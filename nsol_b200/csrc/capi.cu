@@ -223,6 +223,16 @@ static void launch_scale_convert(nsol_ctx *ctx, long long n, const void *in, voi
         scale_convert_kernel<TI, TO, false><<<blocks, threads, 0, s>>>(n, (const TI *)in, (TO *)out, f);
 }
 
+// force the (lazily loaded) conversion kernels into the context -- see pd_preload in pd_kernels.cu
+void nsol_preload_scale_convert() {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, scale_convert_kernel<double, double, true>);
+    cudaFuncGetAttributes(&fa, scale_convert_kernel<double, double, false>);
+    cudaFuncGetAttributes(&fa, scale_convert_kernel<double, float, true>);
+    cudaFuncGetAttributes(&fa, scale_convert_kernel<float, double, false>);
+    cudaGetLastError();
+}
+
 extern "C" int nsol_scale_convert(nsol_ctx *ctx, int64_t n, int dtype_in, const void *in_dev, int dtype_out,
                                   void *out_dev, double factor, int divide, nsol_stream s) {
     if (!ctx) return NSOL_EINVAL;

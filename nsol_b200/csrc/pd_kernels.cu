@@ -533,6 +533,8 @@ struct nsol_pd_plan {
     cudaEvent_t pipe_fork = nullptr;
     std::vector<cudaEvent_t> pipe_ev_up, pipe_ev_x, pipe_ev_dn;
     int pipe_groups_last = 0, pipe_depth_last = 0;   // what the last solve did (0 groups: plain sequence)
+    int pipe_dir = 1;                 // +1: groups travel bottom-up, -1: top-down (odd ranks of a linked z-slab decomposition)
+    unsigned pipe_g0 = 0;             // link generation of the start state of the running pipelined solve
 };
 
 // layout of a link block (all offsets 256-byte aligned)
@@ -862,24 +864,28 @@ __global__ void __launch_bounds__(256) pd_link_publish_kernel(const LinkPublishA
     }
 }
 
-static int pd_link_publish(nsol_pd_plan *pl, cudaStream_t s) {
+// sides: 1 = towards the lower neighbour, 2 = towards the upper one, 3 = both (and the plan's generation counter advances);
+// a one-sided call (pipelined solve: a boundary group has just been reset) publishes generation pl->link_pub without advancing it
+static int pd_link_publish(nsol_pd_plan *pl, cudaStream_t s, int sides = 3) {
     nsol_ctx *ctx = pl->ctx;
     const GridView &gv = pl->gv;
     const size_t plane = (size_t)gv.nx * gv.ny * pl->esz;
     const unsigned g = pl->link_pub;
+    const bool below = pl->peer_below && (sides & 1), above = pl->peer_above && (sides & 2);
+    if (!below && !above && sides != 3) return NSOL_OK;
     const int wr = (int)(g & 1u);
     const char *xb = (const char *)pl->xbar[pl->cur];
     LinkPublishArgs a;
     a.xbar_first = xb;
     a.xbar_last = xb + (size_t)(gv.nz - 1) * plane;
     a.pz_last = (const char *)pl->p[pl->cur][gv.comp_z] + (size_t)(gv.nz - 1) * plane;
-    a.dst_below_xbar = pl->peer_below ? pl->peer_below + link_slot(pl, wr, 0) : nullptr;
-    a.dst_above_xbar = pl->peer_above ? pl->peer_above + link_slot(pl, wr, 1) : nullptr;
-    a.dst_above_pz = pl->peer_above ? pl->peer_above + link_slot(pl, wr, 2) : nullptr;
-    a.flag_below = pl->peer_below ? (const unsigned *)(pl->link_block + LINK_FLAG_BELOW) : nullptr;
-    a.flag_above = pl->peer_above ? (const unsigned *)(pl->link_block + LINK_FLAG_ABOVE) : nullptr;
-    a.peer_flag_below = pl->peer_below ? (unsigned *)(pl->peer_below + LINK_FLAG_ABOVE) : nullptr;
-    a.peer_flag_above = pl->peer_above ? (unsigned *)(pl->peer_above + LINK_FLAG_BELOW) : nullptr;
+    a.dst_below_xbar = below ? pl->peer_below + link_slot(pl, wr, 0) : nullptr;
+    a.dst_above_xbar = above ? pl->peer_above + link_slot(pl, wr, 1) : nullptr;
+    a.dst_above_pz = above ? pl->peer_above + link_slot(pl, wr, 2) : nullptr;
+    a.flag_below = below ? (const unsigned *)(pl->link_block + LINK_FLAG_BELOW) : nullptr;
+    a.flag_above = above ? (const unsigned *)(pl->link_block + LINK_FLAG_ABOVE) : nullptr;
+    a.peer_flag_below = below ? (unsigned *)(pl->peer_below + LINK_FLAG_ABOVE) : nullptr;
+    a.peer_flag_above = above ? (unsigned *)(pl->peer_above + LINK_FLAG_BELOW) : nullptr;
     a.count = (unsigned *)(pl->link_block + LINK_COUNT_BELOW);
     a.error = (int *)(pl->link_block + LINK_ERROR);
     a.plane_vec = plane / 16;
@@ -888,8 +894,10 @@ static int pd_link_publish(nsol_pd_plan *pl, cudaStream_t s) {
     a.publish = g + 1u;
     pd_link_publish_kernel<<<32, 256, 0, s>>>(a);
     NSOL_LAUNCH_CHECK(ctx);
-    pl->link_pub = g + 1u;
-    pl->link_fresh = true;
+    if (sides == 3) {
+        pl->link_pub = g + 1u;
+        pl->link_fresh = true;
+    }
     return NSOL_OK;
 }
 
@@ -981,6 +989,20 @@ extern "C" int nsol_pd_plan_link_status(nsol_pd_plan *pl, nsol_stream s) {
     return NSOL_OK;
 }
 
+// Query mode: the launch helpers below only make sure the kernel they would launch is LOADED (CUDA loads kernels lazily, and loading
+// one may wait for every running kernel of the context -- which must not happen behind a kernel that spins on a neighbour's flag:
+// the pipelined solve through linked z-slabs preloads what it is going to launch, pd_preload).
+static thread_local bool g_pd_query_only = false;
+#define NSOL_PD_LAUNCH(KERNEL, GRID, BLOCK, SMEM, STREAM, ARGS)                \
+    do {                                                                       \
+        if (g_pd_query_only) {                                                 \
+            cudaFuncAttributes fa__;                                           \
+            cudaFuncGetAttributes(&fa__, KERNEL);                              \
+        } else {                                                               \
+            KERNEL<<<GRID, BLOCK, SMEM, STREAM>>>(ARGS);                       \
+        }                                                                      \
+    } while (0)
+
 template <typename T, int VEC, bool HAS_Y>
 static void pd_launch_rd(const nsol_pd_plan *pl, const PdArgs<T> &a, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
     const int reg = pl->desc.reg, data = pl->desc.data;
@@ -991,11 +1013,11 @@ static void pd_launch_rd(const nsol_pd_plan *pl, const PdArgs<T> &a, dim3 grid, 
 #define NSOL_PD_CASE(R, D)                                                                                   \
     if (reg == R && data == D) {                                                                             \
         if (unit) {                                                                                          \
-            if (link) pd_iter_kernel<T, VEC, HAS_Y, R, D, true, CAN_UNIT><<<grid, block, smem, s>>>(a);      \
-            else pd_iter_kernel<T, VEC, HAS_Y, R, D, false, CAN_UNIT><<<grid, block, smem, s>>>(a);          \
+            if (link) NSOL_PD_LAUNCH((pd_iter_kernel<T, VEC, HAS_Y, R, D, true, CAN_UNIT>), grid, block, smem, s, a);   \
+            else NSOL_PD_LAUNCH((pd_iter_kernel<T, VEC, HAS_Y, R, D, false, CAN_UNIT>), grid, block, smem, s, a);       \
         } else {                                                                                             \
-            if (link) pd_iter_kernel<T, VEC, HAS_Y, R, D, true, false><<<grid, block, smem, s>>>(a);         \
-            else pd_iter_kernel<T, VEC, HAS_Y, R, D, false, false><<<grid, block, smem, s>>>(a);             \
+            if (link) NSOL_PD_LAUNCH((pd_iter_kernel<T, VEC, HAS_Y, R, D, true, false>), grid, block, smem, s, a);      \
+            else NSOL_PD_LAUNCH((pd_iter_kernel<T, VEC, HAS_Y, R, D, false, false>), grid, block, smem, s, a);          \
         }                                                                                                    \
         return;                                                                                              \
     }
@@ -1019,7 +1041,7 @@ static int pd_launch_bulk_one(const nsol_pd_plan *pl, const PdArgs<T> &a, dim3 g
         if (e != cudaSuccess) return nsol_fail(pl->ctx, NSOL_ECUDA, "pd bulk: smem opt-in %zu -> %s", smem, cudaGetErrorString(e));
         configured[dev] = smem;
     }
-    pd_iter_bulk_kernel<T, VEC, R, D, LINK, UNIT><<<grid, block, smem, s>>>(a);
+    NSOL_PD_LAUNCH((pd_iter_bulk_kernel<T, VEC, R, D, LINK, UNIT>), grid, block, smem, s, a);
     return NSOL_OK;
 }
 
@@ -1132,7 +1154,7 @@ template <typename T, int VECW>
 static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, int persist_n = 0, const PdRange *rg = nullptr) {
     nsol_ctx *ctx = pl->ctx;
     const GridView &gv = pl->gv;
-    if (rg && (pl->link_on || part != 0 || persist_n > 1)) return nsol_fail(ctx, NSOL_ESTATE, "pd: chunk-range launch in link / split / persistent mode");
+    if (rg && (part != 0 || persist_n > 1)) return nsol_fail(ctx, NSOL_ESTATE, "pd: chunk-range launch in split / persistent mode");
     const int cur = rg ? (rg->it & 1) : pl->cur, nxt = cur ^ 1;
     PdArgs<T> a;
     a.xbar_in = (const T *)pl->xbar[cur];
@@ -1159,12 +1181,14 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, i
     a.link_timeout_ns = (unsigned long long)(ctx->link_timeout_ms > 0 ? ctx->link_timeout_ms : NSOL_LINK_TIMEOUT_MS) * 1000000ull;
     if (pl->link_on) {
         if (part != 0) return nsol_fail(ctx, NSOL_ESTATE, "pd: the split iteration is not available with the in-kernel halo exchange");
-        // this iteration consumes generation g = link_pub - 1 and publishes generation link_pub
-        const unsigned g = pl->link_pub - 1;
-        const int rd = (int)(g & 1u), wr = (int)(pl->link_pub & 1u);
+        // this iteration consumes generation g = link_pub - 1 and publishes generation link_pub; a chunk-range launch of the
+        // pipelined solve counts from the generation of the solve's start state (every boundary has its own pace there)
+        const unsigned link_pub = rg ? pl->pipe_g0 + 1u + (unsigned)rg->it : pl->link_pub;
+        const unsigned g = link_pub - 1;
+        const int rd = (int)(g & 1u), wr = (int)(link_pub & 1u);
         a.link_error = (int *)(pl->link_block + LINK_ERROR);
         a.want = g + 1u;
-        a.publish = pl->link_pub + 1u;
+        a.publish = link_pub + 1u;
         if (pl->peer_below) {
             a.halo_xbar_below = (const T *)(pl->link_block + link_slot(pl, rd, 1));
             a.halo_pz_below = (const T *)(pl->link_block + link_slot(pl, rd, 2));
@@ -1227,8 +1251,21 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, i
         if (rg->c0 < 0 || rg->c1 > a.nchunks || rg->c0 >= rg->c1) return nsol_fail(ctx, NSOL_EINVAL, "pd: bad chunk range [%d, %d) of %d", rg->c0, rg->c1, a.nchunks);
         a.chunk_first = rg->c0;
         a.nsel = rg->c1 - rg->c0;
+        // a boundary that is not part of the range neither waits nor publishes in this launch
+        if (rg->c0 > 0) {
+            a.flag_below = nullptr;
+            a.count_below = nullptr;
+            a.push_below_xbar = nullptr;
+            a.peer_flag_below = nullptr;
+        }
+        if (rg->c1 < a.nchunks) {
+            a.flag_above = nullptr;
+            a.count_above = nullptr;
+            a.push_above_xbar = a.push_above_pz = nullptr;
+            a.peer_flag_above = nullptr;
+        }
     }
-    a.front_chunks = (pl->link_on && a.nchunks >= 3) ? 1 : 0;
+    a.front_chunks = (pl->link_on && a.nchunks >= 3 && !rg) ? 1 : 0;
     const long long gz = (long long)a.nsel * gv.batch;
     if (gz > 65535) return nsol_fail(ctx, NSOL_EINVAL, "pd: nchunks*batch = %lld exceeds the grid limit; raise pd_zc", gz);
     grid.z = (unsigned)gz;
@@ -1256,6 +1293,7 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, i
     } else {
         pd_launch_rd<T, VECW, false>(pl, a, grid, block, smem, s);
     }
+    if (g_pd_query_only) return NSOL_OK;
     NSOL_LAUNCH_CHECK(ctx);
     if (part != 1 && !rg) {
         pl->cur = nxt;
@@ -1471,6 +1509,22 @@ static int pd_launch_range(nsol_pd_plan *pl, cudaStream_t st, int c0, int c1, in
 // 0, 1, ..., D-1; after the last upload the volume is brought to D iterations everywhere, iterations D ... n-D'-1 are whole-volume
 // launches, and the mirror image at the end lets group 0 finish first and go back to the host while the groups above it catch up.
 // The kernels, the chunk geometry and therefore every bit of the result are those of nsol_pd_plan_iterate.
+void nsol_preload_scale_convert();      // capi.cu
+
+// load every kernel the pipelined solve of this plan is going to launch (see g_pd_query_only)
+template <typename T>
+static int pd_preload(nsol_pd_plan *pl, cudaStream_t st) {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, pd_reset_range_kernel<T>);
+    cudaFuncGetAttributes(&fa, pd_link_publish_kernel);
+    nsol_preload_scale_convert();
+    g_pd_query_only = true;
+    const int rc = pd_launch_range<T>(pl, st, 0, 1, 0);
+    g_pd_query_only = false;
+    cudaGetLastError();
+    return rc;
+}
+
 template <typename T>
 static int pd_solve_pipelined(nsol_pd_plan *pl, const double *b_host, const double *x0_host, int iterations, double *x_host,
                               cudaStream_t st, int planes, int depth) {
@@ -1478,7 +1532,7 @@ static int pd_solve_pipelined(nsol_pd_plan *pl, const double *b_host, const doub
     const GridView &gv = pl->gv;
     const int vecw = sizeof(T) == 4 ? 4 : 2;
     int ty, zc;
-    pd_tiling(ctx, gv, (gv.nx % vecw) == 0 ? vecw : 1, &ty, &zc, false);
+    pd_tiling(ctx, gv, (gv.nx % vecw) == 0 ? vecw : 1, &ty, &zc, pl->link_on);
     const int nchunks = (gv.nz + zc - 1) / zc;
     const int gch = planes / zc > 0 ? planes / zc : 1;              // z-chunks per transfer group
     const int ng = (nchunks + gch - 1) / gch;
@@ -1499,30 +1553,49 @@ static int pd_solve_pipelined(nsol_pd_plan *pl, const double *b_host, const doub
             v->push_back(e);
         }
     double *sb = (double *)pl->stage, *sx = same ? sb : sb + nv;
-    auto g_lo = [&](int g) { return (long long)std::min(g * gch * zc, gv.nz) * plane; };     // first voxel of group g
+    // Groups are numbered in ARRIVAL order: arrival index c is the spatial group c when the transfers run bottom-up and
+    // ng - 1 - c when they run top-down.  Neighbouring z-slabs of a linked decomposition run in opposite directions, so the two
+    // groups that face each other across a slab boundary are both first or both last to arrive -- the wavefront then continues
+    // through the boundary (the boundary groups' launches wait for / publish the halo planes by iteration number).
+    const bool down = pl->link_on && pl->pipe_dir < 0;
+    auto spatial = [&](int c) { return down ? ng - 1 - c : c; };
+    auto g_lo = [&](int g) { return (long long)std::min(g * gch * zc, gv.nz) * plane; };     // first voxel of spatial group g
+    auto chunk_lo = [&](int g) { return std::min(g * gch, nchunks); };
     const int d_up = std::min(depth, iterations / 2), d_dn = std::min(depth, iterations - d_up);
-    std::vector<int> done(ng, -1);                                   // -1: not yet on the device
+    std::vector<int> done(ng, -1);                                   // by arrival index; -1: not yet on the device
     auto advance = [&](int c) -> int {
         // the wavefront rule: both neighbours hold the state this iteration reads
         if (done[c] < 0 || (c > 0 && done[c - 1] < done[c]) || (c + 1 < ng && done[c + 1] < done[c]))
             return nsol_fail(ctx, NSOL_ESTATE, "pd pipelined solve: wavefront order violated at group %d", c);
-        NSOL_CHECK(pd_launch_range<T>(pl, st, c * gch, std::min((c + 1) * gch, nchunks), done[c]));
+        const int g = spatial(c);
+        NSOL_CHECK(pd_launch_range<T>(pl, st, chunk_lo(g), chunk_lo(g + 1), done[c]));
         done[c] += 1;
         return NSOL_OK;
     };
+    // a merged launch of the arrival groups [0, top], all at iteration `it`
+    auto advance_first = [&](int top, int it) -> int {
+        const int ga = spatial(0), gb = spatial(top);
+        return pd_launch_range<T>(pl, st, chunk_lo(std::min(ga, gb)), chunk_lo(std::max(ga, gb) + 1), it);
+    };
+    NSOL_CHECK(pd_preload<T>(pl, st));
+    pl->cur = 0;
+    pl->it = 0;
+    pl->pipe_g0 = pl->link_pub;          // generation of this solve's start state
     // ---- uploads, all queued on the copy stream behind whatever the caller's stream holds
     NSOL_CUDA(ctx, cudaEventRecord(pl->pipe_fork, st));
     NSOL_CUDA(ctx, cudaStreamWaitEvent(pl->pipe_up, pl->pipe_fork, 0));
-    for (int g = 0; g < ng; ++g) {
+    for (int c = 0; c < ng; ++c) {
+        const int g = spatial(c);
         const long long lo = g_lo(g), cnt = g_lo(g + 1) - lo;
         NSOL_CUDA(ctx, cudaMemcpyAsync(sb + lo, b_host + lo, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, pl->pipe_up));
         if (!same) NSOL_CUDA(ctx, cudaMemcpyAsync(sx + lo, x0_host + lo, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, pl->pipe_up));
-        NSOL_CUDA(ctx, cudaEventRecord(pl->pipe_ev_up[g], pl->pipe_up));
+        NSOL_CUDA(ctx, cudaEventRecord(pl->pipe_ev_up[c], pl->pipe_up));
     }
     // ---- arrival phase: group j lands -> reset it, groups j-1 ... j-D advance one iteration each (newest first)
     for (int j = 0; j < ng + d_up; ++j) {
         if (j < ng) {
-            const long long lo = g_lo(j), cnt = g_lo(j + 1) - lo;
+            const int g = spatial(j);
+            const long long lo = g_lo(g), cnt = g_lo(g + 1) - lo;
             NSOL_CUDA(ctx, cudaStreamWaitEvent(st, pl->pipe_ev_up[j], 0));
             const int threads = 256;
             const long long want = (cnt + threads - 1) / threads;
@@ -1532,6 +1605,11 @@ static int pd_solve_pipelined(nsol_pd_plan *pl, const double *b_host, const doub
                                                                 (T *)pl->x + lo, (T *)pl->xbar[0] + lo, (T *)pl->p[0][0] + lo, p1, p2);
             NSOL_LAUNCH_CHECK(ctx);
             done[j] = 0;
+            if (pl->link_on) {
+                // the start state of a boundary group goes to the neighbour as soon as it exists
+                if (g == 0) NSOL_CHECK(pd_link_publish(pl, st, 1));
+                if (g == ng - 1) NSOL_CHECK(pd_link_publish(pl, st, 2));
+            }
         }
         for (int c = std::min(j - 1, ng - 1); c >= std::max(0, j - d_up); --c) NSOL_CHECK(advance(c));
     }
@@ -1539,17 +1617,20 @@ static int pd_solve_pipelined(nsol_pd_plan *pl, const double *b_host, const doub
     pl->cur = d_up & 1;
     pl->it = d_up;
     pl->ready = true;
-    pl->link_fresh = false;
+    if (pl->link_on) {
+        pl->link_pub = pl->pipe_g0 + 1u + (unsigned)d_up;
+        pl->link_fresh = true;
+    }
     for (int i = d_up; i < iterations - d_dn; ++i) {
         if (sizeof(T) == 4) NSOL_CHECK(((gv.nx % 4) == 0 ? pd_launch_iteration<float, 4>(pl, st) : pd_launch_iteration<float, 1>(pl, st)));
         else NSOL_CHECK(((gv.nx % 2) == 0 ? pd_launch_iteration<double, 2>(pl, st) : pd_launch_iteration<double, 1>(pl, st)));
     }
     for (int c = 0; c < ng; ++c) done[c] = iterations - d_dn;
-    // ---- ramp: round t advances the groups [0, d_dn - t] (one launch, they are at the same iteration) -> group c is c iterations
-    // short of the end
+    // ---- ramp: round t advances the arrival groups [0, d_dn - t] (one launch, they are at the same iteration) -> group c is c
+    // iterations short of the end
     for (int t = 1; t <= d_dn; ++t) {
         const int top = std::min(d_dn - t, ng - 1);
-        NSOL_CHECK(pd_launch_range<T>(pl, st, 0, std::min((top + 1) * gch, nchunks), iterations - d_dn + t - 1));
+        NSOL_CHECK(advance_first(top, iterations - d_dn + t - 1));
         for (int c = 0; c <= top; ++c) done[c] += 1;
     }
     // ---- departure phase: step j finishes group j (farthest group first), converts it and sends it home on the copy stream
@@ -1557,7 +1638,8 @@ static int pd_solve_pipelined(nsol_pd_plan *pl, const double *b_host, const doub
         for (int c = std::min(j + d_dn - 1, ng - 1); c >= j; --c)
             if (done[c] < iterations && (c + 1 >= ng || done[c + 1] >= done[c])) NSOL_CHECK(advance(c));
         if (done[j] != iterations) return nsol_fail(ctx, NSOL_ESTATE, "pd pipelined solve: group %d stopped at iteration %d", j, done[j]);
-        const long long lo = g_lo(j), cnt = g_lo(j + 1) - lo;
+        const int g = spatial(j);
+        const long long lo = g_lo(g), cnt = g_lo(g + 1) - lo;
         NSOL_CHECK(nsol_scale_convert(ctx, cnt, gv.dtype, (const T *)pl->x + lo, NSOL_F64, sb + lo, pl->desc.x_scale, 0, (nsol_stream)st));
         NSOL_CUDA(ctx, cudaEventRecord(pl->pipe_ev_x[j], st));
         NSOL_CUDA(ctx, cudaStreamWaitEvent(pl->pipe_dn, pl->pipe_ev_x[j], 0));
@@ -1567,9 +1649,14 @@ static int pd_solve_pipelined(nsol_pd_plan *pl, const double *b_host, const doub
     NSOL_CUDA(ctx, cudaStreamWaitEvent(st, pl->pipe_ev_dn[0], 0));
     pl->cur = iterations & 1;
     pl->it = iterations;
+    if (pl->link_on) {
+        pl->link_pub = pl->pipe_g0 + 1u + (unsigned)iterations;
+        pl->link_fresh = true;
+    }
     pl->pipe_groups_last = ng;
     pl->pipe_depth_last = d_up;
     NSOL_CUDA(ctx, cudaStreamSynchronize(st));
+    if (pl->link_on) NSOL_CHECK(nsol_pd_plan_link_status(pl, (nsol_stream)st));
     return NSOL_OK;
 }
 
@@ -1582,7 +1669,8 @@ extern "C" int nsol_pd_plan_solve_host(nsol_pd_plan *pl, const double *b_host, c
     NSOL_CHECK(nsol_bind_device(ctx));
     const GridView &gv = pl->gv;
     pl->pipe_groups_last = 0;
-    const bool possible = gv.comp_z >= 0 && gv.batch == 1 && !pl->link_on && !pl->halo_above && !pl->halo_below && ctx->pd_pipe != 2;
+    // z-slabs: only with the in-kernel halo exchange (caller-refreshed halo buffers belong to whole-slab iterations)
+    const bool possible = gv.comp_z >= 0 && gv.batch == 1 && (pl->link_on || (!pl->halo_above && !pl->halo_below)) && ctx->pd_pipe != 2;
     if (possible && (ctx->pd_pipe == 1 || ((size_t)gv.n * sizeof(double) >= ((size_t)64 << 20) && pd_host_pinned(b_host) &&
                                            pd_host_pinned(x_host) && (!x0_host || x0_host == b_host || pd_host_pinned(x0_host))))) {
         const int planes = ctx->pd_pipe_planes > 0 ? ctx->pd_pipe_planes : 16;
@@ -1593,6 +1681,14 @@ extern "C" int nsol_pd_plan_solve_host(nsol_pd_plan *pl, const double *b_host, c
     NSOL_CHECK(nsol_pd_plan_reset_host(pl, b_host, x0_host, s));
     NSOL_CHECK(nsol_pd_plan_iterate(pl, iterations, s));
     return nsol_pd_plan_get_x_host(pl, x_host, s);
+}
+
+// Direction in which the transfer groups of nsol_pd_plan_solve_host travel through a linked z-slab: +1 bottom-up, -1 top-down.
+// Neighbouring slabs must run in opposite directions (rank parity) for the wavefront to continue through their boundary.
+extern "C" int nsol_pd_plan_set_pipe_direction(nsol_pd_plan *pl, int direction) {
+    if (!pl) return NSOL_EINVAL;
+    pl->pipe_dir = direction < 0 ? -1 : 1;
+    return NSOL_OK;
 }
 
 // transfer groups and wavefront depth of the last nsol_pd_plan_solve_host (0 groups: the plain upload / iterate / download sequence)

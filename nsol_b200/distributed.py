@@ -129,6 +129,9 @@ class SlabPrimalDual(object):
             err = self._connect_link()
             if err is None:
                 self.mode = "p2p"
+                # pipelined host solves (nsol_pd_plan_solve_host): neighbouring slabs move their transfer groups in opposite
+                # directions, so the wavefront of iterations continues through the slab boundaries
+                ctx.check(ctx.lib.nsol_pd_plan_set_pipe_direction(self.plan, -1 if rank % 2 else 1))
             elif self.mode == "p2p":
                 raise RuntimeError("in-kernel halo exchange unavailable: %s" % err)
             else:
@@ -226,6 +229,20 @@ class SlabPrimalDual(object):
             self.check(stream)
         self._halo_fresh = False
         self.ctx.check(self.ctx.lib.nsol_pd_plan_reset_host(self.plan, b_host_ptr, x0_host_ptr, stream))
+
+    def solve_host(self, b_host_ptr, x0_host_ptr, iterations, x_host_ptr, stream):
+        """One whole solve from / to host memory (every rank, same ``iterations``): upload, iterations and download of the slab
+        overlap where the library can pipeline them (single rank or in-kernel halo exchange, page-locked buffers); with
+        NCCL halos it is reset + iterate + download.  Synchronous; raises if a halo wait timed out."""
+        lib, ctx, plan = self.ctx.lib, self.ctx, self.plan
+        if self._unchecked:
+            self.check(stream)
+        if self.mode in ("single", "p2p"):
+            ctx.check(lib.nsol_pd_plan_solve_host(plan, b_host_ptr, x0_host_ptr, iterations, x_host_ptr, stream))
+            return
+        self.reset_host(b_host_ptr, x0_host_ptr, stream)
+        self.iterate(iterations, stream)
+        ctx.check(lib.nsol_pd_plan_get_x_host(plan, x_host_ptr, stream))
 
     def reset_dev(self, b_dev_ptr, x0_dev_ptr, stream, check=True):
         if check and self._unchecked:

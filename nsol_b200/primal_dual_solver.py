@@ -258,13 +258,16 @@ class PrimalDualSolver(Solver):
             ctx.check(lib.nsol_pd_plan_get_x_host(plan, out.ctypes.data, None))
             return out
 
-        if slab is None and self._observer is None:
+        if self._observer is None:
             # No Observer: the whole solve is ONE library call that also brings the result back -- for a large volume the upload,
             # the iterations and the download overlap (nsol_pd_plan_solve_host).  The first get_x() hands that array out, later
             # calls download a fresh copy like the reference returns a fresh array (nsol/solver.py:117-118).
             first = [ctx.result_empty(n, np.float64)]
-            ctx.check(lib.nsol_pd_plan_solve_host(plan, b.ctypes.data, x0.ctypes.data if x0 is not None else None, iters,
-                                                  first[0].ctypes.data, None))
+            if slab is not None:
+                slab.solve_host(b.ctypes.data, x0.ctypes.data if x0 is not None else None, iters, first[0].ctypes.data, None)
+            else:
+                ctx.check(lib.nsol_pd_plan_solve_host(plan, b.ctypes.data, x0.ctypes.data if x0 is not None else None, iters,
+                                                      first[0].ctypes.data, None))
 
             def fetch_first():
                 if first:

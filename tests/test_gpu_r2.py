@@ -619,3 +619,105 @@ def test_temporal_blocking_2d_batched_sweep_and_observer():
         assert all(np.array_equal(u, v) for u, v in zip(o2.get_x_list(), its))
     finally:
         ctx.set_tuning("pd_tb", 0)
+
+
+# ------------------------------------------------------------------ pipelined host solve through linked z-slabs
+@pytest.mark.parametrize("nslabs,nz,planes,depth,dtype", [
+    (2, 36, 4, 3, "float64"),
+    (3, 40, 4, 10, "float64"),          # ragged slabs (14 / 13 / 13 planes), wavefront as deep as the iterations allow
+    (2, 17, 2, 2, "float32"),
+    (3, 30, 64, 4, "float64"),          # one transfer group per slab: both boundaries in every launch
+])
+def test_pipelined_host_solve_through_linked_zslabs(nslabs, nz, planes, depth, dtype):
+    """nsol_pd_plan_solve_host on z-slabs whose link blocks are connected (one GPU, one context + stream + host thread per slab,
+    like one process per GPU): neighbouring slabs move their transfer groups in opposite directions and the boundary groups
+    exchange their halo planes inside the chunk-range launches, by iteration number.  Bit-identical to the unsharded solve;
+    a second solve and a following plain iterate() continue the generation counters."""
+    import ctypes as C
+    import threading
+
+    import torch
+
+    from nsol_b200 import _lib
+    from nsol_b200.distributed import slab_bounds
+    rng = np.random.RandomState(nz)
+    shape = (nz, 10, 68)
+    obs = rng.rand(*shape) * 255
+    xs = float(obs.max())
+    dcode = _lib.dtype_code(dtype)
+    plane = shape[1] * shape[2]
+    alpha = np.array([0.05])
+    ctxs = [_lib.Context(-1) for _ in range(nslabs)]
+    streams = [torch.cuda.Stream() for _ in range(nslabs)]
+    lib = ctxs[0].lib
+    plans, spans, blocks = [], [], []
+    try:
+        for r, ctx in enumerate(ctxs):
+            for key, val in (("pd_zc", 2), ("pd_pipe", 1), ("pd_pipe_planes", planes), ("pd_pipe_depth", depth), ("link_timeout_ms", 20000)):
+                ctx.set_tuning(key, val)
+            z_lo, z_hi = slab_bounds(shape[0], r, nslabs)
+            spans.append((z_lo, z_hi))
+            desc = _lib.PdDesc()
+            desc.grid = _lib.make_grid((z_hi - z_lo,) + shape[1:], None, dcode, 1)
+            desc.reg, desc.data, desc.alg = _lib.REG["TV"], _lib.DATA["L2"], _lib.ALG["ALG2"]
+            desc.huber_gamma, desc.L2 = 0.05, 8.0
+            desc.x_scale = desc.x0_scale = desc.b_scale = xs
+            desc.alpha = alpha.ctypes.data_as(_lib.c_double_p)
+            h = C.c_void_p()
+            ctx.check(lib.nsol_pd_plan_create(ctx.handle, C.byref(desc), C.byref(h)))
+            plans.append(h)
+            blk, nbytes = C.c_void_p(), C.c_size_t()
+            ctx.check(lib.nsol_pd_plan_link_create(h, C.byref(blk), C.byref(nbytes)))
+            blocks.append(blk)
+        for r, (ctx, h) in enumerate(zip(ctxs, plans)):
+            ctx.check(lib.nsol_pd_plan_link_connect(h, blocks[r - 1] if r > 0 else None, blocks[r + 1] if r < nslabs - 1 else None))
+            ctx.check(lib.nsol_pd_plan_set_pipe_direction(h, -1 if r % 2 else 1))
+        # page-locked host buffers, as the solvers use them: every transfer of the pipeline is asynchronous
+        slabs = []
+        for z_lo, z_hi in spans:
+            a = ctxs[0].pinned_empty(((z_hi - z_lo) * plane,), np.float64)
+            a[:] = obs[z_lo:z_hi].reshape(-1)
+            slabs.append(a)
+        total = 0
+        for iters in (13, 6):
+            outs = [ctxs[0].pinned_empty((s.size,), np.float64) for s in slabs]
+            errs = [None] * nslabs
+
+            def work(r):
+                try:
+                    ctxs[r].check(lib.nsol_pd_plan_solve_host(plans[r], slabs[r].ctypes.data, None, iters, outs[r].ctypes.data,
+                                                              C.c_void_p(streams[r].cuda_stream)))
+                except Exception as e:      # noqa
+                    errs[r] = e
+            threads = [threading.Thread(target=work, args=(r,)) for r in range(nslabs)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            assert errs == [None] * nslabs, errs
+            g, d = C.c_int(), C.c_int()
+            ctxs[0].check(lib.nsol_pd_plan_solve_info(plans[0], C.byref(g), C.byref(d)))
+            assert g.value >= 1 and d.value == min(depth, iters // 2)
+            ref = run_pd(obs, reg="TV", data="L2", alpha=0.05, L2=8, iterations=iters, x_scale=xs, dtype=dtype)
+            got = np.concatenate(outs)
+            if dtype == "float64":
+                assert np.array_equal(got, ref), iters
+            else:
+                assert rel_max(got, ref) < 1e-5
+            total = iters
+        # three more whole-slab iterations on top of the last solve: the generation counters must have stayed consistent
+        for _ in range(3):
+            for ctx, h, st in zip(ctxs, plans, streams):
+                ctx.check(lib.nsol_pd_plan_iterate(h, 1, C.c_void_p(st.cuda_stream)))
+        outs = [np.empty(s.size) for s in slabs]
+        for ctx, h, st, o in zip(ctxs, plans, streams, outs):
+            ctx.check(lib.nsol_pd_plan_get_x_host(h, o.ctypes.data, C.c_void_p(st.cuda_stream)))
+        ref = run_pd(obs, reg="TV", data="L2", alpha=0.05, L2=8, iterations=total + 3, x_scale=xs, dtype=dtype)
+        if dtype == "float64":
+            assert np.array_equal(np.concatenate(outs), ref)
+        else:
+            assert rel_max(np.concatenate(outs), ref) < 1e-5
+    finally:
+        torch.cuda.synchronize()
+        for h in plans:
+            lib.nsol_pd_plan_destroy(h)

@@ -7,7 +7,8 @@
 Every rank constructs the reference-shaped solver on ITS z-slab of one volume, calls distribute() and run(); rank 0
 gathers get_x() of all ranks and compares with the unsharded solver run on its own GPU: the primal-dual result must
 be bit-identical (float64), the ADMM result within 1e-12 (the all-reduced norms are summed in a different order).
-Prints one JSON line; exits non-zero on a mismatch.
+Prints one JSON line; exits non-zero on a mismatch.  With NSOL_PD_PIPE=1 (and NSOL_PD_PIPE_PLANES / NSOL_PD_PIPE_DEPTH) in the
+environment the primal-dual solves take the pipelined host solve through the linked slabs even at small sizes.
 """
 import argparse
 import json
@@ -77,6 +78,12 @@ def main():
         s.run()
         s.run()                                # a second run on the same sharded solver (generation counters, cached plan)
         mine = np.array(s.get_x())
+        if name == "primal_dual":
+            import ctypes as C
+            from nsol_b200 import _lib
+            g, d = C.c_int(), C.c_int()
+            _lib.context().lib.nsol_pd_plan_solve_info(s._plan, C.byref(g), C.byref(d))
+            out["pipelined_groups_depth_rank%d" % rank] = [g.value, d.value]      # (0, 0): plain upload / iterate / download
         parts = [None] * world if rank == 0 else None
         dist.gather_object(mine, parts, dst=0)
         s.release()
