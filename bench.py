@@ -296,8 +296,10 @@ def other_configs(ctx, stream, peak):
         words = 5 + 2 * img.ndim
         return {"ms_per_solve": ms, "voxel_iters_per_s": vox_it / (ms * 1e-3), "iterations": iters, "batch": len(alphas),
                 "us_per_iteration": ms * 1e3 / iters,
-                "hbm_frac_of_measured": words * esz * vox_it / (ms * 1e-3) / 1e9 / peak, "dtype": dtype,
-                "note": "includes the H2D copy of the observation and the reset"}
+                "one_pass_hbm_model_frac": words * esz * vox_it / (ms * 1e-3) / 1e9 / peak, "dtype": dtype,
+                "note": "includes the H2D copy of the observation and the reset; one_pass_hbm_model_frac = (5 + 2d words per "
+                        "pixel-iteration) / time / measured HBM bandwidth -- 2-D solves run K iterations per pass over the state "
+                        "(temporal blocking, csrc/pd_tb2d.cuh), so a value above 1 means fewer passes, not more bandwidth"}
 
     lena = z["lena_256_noise"].astype(np.float64)
     out["C1_2D_TVL2_PD_lena256_100it"] = pd_case(lena, "TV", "L2", [0.05], 100)

@@ -40,6 +40,7 @@ extern "C" int nsol_create(int device, nsol_ctx **out) {
     if (const char *v = getenv("NSOL_LSMR_BLOCKS")) ctx->lsmr_blocks = atoi(v);
     if (const char *v = getenv("NSOL_LSMR_FUSE2D")) ctx->lsmr_fuse2d = atoi(v);
     if (const char *v = getenv("NSOL_LSMR_FUSE3D")) ctx->lsmr_fuse3d = atoi(v);
+    if (const char *v = getenv("NSOL_LSMR_TILE")) ctx->lsmr_tile = atoi(v);
     if (const char *v = getenv("NSOL_PD_PERSIST")) ctx->pd_persist = atoi(v);
     if (const char *v = getenv("NSOL_PD_PERSIST_BLOCKS")) ctx->pd_persist_blocks = atoi(v);
     if (const char *v = getenv("NSOL_PD_TB")) ctx->pd_tb = atoi(v);
@@ -69,6 +70,7 @@ extern "C" int nsol_set_tuning(nsol_ctx *ctx, const char *key, int value) {
     else if (!strcmp(key, "link_timeout_ms")) ctx->link_timeout_ms = value;
     else if (!strcmp(key, "lsmr_fuse2d")) ctx->lsmr_fuse2d = value;
     else if (!strcmp(key, "lsmr_fuse3d")) ctx->lsmr_fuse3d = value;
+    else if (!strcmp(key, "lsmr_tile")) ctx->lsmr_tile = value;
     else if (!strcmp(key, "debug_guard")) ctx->debug_guard = value;
     else if (!strcmp(key, "pd_persist")) ctx->pd_persist = value;
     else if (!strcmp(key, "pd_persist_blocks")) ctx->pd_persist_blocks = value;

@@ -34,6 +34,7 @@ struct nsol_ctx {
                             // 3 multi-kernel with the generic kernels, 4 persistent cooperative solve built from the vector phases
     int lsmr_fuse2d = 0;    // fused 2-D forward / adjoint LSMR kernels: 0 auto (large images), 1 whenever possible, 2 never,
                             // 3 whenever possible with the first-generation kernels (lsmr_fastv.cuh; kept for comparison)
+    int lsmr_tile = 0;      // 2-D persistent solve with tile-fused blur, two grid barriers per inner iteration (csrc/lsmr_tile2d.cuh): 0 on, 2 never
     int lsmr_fuse3d = 0;    // fused 3-D forward / adjoint LSMR kernels (csrc/lsmr_fused3d.cuh): same values
     int link_timeout_ms = 0; // in-kernel halo exchange: give up waiting for a neighbour after this long (0 = 5000)
     // "debug_guard" = 1: the arrays of every plan created afterwards sit between two NaN-filled guard bands; an out-of-bounds

@@ -232,17 +232,23 @@ static bool coopv_ok(const nsol_lsmr_plan *pl) {
     return pl->gv.n <= NSOL_COOPV_MAX_ELEMENTS;
 }
 
+#include "lsmr_tile2d.cuh"
+
 template <typename T, int R>
 static int lsmr_solve_coopv_r(nsol_lsmr_plan *pl, double alpha, const void *b_dev, const void *breg_dev, int maxiter, double lo, double hi,
                               void *x_out, cudaStream_t s, const double *sa_dev) {
     constexpr int VEC = FastvCfg<T>::VEC;
     nsol_ctx *ctx = pl->ctx;
-    static int per_sm[64] = {0};      // co-resident CTAs per SM of this instantiation, per device (0: unknown, -1: unavailable)
+    // 2-D: the tile-fused solve with two grid barriers per inner iteration (lsmr_tile2d.cuh; "lsmr_tile" knob: 2 = never)
+    const bool tile = pl->gv.dim == 2 && ctx->lsmr_tile != 2;
+    static int per_sm_v[64] = {0}, per_sm_t[64] = {0};   // co-resident CTAs per SM of the two kernels of this instantiation, per device
+    int *per_sm = tile ? per_sm_t : per_sm_v;            // (0: unknown, -1: unavailable)
     const int dev = ctx->device & 63;
     if (per_sm[dev] == 0) {
         int coop = 0, v = 0;
         NSOL_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
-        if (coop) NSOL_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, lsmr_coopv_kernel<T, R, VEC>, FAST_TH, 0));
+        if (coop && tile) NSOL_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, lsmr_coopt_kernel<T, R, VEC>, FAST_TH, 0));
+        else if (coop) NSOL_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, lsmr_coopv_kernel<T, R, VEC>, FAST_TH, 0));
         per_sm[dev] = v > 0 ? v : -1;
     }
     if (per_sm[dev] < 0) return NSOL_ESTATE;
@@ -267,6 +273,7 @@ static int lsmr_solve_coopv_r(nsol_lsmr_plan *pl, double alpha, const void *b_de
     a.vgx = (unsigned)((pl->gv.nx / VEC + FAST_TH - 1) / FAST_TH);
     // grid: one CTA per row-mapped virtual block up to what is co-resident; grid.sync() cost grows with the block count
     long long want = (long long)a.vgx * pl->gv.ny * pl->gv.nz;
+    if (tile) want = (long long)((pl->gv.nx + LT_TW - 1) / LT_TW) * ((pl->gv.nz + LT_TH - 1) / LT_TH);
     // measured (profiles/r2_latency_configs.md): flat from 2 CTAs per SM on, slower below (the phases are bound by the latency
     // of their dependent L2 accesses, which more CTAs overlap -- not by grid.sync())
     int cap_per_sm = per_sm[dev] > 4 ? 4 : per_sm[dev];
@@ -284,7 +291,8 @@ static int lsmr_solve_coopv_r(nsol_lsmr_plan *pl, double alpha, const void *b_de
     }
     a.part = pl->coopv_part;
     void *params[] = {(void *)&a};
-    NSOL_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)lsmr_coopv_kernel<T, R, VEC>, dim3(blocks), dim3(FAST_TH), params, 0, s));
+    const void *kernel = tile ? (const void *)lsmr_coopt_kernel<T, R, VEC> : (const void *)lsmr_coopv_kernel<T, R, VEC>;
+    NSOL_CUDA(ctx, cudaLaunchCooperativeKernel(kernel, dim3(blocks), dim3(FAST_TH), params, 0, s));
     ctx->launches++;
     return NSOL_OK;
 }

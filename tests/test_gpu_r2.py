@@ -721,3 +721,70 @@ def test_pipelined_host_solve_through_linked_zslabs(nslabs, nz, planes, depth, d
         torch.cuda.synchronize()
         for h in plans:
             lib.nsol_pd_plan_destroy(h)
+
+
+# ------------------------------------------------------------------ 2-D LSMR: tile-fused persistent solve (two barriers per iteration)
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("shape,sigma2", [((64, 48), 1.0), ((75, 131), 2.2), ((40, 36), 0.1), ((17, 200), 3.9), ((128, 128), 1.0)])
+def test_lsmr_tile_solve_matches_other_paths(shape, sigma2, dtype):
+    """csrc/lsmr_tile2d.cuh (default for 2-D problems up to 2^18 elements) against the four-phase persistent solve it replaces
+    ("lsmr_tile" = 2) and the oracle: ADMM TV-L2 (B = grad), Tikhonov TK0 (B = identity) and TK1, iter_max 0 / 1 / 7, radius 1 ... 6
+    (sigma^2 0.1 ... 3.9), ragged tiles, images smaller than a tile."""
+    from nsol_b200 import _lib
+    ctx = _lib.context()
+    rng = np.random.RandomState(shape[1])
+    obs = rng.rand(*shape) * 200 + 10
+    xs = float(obs.max())
+    var = [sigma2, sigma2]
+    A, A_adj, D, D_adj = deconv_callables(shape, var)
+    ident = lambda x: x.flatten()
+    tol_paths = 1e-11 if dtype == "float64" else 1e-4
+
+    def solvers(iter_max):
+        yield "admm", admm.ADMMLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=D, B_adj=D_adj, x0=obs.flatten(), dimension=2, alpha=0.02,
+                                            rho=0.3, iterations=3, iter_max=iter_max, x_scale=xs, dtype=dtype)
+        yield "tk0", tk.TikhonovLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=ident, B_adj=ident, x0=obs.flatten(), alpha=0.05,
+                                             iter_max=iter_max, x_scale=xs, dtype=dtype)
+        yield "tk1", tk.TikhonovLinearSolver(A=A, A_adj=A_adj, b=obs.flatten(), B=D, B_adj=D_adj, x0=obs.flatten(), alpha=0.05,
+                                             iter_max=iter_max, x_scale=xs, dtype=dtype)
+    try:
+        for iter_max in (7, 1, 0):
+            res = {}
+            for tile in (2, 0):
+                ctx.set_tuning("lsmr_tile", tile)
+                ctx.set_tuning("lsmr_path", 4)          # the persistent solve whatever the size
+                for name, s in solvers(iter_max):
+                    s.run()
+                    res[(name, tile)] = s.get_x()
+            for name in ("admm", "tk0", "tk1"):
+                assert np.all(np.isfinite(res[(name, 0)]))
+                assert rel_max(res[(name, 0)], res[(name, 2)]) < tol_paths, (name, iter_max, rel_max(res[(name, 0)], res[(name, 2)]))
+            if iter_max == 7 and dtype == "float64":
+                Ao, Ao_adj, Do, Do_adj = orc.deconvolution_operators(shape, np.diag(var))
+                ref = orc.admm_tv(Ao, Ao_adj, Do, Do_adj, obs.reshape(-1), obs.reshape(-1), 2, alpha=0.02, rho=0.3, iterations=3,
+                                  iter_max=7, x_scale=xs)
+                assert rel_max(res[("admm", 0)], ref) < 1e-10
+    finally:
+        ctx.set_tuning("lsmr_tile", 0)
+        ctx.set_tuning("lsmr_path", 0)
+
+
+def test_lsmr_tile_solve_primal_dual_deconvolution(golden):
+    """The reference's default deconvolution solver (PD with prox_linear_least_squares) rides on the tile-fused solve in 2-D."""
+    from nsol_b200 import _lib
+    from test_gpu_parity import make_pd_deconv
+    ctx = _lib.context()
+    meta = golden.manifest["lsmr"]["pdd_2d_TV"]
+    obs = golden("lsmr", "in/" + meta["input"])
+    xs = meta["x_scale"] or float(obs.max())
+    out = {}
+    try:
+        for tile in (2, 0):
+            ctx.set_tuning("lsmr_tile", tile)
+            s = make_pd_deconv(obs, meta["var"], meta["reg"], meta["alpha"], meta["iterations"], meta["iter_max"], xs, meta["L2"])
+            s.run()
+            out[tile] = s.get_x()
+    finally:
+        ctx.set_tuning("lsmr_tile", 0)
+    assert rel_max(out[0], golden("lsmr", "pdd_2d_TV")) < 1e-10
+    assert rel_max(out[0], out[2]) < 1e-11
