@@ -452,6 +452,7 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: strong = the ONE 512^3 volume of BASELINE config 4 sharded over N GPUs (default, the "
                          "BASELINE metric); weak = 512^3 per GPU (always reported in the 'weak' sub-record)")
+    ap.add_argument("--planes", type=int, default=0, help="experiments only: z-planes of the (strong-scaling) volume instead of --size")
     ap.add_argument("--ref-size", type=int, default=256)
     ap.add_argument("--ref-budget", type=float, default=100.0, help="seconds of CPU time the reference arm may spend in total")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -514,7 +515,7 @@ def main():
 
     def measure(dtype_name, scaling, steps, want_e2e, want_parity):
         """One workload: global volume (nz_global, n, n) sharded over the ranks."""
-        nz_global = n * world if scaling == "weak" else n
+        nz_global = n * world if scaling == "weak" else (args.planes if args.planes > 0 else n)
         z_lo, z_hi = slab_bounds(nz_global, rank, world)
         nz_loc = z_hi - z_lo
         shape = (nz_loc, n, n)

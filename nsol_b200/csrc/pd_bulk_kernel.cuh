@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kern
     constexpr int S = NSOL_PD_STAGES;
     constexpr int W = L::W;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_launch_dependents();
 
     const int lane = threadIdx.x;
     const int TY = (int)blockDim.y;
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kern
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    pdl_wait();                     // nothing above read solver state: the previous iteration may still have been running
 
     // lane 0: bulk copies of everything plane zq needs into ring slot `slot`
     auto issue = [&](int zq, int slot, long long o, long long bo) {

@@ -26,6 +26,10 @@
 
 #include "common.cuh"
 
+// programmatic dependent launch (see NSOL_PD_LAUNCH): no-ops when the kernel was launched without the attribute
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <typename T>
 struct PdArgs {
     const T *xbar_in;
@@ -339,6 +343,7 @@ __device__ __forceinline__ void pd_iter_body(const PdArgs<T> &a, const unsigned 
     };
 
     // ---- prologue: plane z0 --------------------------------------------------
+    pdl_wait();                     // everything above touched only launch constants and the step-size table
     if (LINK) pd_link_begin(a, z0, z1);
     PdStep<T, VEC> cur;
     load_step(z0, off, boff, cur);
@@ -457,6 +462,7 @@ __device__ __forceinline__ void pd_iter_body(const PdArgs<T> &a, const unsigned 
 
 template <typename T, int VEC, bool HAS_Y, int REG, int DATA, bool LINK, bool UNIT>
 __global__ void __launch_bounds__(256, sizeof(T) == 4 ? NSOL_PD_MINB_F32 : (HAS_Y ? NSOL_PD_MINB_F64 : NSOL_PD_MINB_F64_2D)) pd_iter_kernel(const PdArgs<T> a) {
+    pdl_launch_dependents();
     pd_iter_body<T, VEC, HAS_Y, REG, DATA, LINK, UNIT>(a, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
@@ -993,14 +999,31 @@ extern "C" int nsol_pd_plan_link_status(nsol_pd_plan *pl, nsol_stream s) {
 // one may wait for every running kernel of the context -- which must not happen behind a kernel that spins on a neighbour's flag:
 // the pipelined solve through linked z-slabs preloads what it is going to launch, pd_preload).
 static thread_local bool g_pd_query_only = false;
-#define NSOL_PD_LAUNCH(KERNEL, GRID, BLOCK, SMEM, STREAM, ARGS)                \
-    do {                                                                       \
-        if (g_pd_query_only) {                                                 \
-            cudaFuncAttributes fa__;                                           \
-            cudaFuncGetAttributes(&fa__, KERNEL);                              \
-        } else {                                                               \
-            KERNEL<<<GRID, BLOCK, SMEM, STREAM>>>(ARGS);                       \
-        }                                                                      \
+// Programmatic dependent launch ("pd_pdl" knob: 0 on, 2 off): the iteration kernels call griddepcontrol.launch_dependents when they
+// start and griddepcontrol.wait before their first read of solver state, so the CTAs of iteration k + 1 are launched (shared memory
+// carved, mbarriers initialised) while the last wave of iteration k drains, and start the moment it has completed -- the launch gap
+// and ramp of a 0.24 ms kernel on a 64-plane z-slab are a few per cent of it.
+static thread_local bool g_pd_pdl = true;
+#define NSOL_PD_LAUNCH(KERNEL, GRID, BLOCK, SMEM, STREAM, ARGS)                                                   \
+    do {                                                                                                          \
+        if (g_pd_query_only) {                                                                                    \
+            cudaFuncAttributes fa__;                                                                              \
+            cudaFuncGetAttributes(&fa__, KERNEL);                                                                 \
+        } else if (g_pd_pdl) {                                                                                    \
+            cudaLaunchConfig_t cfg__ = {};                                                                        \
+            cfg__.gridDim = GRID;                                                                                 \
+            cfg__.blockDim = BLOCK;                                                                               \
+            cfg__.dynamicSmemBytes = SMEM;                                                                        \
+            cfg__.stream = STREAM;                                                                                \
+            cudaLaunchAttribute at__[1];                                                                          \
+            at__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                      \
+            at__[0].val.programmaticStreamSerializationAllowed = 1;                                               \
+            cfg__.attrs = at__;                                                                                   \
+            cfg__.numAttrs = 1;                                                                                   \
+            cudaLaunchKernelEx(&cfg__, KERNEL, ARGS);                                                             \
+        } else {                                                                                                  \
+            KERNEL<<<GRID, BLOCK, SMEM, STREAM>>>(ARGS);                                                          \
+        }                                                                                                         \
     } while (0)
 
 template <typename T, int VEC, bool HAS_Y>
@@ -1116,7 +1139,9 @@ static void pd_tiling(const nsol_ctx *ctx, const GridView &gv, int vecw, int *ty
     const bool has_y = gv.comp_y >= 0;
     int ty = 1;
     if (has_y) {
-        ty = ctx->pd_ty ? ctx->pd_ty : 2;
+        // thin linked z-slabs (strong scaling: 64 planes per GPU at N = 8): 4 rows per CTA -- half as many boundary CTAs paying the
+        // system-scope fence; measured on 2 x 64 planes 0.2454 vs 0.2494 ms per launch (profiles/r2_thin_slabs.md)
+        ty = ctx->pd_ty ? ctx->pd_ty : ((link && gv.nz <= 96) ? 4 : 2);
         if (ty < 1) ty = 1;
         if (ty > 8) ty = 8;
     }
@@ -1281,6 +1306,7 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, i
         }
         return NSOL_ESTATE;
     }
+    g_pd_pdl = ctx->pd_pdl != 2;
     // kernel variant: 1 = register-pipelined loads (LDG), 2 = TMA bulk-async staged tiles;
     // default: bulk for float64 3-D volumes (issue-bound with LDG), LDG otherwise
     int variant = ctx->pd_variant;
