@@ -1173,6 +1173,7 @@ static void pd_tiling(const nsol_ctx *ctx, const GridView &gv, int vecw, int *ty
 // buffers of parity it & 1; the plan's own counters do not move.
 struct PdRange {
     int c0, c1, it;
+    int zc;        // > 0: planes per z-chunk of this launch (the result does not depend on the chunking)
 };
 
 template <typename T, int VECW>
@@ -1248,6 +1249,7 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, i
     size_t smem = 0;
     int ty = 1, zc = 1;
     pd_tiling(ctx, gv, VECW, &ty, &zc, pl->link_on);
+    if (rg && rg->zc > 0) zc = std::min(rg->zc, gv.nz);
     if (has_y) {
         block = dim3(32, ty, 1);
         smem = (size_t)(2 * (ty + 2) + 2 * (ty + 1)) * 32 * VECW * sizeof(T);
@@ -1517,8 +1519,8 @@ static bool pd_host_pinned(const void *p) {
 }
 
 template <typename T>
-static int pd_launch_range(nsol_pd_plan *pl, cudaStream_t st, int c0, int c1, int it) {
-    const PdRange rg = {c0, c1, it};
+static int pd_launch_range(nsol_pd_plan *pl, cudaStream_t st, int c0, int c1, int it, int zc = 0) {
+    const PdRange rg = {c0, c1, it, zc};
     const int vecw = sizeof(T) == 4 ? 4 : 2;
     if ((pl->gv.nx % vecw) == 0) {
         if (sizeof(T) == 4) return pd_launch_iteration<float, 4>(pl, st, 0, 0, &rg);
@@ -1559,8 +1561,18 @@ static int pd_solve_pipelined(nsol_pd_plan *pl, const double *b_host, const doub
     const int vecw = sizeof(T) == 4 ? 4 : 2;
     int ty, zc;
     pd_tiling(ctx, gv, (gv.nx % vecw) == 0 ? vecw : 1, &ty, &zc, pl->link_on);
-    const int nchunks = (gv.nz + zc - 1) / zc;
-    const int gch = planes / zc > 0 ? planes / zc : 1;              // z-chunks per transfer group
+    // transfer groups: 16 planes, 8 or 4 for a thin slab so that it still has ~16 groups -- the wavefront gains one iteration of
+    // skew per group, and on a multi-GPU box whose host feeds every GPU at a fraction of its link rate the transfers are worth
+    // dozens of iterations (8 GPUs, 64-plane slabs: 8.7 ms per direction = 33 iterations).  Measured on 2 x 64 planes
+    // (profiles/r2_thin_slabs.md): 4 planes 29.0 ms per solve, 16 planes 29.8, 2 planes 30.7-35.0 (launches too short).
+    if (planes <= 0) {
+        planes = 16;
+        while (planes > 4 && gv.nz / planes < 16) planes /= 2;
+    }
+    if (depth <= 0) depth = planes < 8 ? 12 : 10;
+    const int zr = std::max(1, std::min(zc, planes));               // planes per z-chunk of the chunk-range launches
+    const int nchunks = (gv.nz + zr - 1) / zr;
+    const int gch = planes / zr > 0 ? planes / zr : 1;              // z-chunks per transfer group
     const int ng = (nchunks + gch - 1) / gch;
     const long long plane = (long long)gv.nx * gv.ny;
     const bool same = (x0_host == nullptr) || (x0_host == b_host);
@@ -1585,7 +1597,7 @@ static int pd_solve_pipelined(nsol_pd_plan *pl, const double *b_host, const doub
     // through the boundary (the boundary groups' launches wait for / publish the halo planes by iteration number).
     const bool down = pl->link_on && pl->pipe_dir < 0;
     auto spatial = [&](int c) { return down ? ng - 1 - c : c; };
-    auto g_lo = [&](int g) { return (long long)std::min(g * gch * zc, gv.nz) * plane; };     // first voxel of spatial group g
+    auto g_lo = [&](int g) { return (long long)std::min(g * gch * zr, gv.nz) * plane; };     // first voxel of spatial group g
     auto chunk_lo = [&](int g) { return std::min(g * gch, nchunks); };
     const int d_up = std::min(depth, iterations / 2), d_dn = std::min(depth, iterations - d_up);
     std::vector<int> done(ng, -1);                                   // by arrival index; -1: not yet on the device
@@ -1594,14 +1606,14 @@ static int pd_solve_pipelined(nsol_pd_plan *pl, const double *b_host, const doub
         if (done[c] < 0 || (c > 0 && done[c - 1] < done[c]) || (c + 1 < ng && done[c + 1] < done[c]))
             return nsol_fail(ctx, NSOL_ESTATE, "pd pipelined solve: wavefront order violated at group %d", c);
         const int g = spatial(c);
-        NSOL_CHECK(pd_launch_range<T>(pl, st, chunk_lo(g), chunk_lo(g + 1), done[c]));
+        NSOL_CHECK(pd_launch_range<T>(pl, st, chunk_lo(g), chunk_lo(g + 1), done[c], zr));
         done[c] += 1;
         return NSOL_OK;
     };
     // a merged launch of the arrival groups [0, top], all at iteration `it`
     auto advance_first = [&](int top, int it) -> int {
         const int ga = spatial(0), gb = spatial(top);
-        return pd_launch_range<T>(pl, st, chunk_lo(std::min(ga, gb)), chunk_lo(std::max(ga, gb) + 1), it);
+        return pd_launch_range<T>(pl, st, chunk_lo(std::min(ga, gb)), chunk_lo(std::max(ga, gb) + 1), it, zr);
     };
     NSOL_CHECK(pd_preload<T>(pl, st));
     pl->cur = 0;
@@ -1699,8 +1711,7 @@ extern "C" int nsol_pd_plan_solve_host(nsol_pd_plan *pl, const double *b_host, c
     const bool possible = gv.comp_z >= 0 && gv.batch == 1 && (pl->link_on || (!pl->halo_above && !pl->halo_below)) && ctx->pd_pipe != 2;
     if (possible && (ctx->pd_pipe == 1 || ((size_t)gv.n * sizeof(double) >= ((size_t)64 << 20) && pd_host_pinned(b_host) &&
                                            pd_host_pinned(x_host) && (!x0_host || x0_host == b_host || pd_host_pinned(x0_host))))) {
-        const int planes = ctx->pd_pipe_planes > 0 ? ctx->pd_pipe_planes : 16;
-        const int depth = ctx->pd_pipe_depth > 0 ? ctx->pd_pipe_depth : 10;
+        const int planes = ctx->pd_pipe_planes, depth = ctx->pd_pipe_depth;     // 0: chosen from the slab height
         if (gv.dtype == NSOL_F32) return pd_solve_pipelined<float>(pl, b_host, x0_host, iterations, x_host, (cudaStream_t)s, planes, depth);
         return pd_solve_pipelined<double>(pl, b_host, x0_host, iterations, x_host, (cudaStream_t)s, planes, depth);
     }

@@ -541,7 +541,7 @@ def test_pipelined_host_solve_with_the_reference_wiring_and_pinned_buffers():
     assert s._x0_is_observation(s._probe(), np.asarray(b))
     s.run()
     groups, d_up = _solve_info(s)
-    assert groups == 9 and d_up == 10       # 144 planes in groups of 16, default depth
+    assert groups == 18 and d_up == 10      # 144 planes: groups of 8 planes (a thin volume is cut into >= 16 groups), default depth
     x = s.get_x()
     try:
         ctx.set_tuning("pd_pipe", 2)
