@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kern
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    pdl_wait();                     // nothing above read solver state: the previous iteration may still have been running
+    pd_chain_begin(a, chunk);       // nothing above read solver state: the previous iteration may still be running
 
     // lane 0: bulk copies of everything plane zq needs into ring slot `slot`
     auto issue = [&](int zq, int slot, long long o, long long bo) {
@@ -309,4 +309,5 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kern
         }
     }
     if (LINK) pd_link_finish<T, VEC>(a, z0, z1, hrow_t + lcol, active);
+    pd_chain_end(a, chunk);
 }

@@ -58,6 +58,10 @@ struct PdArgs {
     int has_z;
     T wx, wy, wz;
     int it, batch;
+    // iteration chaining (see pd_chain_begin): per-chunk completion counters of the whole-volume launches
+    unsigned long long *chain_done;   // NULL: this launch does not count
+    unsigned long long chain_need;    // value the counters of chunks c-1, c, c+1 must have reached before chunk c may start
+    int chain;                        // 1: wait on the counters; 0: wait for the whole previous kernel (griddepcontrol.wait)
 };
 
 // ---- in-kernel z-slab halo exchange (peer memory over NVLink) --------------------------------
@@ -109,6 +113,47 @@ __device__ NSOL_LINK_INLINE void pd_link_signal(unsigned *count, unsigned *peer_
         st_release_sys(peer_flag, publish);
     }
 }
+// ---- iteration chaining ---------------------------------------------------------------------------------------------
+// With programmatic dependent launch the CTAs of iteration k + 1 are resident while the last wave of iteration k drains.  Chunk c of
+// iteration k + 1 reads (and overwrites the inputs of) chunks c - 1, c, c + 1 of iteration k only, so instead of waiting for the whole
+// previous kernel (griddepcontrol.wait) it waits until those three chunks have counted all their CTAs: the tail of one iteration
+// overlaps the head of the next.  All CTAs of iteration k have started before the first CTA of k + 1 is launched (that is when the
+// launch_dependents trigger fires), so a spinning CTA never keeps a CTA it waits for off the SMs.  Release: every thread fences its
+// stores, block barrier, one atomic increment; acquire: ld.acquire.gpu by one thread, block barrier (the acquire also drops the SM's
+// stale L1 lines of the buffers the previous iterations read).  A counter that does not arrive within 2 s traps instead of hanging.
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ void pd_chain_begin(const PdArgs<T> &a, int chunk) {
+    if (!a.chain) {
+        pdl_wait();
+        return;
+    }
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const int c0 = chunk > 0 ? chunk - 1 : 0, c1 = chunk + 1 < a.nchunks ? chunk + 1 : a.nchunks - 1;
+        for (int c = c0; c <= c1; ++c) {
+            if (ld_acquire_gpu_u64(a.chain_done + c) >= a.chain_need) continue;
+            const unsigned long long t0 = global_timer_ns();
+            while (ld_acquire_gpu_u64(a.chain_done + c) < a.chain_need) {
+                __nanosleep(32);
+                if (global_timer_ns() - t0 > 2000000000ull) __trap();
+            }
+        }
+    }
+    __syncthreads();
+    asm volatile("fence.proxy.async;" ::: "memory");      // the bulk copies below read what the generic proxy of other SMs wrote
+}
+template <typename T>
+__device__ __forceinline__ void pd_chain_end(const PdArgs<T> &a, int chunk) {
+    if (!a.chain_done) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) atomicAdd(a.chain_done + chunk, 1ull);
+}
+
 // halo planes are written by another GPU while this kernel may already run: bypass L1
 template <typename T, int VEC>
 __device__ __forceinline__ Vec<T, VEC> vec_load_cg(const T *p) {
@@ -343,7 +388,7 @@ __device__ __forceinline__ void pd_iter_body(const PdArgs<T> &a, const unsigned 
     };
 
     // ---- prologue: plane z0 --------------------------------------------------
-    pdl_wait();                     // everything above touched only launch constants and the step-size table
+    pd_chain_begin(a, chunk);       // everything above touched only launch constants and the step-size table
     if (LINK) pd_link_begin(a, z0, z1);
     PdStep<T, VEC> cur;
     load_step(z0, off, boff, cur);
@@ -458,6 +503,7 @@ __device__ __forceinline__ void pd_iter_body(const PdArgs<T> &a, const unsigned 
         if (z + 1 < z1) plane_step(z + 1, alt, cur);
     }
     if (LINK) pd_link_finish<T, VEC>(a, z0, z1, hrow, active);
+    pd_chain_end(a, chunk);
 }
 
 template <typename T, int VEC, bool HAS_Y, int REG, int DATA, bool LINK, bool UNIT>
@@ -539,6 +585,10 @@ struct nsol_pd_plan {
     cudaEvent_t pipe_fork = nullptr;
     std::vector<cudaEvent_t> pipe_ev_up, pipe_ev_x, pipe_ev_dn;
     int pipe_groups_last = 0, pipe_depth_last = 0;   // what the last solve did (0 groups: plain sequence)
+    unsigned long long *chain_done = nullptr;   // iteration chaining: per-chunk completion counters
+    int chain_chunks = 0, chain_zc = 0;         // geometry the counters belong to
+    unsigned long long chain_gen = 0;           // whole-volume launches counted since the counters were cleared
+    bool chain_valid = false;                   // false: something else has touched the state since (reset, chunk-range launch, ...)
     int pipe_dir = 1;                 // +1: groups travel bottom-up, -1: top-down (odd ranks of a linked z-slab decomposition)
     unsigned pipe_g0 = 0;             // link generation of the start state of the running pipelined solve
 };
@@ -636,6 +686,7 @@ extern "C" void nsol_pd_plan_destroy(nsol_pd_plan *pl) {
     }
     cudaFree(pl->stage);
     cudaFree(pl->sched);
+    cudaFree(pl->chain_done);
     for (auto *v : {&pl->pipe_ev_up, &pl->pipe_ev_x, &pl->pipe_ev_dn})
         for (cudaEvent_t e : *v) cudaEventDestroy(e);
     if (pl->pipe_fork) cudaEventDestroy(pl->pipe_fork);
@@ -721,6 +772,7 @@ extern "C" int nsol_pd_plan_update(nsol_pd_plan *pl, const nsol_pd_desc *desc) {
     pl->alpha.assign(desc->alpha, desc->alpha + gv.batch);
     pl->desc.alpha = nullptr;
     pl->sched_cap = 0;      // step-size table is rebuilt by the next iterate
+    pl->chain_valid = false;
     pl->ready = false;
     pl->it = 0;
     return pd_ensure_schedule(pl, 128);
@@ -764,6 +816,7 @@ static int pd_reset_common(nsol_pd_plan *pl, int src_dtype, const void *b_src, c
     pl->it = 0;
     pl->ready = true;
     pl->link_fresh = false;
+    pl->chain_valid = false;
     return NSOL_OK;
 }
 
@@ -1204,6 +1257,9 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, i
     a.link_error = nullptr;
     a.want = a.publish = 0;
     a.front_chunks = 0;
+    a.chain_done = nullptr;
+    a.chain_need = 0;
+    a.chain = 0;
     a.link_timeout_ns = (unsigned long long)(ctx->link_timeout_ms > 0 ? ctx->link_timeout_ms : NSOL_LINK_TIMEOUT_MS) * 1000000ull;
     if (pl->link_on) {
         if (part != 0) return nsol_fail(ctx, NSOL_ESTATE, "pd: the split iteration is not available with the in-kernel halo exchange");
@@ -1309,6 +1365,34 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, i
         return NSOL_ESTATE;
     }
     g_pd_pdl = ctx->pd_pdl != 2;
+    // iteration chaining (pd_chain_begin): whole-volume launches of one 3-D volume, back to back.  OFF unless "pd_chain" = 1: measured
+    // on B200 it LOSES (512^3 float64: 2.138 vs 1.895 ms per launch, float32 96.6 vs 92.9 ms per step; profiles/r2_thin_slabs.md) --
+    // the per-CTA release fence waits for the CTA's stores to be acknowledged by a saturated HBM write queue while the CTA holds its
+    // SM slot, which costs more than the overlapped head / tail of the launches wins.  Kept as a measured, parity-tested experiment.
+    const bool chain_ok = !rg && part == 0 && has_y && gv.batch == 1 && g_pd_pdl && ctx->pd_chain == 1 && !g_pd_query_only;
+    if (chain_ok) {
+        if (pl->chain_chunks != a.nchunks || pl->chain_zc != zc) {
+            if (pl->chain_done) {
+                NSOL_CUDA(ctx, cudaStreamSynchronize(s));
+                NSOL_CUDA(ctx, cudaFree(pl->chain_done));
+                pl->chain_done = nullptr;
+            }
+            NSOL_CUDA(ctx, cudaMalloc((void **)&pl->chain_done, sizeof(unsigned long long) * (size_t)a.nchunks));
+            pl->chain_chunks = a.nchunks;
+            pl->chain_zc = zc;
+            pl->chain_valid = false;
+        }
+        if (!pl->chain_valid) {
+            NSOL_CUDA(ctx, cudaMemsetAsync(pl->chain_done, 0, sizeof(unsigned long long) * (size_t)a.nchunks, s));
+            pl->chain_gen = 0;
+            pl->chain_valid = true;
+        }
+        a.chain_done = pl->chain_done;
+        a.chain = pl->chain_gen > 0 ? 1 : 0;        // the first launch of a chain waits for whatever came before it
+        a.chain_need = pl->chain_gen * (unsigned long long)(grid.x * grid.y);
+    } else if (!g_pd_query_only) {
+        pl->chain_valid = false;
+    }
     // kernel variant: 1 = register-pipelined loads (LDG), 2 = TMA bulk-async staged tiles;
     // default: bulk for float64 3-D volumes (issue-bound with LDG), LDG otherwise
     int variant = ctx->pd_variant;
@@ -1323,6 +1407,7 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, i
     }
     if (g_pd_query_only) return NSOL_OK;
     NSOL_LAUNCH_CHECK(ctx);
+    if (chain_ok) pl->chain_gen += 1;
     if (part != 1 && !rg) {
         pl->cur = nxt;
         pl->it += 1;
@@ -1384,6 +1469,7 @@ static int pd_iterate_tb2d(nsol_pd_plan *pl, int n, cudaStream_t st) {
         a.x_out = (T *)pl->x_alt;
         a.it = pl->it;
         a.ksub = k;
+        pl->chain_valid = false;
         NSOL_CHECK(pd_tb2d_launch<T>(ctx, pl->desc.reg, pl->desc.data, nr, a, grid, st));
         NSOL_LAUNCH_CHECK(ctx);
         std::swap(pl->x, pl->x_alt);
