@@ -483,6 +483,8 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
     ctx = _lib.context(local_rank)
     n = args.size
+    if os.environ.get("NSOL_BENCH_OWN_STREAM", "0") == "1":      # experiments: a created stream instead of the legacy default stream
+        torch.cuda.set_stream(torch.cuda.Stream())
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     lib = ctx.lib
 

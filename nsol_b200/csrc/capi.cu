@@ -48,6 +48,7 @@ extern "C" int nsol_create(int device, nsol_ctx **out) {
     if (const char *v = getenv("NSOL_PD_TB_NR")) ctx->pd_tb_nr = atoi(v);
     if (const char *v = getenv("NSOL_PD_PDL")) ctx->pd_pdl = atoi(v);
     if (const char *v = getenv("NSOL_PD_CHAIN")) ctx->pd_chain = atoi(v);
+    if (const char *v = getenv("NSOL_PD_PUSH")) ctx->pd_push = atoi(v);
     if (const char *v = getenv("NSOL_PD_PIPE")) ctx->pd_pipe = atoi(v);
     if (const char *v = getenv("NSOL_PD_PIPE_DEPTH")) ctx->pd_pipe_depth = atoi(v);
     if (const char *v = getenv("NSOL_PD_PIPE_PLANES")) ctx->pd_pipe_planes = atoi(v);
@@ -81,6 +82,7 @@ extern "C" int nsol_set_tuning(nsol_ctx *ctx, const char *key, int value) {
     else if (!strcmp(key, "pd_tb_nr")) ctx->pd_tb_nr = value;
     else if (!strcmp(key, "pd_pdl")) ctx->pd_pdl = value;
     else if (!strcmp(key, "pd_chain")) ctx->pd_chain = value;
+    else if (!strcmp(key, "pd_push")) ctx->pd_push = value;
     else if (!strcmp(key, "pd_pipe")) ctx->pd_pipe = value;
     else if (!strcmp(key, "pd_pipe_depth")) ctx->pd_pipe_depth = value;
     else if (!strcmp(key, "pd_pipe_planes")) ctx->pd_pipe_planes = value;

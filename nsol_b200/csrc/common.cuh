@@ -29,6 +29,7 @@ struct nsol_ctx {
     // pd_tb_k iterations per pass (0 = 4); pd_tb_nr rows per thread = region height 16 / 32 / 32 for 1 / 2 / 4 (0 = chosen from the
     // problem size)
     int pd_tb = 0, pd_tb_k = 0, pd_tb_nr = 0;
+    int pd_push = 0;        // linked z-slabs: 1 = boundary planes pushed by a publish kernel on a second stream (experiment), else by the boundary CTAs
     int pd_chain = 0;       // iteration chaining (per-chunk dependencies between consecutive whole-volume launches): 1 on (experiment; slower), else off
     int pd_pdl = 0;         // programmatic dependent launch of the primal-dual iteration kernels: 0 on, 2 off
     int lsmr_blocks = 0;

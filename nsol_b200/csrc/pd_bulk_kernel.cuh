@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pd_iter_bulk_kern
     const int x0 = x0t + lane * VEC;
     const int y = (int)blockIdx.y * TY + ty;
     int chunk = a.chunk_first + (int)(blockIdx.z % (unsigned)a.nsel) * a.chunk_stride;
-    if (LINK && a.front_chunks) chunk = chunk == 0 ? 0 : (chunk == 1 ? a.nchunks - 1 : chunk - 1);
+    if (LINK && a.front_chunks == 1) chunk = chunk == 0 ? 0 : (chunk == 1 ? a.nchunks - 1 : chunk - 1);
+    if (LINK && a.front_chunks == 2) chunk = chunk + 2 < a.nchunks ? chunk + 1 : (chunk + 2 == a.nchunks ? 0 : a.nchunks - 1);
     const int bz = (int)(blockIdx.z / (unsigned)a.nsel);
     const int z0 = chunk * a.zc;
     const int z1 = min(a.nz, z0 + a.zc);

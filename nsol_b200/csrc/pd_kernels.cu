@@ -50,7 +50,7 @@ struct PdArgs {
     int *link_error;                           // set when a wait timed out
     unsigned long long link_timeout_ns;
     unsigned want, publish;                    // flag value this iteration needs / stores when its boundary is done
-    int front_chunks;                          // 1: schedule the two boundary chunks first (link mode)
+    int front_chunks;                          // link mode: 1 = the two boundary chunks first (they push from inside the kernel), 2 = last
     long long n;                      // voxels per problem
     long long b_stride;               // 0 (shared observation) or n
     int nx, ny, nz, zc, nchunks;
@@ -99,6 +99,11 @@ __device__ NSOL_LINK_INLINE void pd_link_wait(const unsigned *flag, unsigned wan
     while ((int)(ld_acquire_sys(flag) - want) < 0) {
         __nanosleep(64);
         if (global_timer_ns() - t0 > timeout_ns) {
+            if (*(volatile int *)error == 0) {     // diagnostics: the generation that did not arrive, publish kernels started / finished by then
+                ((volatile unsigned *)error)[1] = want;
+                ((volatile unsigned *)error)[4] = ((volatile unsigned *)error)[2];
+                ((volatile unsigned *)error)[5] = ((volatile unsigned *)error)[3];
+            }
             *(volatile int *)error = 1;
             return;
         }
@@ -324,7 +329,8 @@ __device__ __forceinline__ void pd_iter_body(const PdArgs<T> &a, const unsigned 
     const int y0 = HAS_Y ? (int)by * TY : 0;
     const int y = y0 + ty;
     int chunk = a.chunk_first + (int)(bzi % (unsigned)a.nsel) * a.chunk_stride;
-    if (LINK && a.front_chunks) chunk = chunk == 0 ? 0 : (chunk == 1 ? a.nchunks - 1 : chunk - 1);
+    if (LINK && a.front_chunks == 1) chunk = chunk == 0 ? 0 : (chunk == 1 ? a.nchunks - 1 : chunk - 1);
+    if (LINK && a.front_chunks == 2) chunk = chunk + 2 < a.nchunks ? chunk + 1 : (chunk + 2 == a.nchunks ? 0 : a.nchunks - 1);
     const int bz = (int)(bzi / (unsigned)a.nsel);
     const int z0 = chunk * a.zc;
     const int z1 = min(a.nz, z0 + a.zc);
@@ -585,6 +591,11 @@ struct nsol_pd_plan {
     cudaEvent_t pipe_fork = nullptr;
     std::vector<cudaEvent_t> pipe_ev_up, pipe_ev_x, pipe_ev_dn;
     int pipe_groups_last = 0, pipe_depth_last = 0;   // what the last solve did (0 groups: plain sequence)
+    // link mode, whole-slab iterations: the boundary planes are pushed to the neighbours by a small publish kernel on a second
+    // stream after each iteration kernel instead of by the boundary CTAs themselves (pd_launch_iteration)
+    cudaStream_t push_stream = nullptr;
+    cudaEvent_t push_ev_iter[8] = {nullptr}, push_ev_done[8] = {nullptr};   // rings: an event is never re-recorded while a wait on it may be pending
+    unsigned long long push_count = 0;          // publish kernels queued on push_stream so far
     unsigned long long *chain_done = nullptr;   // iteration chaining: per-chunk completion counters
     int chain_chunks = 0, chain_zc = 0;         // geometry the counters belong to
     unsigned long long chain_gen = 0;           // whole-volume launches counted since the counters were cleared
@@ -593,8 +604,11 @@ struct nsol_pd_plan {
     unsigned pipe_g0 = 0;             // link generation of the start state of the running pipelined solve
 };
 
+static int pd_push_join(nsol_pd_plan *pl, cudaStream_t s);
+static int pd_push_setup(nsol_pd_plan *pl);
+
 // layout of a link block (all offsets 256-byte aligned)
-enum { LINK_FLAG_BELOW = 0, LINK_FLAG_ABOVE = 64, LINK_COUNT_BELOW = 128, LINK_COUNT_ABOVE = 192, LINK_ERROR = 224,
+enum { LINK_FLAG_BELOW = 0, LINK_FLAG_ABOVE = 64, LINK_COUNT_BELOW = 128, LINK_COUNT_ABOVE = 192, LINK_ERROR = 224 /* + 5 diagnostic words */, LINK_COUNT_PUB = 252,
        LINK_HEADER = 256 };
 // receive slots after the header: [parity][0 = xbar_above, 1 = xbar_below, 2 = pz_below]
 static inline size_t link_slot(const nsol_pd_plan *pl, int parity, int which) {
@@ -683,6 +697,14 @@ extern "C" void nsol_pd_plan_destroy(nsol_pd_plan *pl) {
     for (int i = 0; i < 2; ++i) {
         nsol_plan_free(pl->ctx, pl->xbar[i]);
         for (int k = 0; k < 3; ++k) nsol_plan_free(pl->ctx, pl->p[i][k]);
+    }
+    if (pl->push_stream) {
+        cudaStreamSynchronize(pl->push_stream);
+        cudaStreamDestroy(pl->push_stream);
+        for (int i = 0; i < 8; ++i) {
+            cudaEventDestroy(pl->push_ev_iter[i]);
+            cudaEventDestroy(pl->push_ev_done[i]);
+        }
     }
     cudaFree(pl->stage);
     cudaFree(pl->sched);
@@ -798,6 +820,7 @@ static int pd_ensure_stage(nsol_pd_plan *pl, size_t bytes) {
 // x = xbar = x0 / x0_scale, b' = b / b_scale (nsol/solver.py:35-41, proximal_operators.py:97,119), p = 0
 static int pd_reset_common(nsol_pd_plan *pl, int src_dtype, const void *b_src, const void *x0_src, cudaStream_t s) {
     nsol_ctx *ctx = pl->ctx;
+    NSOL_CHECK(pd_push_join(pl, s));            // a queued publish kernel may still read the state this reset overwrites
     const GridView &gv = pl->gv;
     const long long nb = gv.n * (pl->desc.b_batched ? gv.batch : 1);
     const long long nv = gv.n * gv.batch;
@@ -900,6 +923,7 @@ struct LinkPublishArgs {
 };
 
 __global__ void __launch_bounds__(256) pd_link_publish_kernel(const LinkPublishArgs a) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned *)a.error + 2, 1u);      // diagnostics: publish kernels started
     if (a.flag_below) pd_link_wait(a.flag_below, a.want, a.error, a.timeout_ns);
     if (a.flag_above) pd_link_wait(a.flag_above, a.want, a.error, a.timeout_ns);
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -919,19 +943,55 @@ __global__ void __launch_bounds__(256) pd_link_publish_kernel(const LinkPublishA
             __threadfence_system();
             if (a.peer_flag_below) st_release_sys(a.peer_flag_below, a.publish);
             if (a.peer_flag_above) st_release_sys(a.peer_flag_above, a.publish);
+            atomicAdd((unsigned *)a.error + 3, 1u);                                        // diagnostics: ... finished
         }
     }
 }
 
-// sides: 1 = towards the lower neighbour, 2 = towards the upper one, 3 = both (and the plan's generation counter advances);
-// a one-sided call (pipelined solve: a boundary group has just been reset) publishes generation pl->link_pub without advancing it
-static int pd_link_publish(nsol_pd_plan *pl, cudaStream_t s, int sides = 3) {
+// everything queued on the plan's push stream happens before whatever is queued on s next
+static int pd_push_join(nsol_pd_plan *pl, cudaStream_t s) {
+    if (pl->push_stream && pl->push_count > 0)
+        NSOL_CUDA(pl->ctx, cudaStreamWaitEvent(s, pl->push_ev_done[(pl->push_count - 1) & 7], 0));
+    return NSOL_OK;
+}
+
+// The second stream of a linked plan and its events.  Called when the link is established -- while nothing spins on the device: the
+// first launch into a fresh stream makes the driver set the stream up, and that has been seen to wait for the running kernel of the
+// other stream (whose boundary CTAs were spinning for the neighbour's first publish: a time-out at generation 2 on 2 GPUs).  So the
+// stream is created AND used once here.  The publish kernel also asks for the iteration kernel's shared-memory carve-out so that it
+// can run beside it.
+static int pd_push_setup(nsol_pd_plan *pl) {
+    if (pl->push_stream) return NSOL_OK;
+    nsol_ctx *ctx = pl->ctx;
+    NSOL_CUDA(ctx, cudaFuncSetAttribute(pd_link_publish_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    NSOL_CUDA(ctx, cudaStreamCreateWithFlags(&pl->push_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) {
+        NSOL_CUDA(ctx, cudaEventCreateWithFlags(&pl->push_ev_iter[i], cudaEventDisableTiming));
+        NSOL_CUDA(ctx, cudaEventCreateWithFlags(&pl->push_ev_done[i], cudaEventDisableTiming));
+    }
+    LinkPublishArgs a = {};
+    a.count = (unsigned *)(pl->link_block + LINK_COUNT_PUB);
+    a.error = (int *)(pl->link_block + LINK_ERROR);
+    pd_link_publish_kernel<<<32, 256, 0, pl->push_stream>>>(a);      // nothing to wait for, nothing to copy, no flag to raise
+    for (int i = 0; i < 8; ++i) {
+        NSOL_CUDA(ctx, cudaEventRecord(pl->push_ev_iter[i], pl->push_stream));
+        NSOL_CUDA(ctx, cudaEventRecord(pl->push_ev_done[i], pl->push_stream));
+    }
+    NSOL_CUDA(ctx, cudaStreamSynchronize(pl->push_stream));
+    return NSOL_OK;
+}
+
+// sides: 1 = towards the lower neighbour, 2 = towards the upper one, 3 = both (and the plan's generation counter advances unless
+// advance is false); a one-sided call (pipelined solve: a boundary group has just been reset) publishes generation pl->link_pub
+// without advancing it
+static int pd_link_publish(nsol_pd_plan *pl, cudaStream_t s, int sides = 3, bool advance = true) {
     nsol_ctx *ctx = pl->ctx;
     const GridView &gv = pl->gv;
     const size_t plane = (size_t)gv.nx * gv.ny * pl->esz;
     const unsigned g = pl->link_pub;
     const bool below = pl->peer_below && (sides & 1), above = pl->peer_above && (sides & 2);
     if (!below && !above && sides != 3) return NSOL_OK;
+    if (s != pl->push_stream) NSOL_CHECK(pd_push_join(pl, s));       // flags and slots are written in generation order
     const int wr = (int)(g & 1u);
     const char *xb = (const char *)pl->xbar[pl->cur];
     LinkPublishArgs a;
@@ -945,7 +1005,7 @@ static int pd_link_publish(nsol_pd_plan *pl, cudaStream_t s, int sides = 3) {
     a.flag_above = above ? (const unsigned *)(pl->link_block + LINK_FLAG_ABOVE) : nullptr;
     a.peer_flag_below = below ? (unsigned *)(pl->peer_below + LINK_FLAG_ABOVE) : nullptr;
     a.peer_flag_above = above ? (unsigned *)(pl->peer_above + LINK_FLAG_BELOW) : nullptr;
-    a.count = (unsigned *)(pl->link_block + LINK_COUNT_BELOW);
+    a.count = (unsigned *)(pl->link_block + LINK_COUNT_PUB);     // its own counter: a publish may run beside an iteration kernel
     a.error = (int *)(pl->link_block + LINK_ERROR);
     a.plane_vec = plane / 16;
     a.timeout_ns = (unsigned long long)(ctx->link_timeout_ms > 0 ? ctx->link_timeout_ms : NSOL_LINK_TIMEOUT_MS) * 1000000ull;
@@ -953,7 +1013,7 @@ static int pd_link_publish(nsol_pd_plan *pl, cudaStream_t s, int sides = 3) {
     a.publish = g + 1u;
     pd_link_publish_kernel<<<32, 256, 0, s>>>(a);
     NSOL_LAUNCH_CHECK(ctx);
-    if (sides == 3) {
+    if (sides == 3 && advance) {
         pl->link_pub = g + 1u;
         pl->link_fresh = true;
     }
@@ -1004,6 +1064,7 @@ static int pd_link_set_peers(nsol_pd_plan *pl, char *below, bool below_ipc, char
     pl->link_on = (below != nullptr) || (above != nullptr);
     pl->link_fresh = false;
     pl->link_pub = 0;
+    if (pl->link_on && ctx->pd_push == 1) NSOL_CHECK(pd_push_setup(pl));
     return NSOL_OK;
 }
 
@@ -1041,10 +1102,18 @@ extern "C" int nsol_pd_plan_link_status(nsol_pd_plan *pl, nsol_stream s) {
     nsol_ctx *ctx = pl->ctx;
     if (!pl->link_block) return NSOL_OK;
     NSOL_CHECK(nsol_bind_device(ctx));
+    NSOL_CHECK(pd_push_join(pl, (cudaStream_t)s));
     int err = 0;
     NSOL_CUDA(ctx, cudaMemcpyAsync(&err, pl->link_block + LINK_ERROR, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)s));
     NSOL_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)s));
-    if (err) return nsol_fail(ctx, NSOL_ENCCL, "pd link: a wait for a neighbour's halo timed out (neighbour not iterating in lockstep?)");
+    if (err) {
+        unsigned hdr[64] = {0};
+        cudaMemcpy(hdr, pl->link_block, sizeof(hdr), cudaMemcpyDeviceToHost);
+        return nsol_fail(ctx, NSOL_ENCCL, "pd link: a wait for a neighbour's halo timed out (neighbour not iterating in lockstep?) "
+                         "[first missing generation %u (own publish kernels started %u, finished %u at that moment; now %u, %u); now: flag_below %u flag_above %u count_below %u count_above %u count_pub %u; generation %u, %llu publish kernels]",
+                         hdr[LINK_ERROR / 4 + 1], hdr[LINK_ERROR / 4 + 4], hdr[LINK_ERROR / 4 + 5], hdr[LINK_ERROR / 4 + 2], hdr[LINK_ERROR / 4 + 3], hdr[LINK_FLAG_BELOW / 4], hdr[LINK_FLAG_ABOVE / 4], hdr[LINK_COUNT_BELOW / 4], hdr[LINK_COUNT_ABOVE / 4],
+                         hdr[LINK_COUNT_PUB / 4], pl->link_pub, pl->push_count);
+    }
     return NSOL_OK;
 }
 
@@ -1349,6 +1418,26 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, i
         }
     }
     a.front_chunks = (pl->link_on && a.nchunks >= 3 && !rg) ? 1 : 0;
+    // Link mode, whole-slab iteration: the boundary CTAs do not push their planes to the neighbours (peer stores + a system-scope
+    // fence per CTA, while the CTA holds its SM slot -- a quarter of all CTAs on a 64-plane slab); a publish kernel on the plan's
+    // second stream copies the three boundary planes and raises the flags once the iteration kernel has completed.  The boundary
+    // chunks are scheduled LAST, so the neighbours' planes of the previous iteration -- published ~20 us after that iteration
+    // ended -- have long arrived when they are needed ("pd_push" knob: 2 = push from inside the kernel as before).
+    // EXPERIMENT, off unless "pd_push" = 1: on 2 real GPUs it still runs into halo-wait time-outs (first a race on a re-recorded
+    // event -- fixed by the event rings --, then one at the first solve after a device-wide synchronisation; not understood), so the
+    // boundary CTAs keep pushing from inside the kernel by default.  Single-GPU emulation and the small 2-GPU API check pass.
+    const bool ext_push = pl->link_on && !rg && part == 0 && ctx->pd_push == 1 && !g_pd_query_only;
+    if (ext_push) {
+        a.push_below_xbar = a.push_above_xbar = a.push_above_pz = nullptr;
+        a.peer_flag_below = a.peer_flag_above = nullptr;
+        a.count_below = a.count_above = nullptr;
+        a.front_chunks = a.nchunks >= 3 ? 2 : 0;
+        NSOL_CHECK(pd_push_setup(pl));
+        // this launch overwrites the buffers the publish kernel of two iterations ago read
+        if (pl->push_count >= 2) NSOL_CUDA(ctx, cudaStreamWaitEvent(s, pl->push_ev_done[(pl->push_count - 2) & 7], 0));
+    } else if (pl->link_on && !g_pd_query_only) {
+        NSOL_CHECK(pd_push_join(pl, s));        // in-kernel pushes of this launch come after every queued publish kernel
+    }
     const long long gz = (long long)a.nsel * gv.batch;
     if (gz > 65535) return nsol_fail(ctx, NSOL_EINVAL, "pd: nchunks*batch = %lld exceeds the grid limit; raise pd_zc", gz);
     grid.z = (unsigned)gz;
@@ -1364,7 +1453,11 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, i
         }
         return NSOL_ESTATE;
     }
-    g_pd_pdl = ctx->pd_pdl != 2;
+    // No programmatic dependent launch together with the publish kernel: CTAs of iteration k + 1 launched early sit on the SMs
+    // (blocked in griddepcontrol.wait) while the boundary CTAs of iteration k spin for the neighbour's planes -- and the publish
+    // kernel of iteration k - 1 on the second stream, which the neighbour is waiting for in turn, finds no free SM (observed as a
+    // halo-wait time-out on 2 GPUs).
+    g_pd_pdl = ctx->pd_pdl != 2 && !ext_push;
     // iteration chaining (pd_chain_begin): whole-volume launches of one 3-D volume, back to back.  OFF unless "pd_chain" = 1: measured
     // on B200 it LOSES (512^3 float64: 2.138 vs 1.895 ms per launch, float32 96.6 vs 92.9 ms per step; profiles/r2_thin_slabs.md) --
     // the per-CTA release fence waits for the CTA's stores to be acknowledged by a saturated HBM write queue while the CTA holds its
@@ -1411,6 +1504,14 @@ static int pd_launch_iteration(nsol_pd_plan *pl, cudaStream_t s, int part = 0, i
     if (part != 1 && !rg) {
         pl->cur = nxt;
         pl->it += 1;
+        if (ext_push) {
+            // publish the state this launch produces (generation link_pub, slot link_pub & 1 -- what the boundary CTAs would have done)
+            NSOL_CUDA(ctx, cudaEventRecord(pl->push_ev_iter[pl->push_count & 7], s));
+            NSOL_CUDA(ctx, cudaStreamWaitEvent(pl->push_stream, pl->push_ev_iter[pl->push_count & 7], 0));
+            NSOL_CHECK(pd_link_publish(pl, pl->push_stream, 3, false));
+            NSOL_CUDA(ctx, cudaEventRecord(pl->push_ev_done[pl->push_count & 7], pl->push_stream));
+            pl->push_count += 1;
+        }
         if (pl->link_on) pl->link_pub += 1;
     }
     return NSOL_OK;
@@ -1702,6 +1803,7 @@ static int pd_solve_pipelined(nsol_pd_plan *pl, const double *b_host, const doub
         return pd_launch_range<T>(pl, st, chunk_lo(std::min(ga, gb)), chunk_lo(std::max(ga, gb) + 1), it, zr);
     };
     NSOL_CHECK(pd_preload<T>(pl, st));
+    NSOL_CHECK(pd_push_join(pl, st));           // a queued publish kernel may still read the state this solve overwrites
     pl->cur = 0;
     pl->it = 0;
     pl->pipe_g0 = pl->link_pub;          // generation of this solve's start state
