@@ -78,6 +78,46 @@ class HaloExchanger(object):
         self.finish_exchange(self.start_exchange(xbar_first, xbar_last, pz_last))
 
 
+def pipelined_schedule(groups, iterations, depth):
+    """The order in which ``nsol_pd_plan_solve_host`` (csrc/pd_kernels.cu, pd_solve_pipelined) queues its work for a slab cut
+    into ``groups`` transfer groups, as a list of steps -- a host-side mirror of the C++ loop, used by the CPU tests to check
+    the wavefront order and the halo exchange by iteration number without a GPU.  Groups are numbered in ARRIVAL order
+    (spatial group ``c`` when the transfers run bottom-up, ``groups - 1 - c`` top-down).  Steps:
+
+    * ``("reset", c)``: group c has landed, its start state exists (a boundary group publishes it to its neighbour);
+    * ``("advance", c0, c1, it)``: iteration ``it`` (0-based) on the arrival groups c0 ... c1, one launch;
+    * ``("full", it)``: iteration ``it`` on the whole slab;
+    * ``("download", c)``: group c holds the final state and goes back to the host.
+    """
+    d_up = min(depth, iterations // 2)
+    d_dn = min(depth, iterations - d_up)
+    done = [-1] * groups
+    steps = []
+    for j in range(groups + d_up):
+        if j < groups:
+            steps.append(("reset", j))
+            done[j] = 0
+        for c in range(min(j - 1, groups - 1), max(0, j - d_up) - 1, -1):
+            steps.append(("advance", c, c, done[c]))
+            done[c] += 1
+    for it in range(d_up, iterations - d_dn):
+        steps.append(("full", it))
+    done = [iterations - d_dn] * groups
+    for t in range(1, d_dn + 1):
+        top = min(d_dn - t, groups - 1)
+        steps.append(("advance", 0, top, iterations - d_dn + t - 1))
+        for c in range(top + 1):
+            done[c] += 1
+    for j in range(groups):
+        for c in range(min(j + d_dn - 1, groups - 1), j - 1, -1):
+            if done[c] < iterations and (c + 1 >= groups or done[c + 1] >= done[c]):
+                steps.append(("advance", c, c, done[c]))
+                done[c] += 1
+        assert done[j] == iterations
+        steps.append(("download", j))
+    return steps
+
+
 class _DevicePtr(object):
     """Expose a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
 

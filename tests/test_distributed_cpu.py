@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import nsol_oracle as orc
-from nsol_b200.distributed import HaloExchanger, exchange_slab_halos, partition_round_robin, slab_bounds
+from nsol_b200.distributed import HaloExchanger, exchange_slab_halos, partition_round_robin, pipelined_schedule, slab_bounds
 
 
 def test_slab_bounds_and_partition():
@@ -292,3 +292,134 @@ def test_admm_zslab_with_gloo_matches_unsharded_oracle(tmp_path, world, shape):
     ref = orc.admm_tv(A, A_adj, D, D_adj, vol.reshape(-1), vol.reshape(-1), len(shape), x_scale=220.0, **params)
     got = np.load(out)
     assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------
+# pipelined host solve through linked z-slabs: wavefront order + halo exchange by iteration number
+# ---------------------------------------------------------------------------------------------
+def _pipelined_worker(rank, world, port, shape, iterations, planes, depth, out):
+    """Every rank executes the step list of nsol_pd_plan_solve_host (pipelined_schedule) on numpy arrays laid out like the
+    plan -- two parity copies of xbar and p, x in place -- so a step that ran before its inputs were at the right iteration
+    (a wavefront-order violation) reads the wrong state and the result differs from the unsharded oracle.  Odd ranks move
+    their groups top-down.  Boundary planes travel as tagged messages (tag = iteration number of the state)."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.RandomState(7)
+    vol = rng.rand(*shape) * 255
+    xs = float(vol.max())
+    z_lo, z_hi = slab_bounds(shape[0], rank, world)
+    nzl = z_hi - z_lo
+    b = vol[z_lo:z_hi] / xs
+    x = np.full_like(b, np.nan)                              # nothing is valid before its group has "landed"
+    xbar = [np.full_like(b, np.nan), np.full_like(b, np.nan)]
+    p = [[np.full_like(b, np.nan) for _ in range(3)] for _ in range(2)]
+    sched = orc.pd_schedule("ALG2", 8.0, 0.05, iterations)
+    ng = (nzl + planes - 1) // planes
+    down = world > 1 and rank % 2 == 1
+    spatial = lambda c: ng - 1 - c if down else c
+    lo_of = lambda g: min(g * planes, nzl)
+    has_below, has_above = rank > 0, rank < world - 1
+    pending = []
+
+    def send(plane, dst, kind, state):                       # kind 0: my first xbar plane, 1: my last xbar plane, 2: my last p_z plane
+        pending.append(dist.isend(torch.from_numpy(np.ascontiguousarray(plane)), dst, tag=state * 4 + kind))
+
+    def recv(src, kind, state):
+        t = torch.empty(shape[1:], dtype=torch.float64)
+        dist.recv(t, src, tag=state * 4 + kind)
+        return t.numpy()
+
+    def publish(plo, phi, state, par):
+        if state == iterations:
+            return                                           # nobody consumes the final state (on the GPU it just lands in the slots)
+        if plo == 0 and has_below:
+            send(xbar[par][0], rank - 1, 0, state)
+        if phi == nzl and has_above:
+            send(xbar[par][-1], rank + 1, 1, state)
+            send(p[par][2][-1], rank + 1, 2, state)
+
+    def advance(plo, phi, it):
+        rd, wr = it & 1, (it + 1) & 1
+        if phi < nzl:
+            above = xbar[rd][phi]
+        else:
+            above = recv(rank + 1, 0, it) if has_above else None
+        if plo > 0:
+            below, pzb = xbar[rd][plo - 1], p[rd][2][plo - 1]
+        elif has_below:
+            below, pzb = recv(rank - 1, 1, it), recv(rank - 1, 2, it)
+        else:
+            below = pzb = None
+        xn, xbn, pn = slab_iteration(x[plo:phi], xbar[rd][plo:phi], [q[plo:phi] for q in p[rd]], b[plo:phi], sched[it],
+                                     above, below, pzb)
+        assert np.all(np.isfinite(xn)), ("read a plane that was not valid yet", rank, plo, phi, it)
+        x[plo:phi] = xn
+        xbar[wr][plo:phi] = xbn
+        for k in range(3):
+            p[wr][k][plo:phi] = pn[k]
+        publish(plo, phi, it + 1, wr)
+
+    result = np.full_like(b, np.nan)
+    for step in pipelined_schedule(ng, iterations, depth):
+        if step[0] == "reset":
+            g = spatial(step[1])
+            plo, phi = lo_of(g), lo_of(g + 1)
+            x[plo:phi] = b[plo:phi]
+            xbar[0][plo:phi] = b[plo:phi]
+            for k in range(3):
+                p[0][k][plo:phi] = 0.0
+            publish(plo, phi, 0, 0)
+        elif step[0] == "advance":
+            ga, gb = spatial(step[1]), spatial(step[2])
+            advance(lo_of(min(ga, gb)), lo_of(max(ga, gb) + 1), step[3])
+        elif step[0] == "full":
+            advance(0, nzl, step[1])
+        else:
+            g = spatial(step[1])
+            result[lo_of(g):lo_of(g + 1)] = x[lo_of(g):lo_of(g + 1)] * xs
+    for r in pending:
+        r.wait()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (z_lo, result))
+    if rank == 0:
+        np.save(out, np.concatenate([g[1] for g in sorted(gathered, key=lambda t: t[0])]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape,iterations,planes,depth", [
+    (1, (13, 4, 5), 9, 2, 3),          # one rank: the plain wavefront (upload / download overlap of nsol_pd_plan_solve_host)
+    (2, (23, 4, 5), 9, 2, 3),          # two slabs, opposite directions, ragged last groups
+    (3, (25, 4, 5), 8, 3, 10),         # three slabs, depth clipped by the iteration count
+    (2, (9, 4, 5), 5, 16, 4),          # one group per slab: both boundaries in every launch
+])
+def test_pipelined_wavefront_through_linked_slabs(tmp_path, world, shape, iterations, planes, depth):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "piped.npy")
+    mp.spawn(_pipelined_worker, args=(world, _free_port(), shape, iterations, planes, depth, out), nprocs=world, join=True)
+    rng = np.random.RandomState(7)
+    vol = rng.rand(*shape) * 255
+    ref = orc.primal_dual_denoise(vol.reshape(-1), shape, reg="TV", data="L2", alpha=0.05, L2=8.0,
+                                  iterations=iterations, x_scale=float(vol.max()))
+    assert np.array_equal(np.load(out).reshape(-1), ref)
+
+
+def test_pipelined_schedule_counts():
+    """Every group is reset once, advanced `iterations` times in total (alone, merged or as part of a whole-slab step) and
+    downloaded once, in arrival order."""
+    for groups, iterations, depth in ((1, 0, 10), (1, 7, 10), (5, 1, 10), (9, 24, 10), (32, 100, 10), (4, 9, 2)):
+        steps = pipelined_schedule(groups, iterations, depth)
+        count = [0] * groups
+        for st in steps:
+            if st[0] == "advance":
+                for c in range(st[1], st[2] + 1):
+                    assert count[c] == st[3], (groups, iterations, depth, st)
+                    count[c] += 1
+            elif st[0] == "full":
+                assert all(c == st[1] for c in count)
+                count = [c + 1 for c in count]
+        assert count == [iterations] * groups
+        assert [st[1] for st in steps if st[0] == "reset"] == list(range(groups))
+        assert [st[1] for st in steps if st[0] == "download"] == list(range(groups))
