@@ -284,9 +284,11 @@ __device__ __forceinline__ void pd_link_finish(const PdArgs<T> &a, int z0, int z
             vec_store<T, VEC>(a.push_above_pz + hoff, vec_load<T, VEC>(a.pz_out + o));
         }
     }
-    __threadfence_system();
+    // one system-scope fence per CTA, by the thread that signals, after the block barrier (the pattern of a cooperative-groups grid
+    // barrier: the fence is cumulative over the writes the barrier orders before it) -- not one per thread
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) {
+        __threadfence_system();
         const unsigned ctas = gridDim.x * gridDim.y;
         if (bot) pd_link_signal(a.count_below, a.peer_flag_below, ctas, a.publish);
         if (top) pd_link_signal(a.count_above, a.peer_flag_above, ctas, a.publish);
