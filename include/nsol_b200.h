@@ -83,7 +83,7 @@ int nsol_create(int device, nsol_ctx **out);
 void nsol_destroy(nsol_ctx *ctx);
 /* ctx may be NULL: returns the calling thread's last creation error. */
 const char *nsol_last_error(const nsol_ctx *ctx);
-/* tuning knobs ("pd_zc", "pd_ty", "pd_variant", "pd_persist", "pd_pipe", "pd_pipe_depth", "pd_pipe_planes", "pd_tb", "pd_tb_k", "pd_tb_nr", "lsmr_blocks", "lsmr_path", "lsmr_fuse2d", "lsmr_fuse3d", "lsmr_tile", "link_timeout_ms", "debug_guard"); value <= 0 restores the default */
+/* tuning knobs ("pd_zc", "pd_ty", "pd_variant", "pd_persist", "pd_pipe", "pd_pipe_depth", "pd_pipe_planes", "pd_tb", "pd_tb_k", "pd_tb_nr", "pd_pdl", "pd_chain", "pd_push", "lsmr_blocks", "lsmr_path", "lsmr_fuse2d", "lsmr_fuse3d", "lsmr_tile", "link_timeout_ms", "debug_guard"); value <= 0 restores the default */
 int nsol_set_tuning(nsol_ctx *ctx, const char *key, int value);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t nsol_launch_count(const nsol_ctx *ctx);
