@@ -423,3 +423,30 @@ def test_pipelined_schedule_counts():
         assert count == [iterations] * groups
         assert [st[1] for st in steps if st[0] == "reset"] == list(range(groups))
         assert [st[1] for st in steps if st[0] == "download"] == list(range(groups))
+
+
+def test_pipelined_schedule_obeys_the_wavefront_rule():
+    """Iteration `it` of a group reads state `it` of its two neighbours out of the parity buffers: when it is queued, both
+    neighbours must have done at least `it` iterations (their state `it` exists) and at most `it + 1` (it has not been
+    overwritten) -- for every step of every schedule, and merged launches must cover groups at one common iteration."""
+    rng = np.random.RandomState(0)
+    cases = [(g, n, d) for g in (1, 2, 3, 7, 16, 33) for n in (0, 1, 2, 5, 24, 100) for d in (1, 2, 10, 40)]
+    cases += [tuple(int(v) for v in rng.randint(1, 60, size=3)) for _ in range(200)]
+    for groups, iterations, depth in cases:
+        done = [None] * groups                              # None: not on the device yet
+        for st in pipelined_schedule(groups, iterations, depth):
+            if st[0] == "reset":
+                assert done[st[1]] is None
+                done[st[1]] = 0
+            elif st[0] in ("advance", "full"):
+                c0, c1, it = (st[1], st[2], st[3]) if st[0] == "advance" else (0, groups - 1, st[1])
+                for c in range(c0, c1 + 1):
+                    assert done[c] == it, (groups, iterations, depth, st)
+                for nb in (c0 - 1, c1 + 1):
+                    if 0 <= nb < groups:
+                        assert done[nb] is not None and it <= done[nb] <= it + 1, (groups, iterations, depth, st, nb, done[nb])
+                for c in range(c0, c1 + 1):
+                    done[c] = it + 1
+            else:
+                assert done[st[1]] == iterations
+        assert done == [iterations] * groups
