@@ -62,5 +62,27 @@ int main() {
             int h = -1; cudaMemcpy(&h, to, 4, cudaMemcpyDeviceToHost);
             printf("pattern K1,record,[B: wait,set],K2 on %s stream, event %s timing: %.3f ms%s\n", legacy ? "legacy" : "created", timing ? "with" : "without", ms, h ? "  TIMED OUT" : "");
         }
+    // the same pattern with a LONG K1 (2 ms): stream B's wait is evaluated before the event has completed, so B's channel blocks on
+    // the semaphore; does it wake up while K2 is spinning on stream A?
+    for (int legacy = 0; legacy < 2; ++legacy) {
+        cudaMemset(flag, 0, 4); cudaMemset(to, 0, 4); cudaDeviceSynchronize();
+        cudaEvent_t ev, e0, e1;
+        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaStream_t sa = legacy ? 0 : a;
+        int *never; cudaMalloc(&never, 4); cudaMemset(never, 0, 4);
+        int *to2; cudaMalloc(&to2, 4); cudaMemset(to2, 0, 4);
+        spin<<<148, 128, 64, sa>>>(never, 148, 2000000ull, to2);          // K1: every CTA spins for 2 ms
+        cudaEventRecord(ev, sa);
+        cudaStreamWaitEvent(b, ev, 0);
+        setflag<<<32, 256, 0, b>>>(flag);                                  // the "publish"
+        cudaEventRecord(e0, sa);
+        spin<<<148 * 4, 128, 50 * 1024, sa>>>(flag, 592, 2000000000ull, to);   // K2 spins until the publish has run (or 2 s)
+        cudaEventRecord(e1, sa);
+        cudaDeviceSynchronize();
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        int h = -1; cudaMemcpy(&h, to, 4, cudaMemcpyDeviceToHost);
+        printf("long K1 (2 ms), record, [B: wait, set], K2 on %s stream: K2 waited %.3f ms%s\n", legacy ? "legacy" : "created", ms, h ? "  TIMED OUT" : "");
+    }
     return 0;
 }
